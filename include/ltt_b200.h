@@ -1,0 +1,140 @@
+/* C-ABI of the B200-native layout-conditioned diffusion hot path (libltt_b200.so).
+ *
+ * The reference (LayoutLLM-T2I, /root/reference) is pure Python/PyTorch and has no FFI; the boundary this library
+ * sits behind is the Python duck type described in SURVEY.md section 8(b).  Each entry point names the reference
+ * interface it replaces.  Conventions: plain pointers and sizes only, every pointer is a DEVICE pointer unless it
+ * says "host", the caller owns all I/O buffers, the library owns weights/workspaces, `stream` is a cudaStream_t
+ * (pass torch.cuda.current_stream().cuda_stream), one handle per device, not thread safe, stream ordered.
+ * Return value: 0 on success, negative on error (ltt_last_error() gives the message); nothing throws.
+ *
+ * fp16 = IEEE half.  "NHWC" = [B, H, W, C] with C contiguous; token tensors [B, N, C] are the same thing.
+ */
+#ifndef LTT_B200_H
+#define LTT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ltt_model ltt_model;
+
+enum { LTT_F16 = 0, LTT_F32 = 1 };
+enum { LTT_ACT_NONE = 0, LTT_ACT_SILU = 1, LTT_ACT_GEGLU = 2 };
+
+const char* ltt_last_error(void);
+/* library / build identification: "ltt_b200 <version> sm_100a" */
+const char* ltt_version(void);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Model-level API  (replaces ldm.modules.diffusionmodules.openaimodel.UNetModel + ldm.models.diffusion.plms)
+ * -------------------------------------------------------------------------------------------------------------- */
+
+/* UNetModel.__init__ hyper-parameters (openaimodel.py:235-256; GLIGEN/configs/coco2014.yaml:8-30). */
+typedef struct {
+    int in_channels, out_channels, model_channels;
+    int num_res_blocks;
+    int n_levels;
+    int channel_mult[8];
+    int n_attn_res;
+    int attention_resolutions[8];
+    int num_heads;
+    int context_dim;
+    int grounding_in_dim, grounding_out_dim, fourier_freqs;
+    int max_objs;      /* 30 (txt2img.py:173) */
+} ltt_unet_config;
+
+int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out);
+void ltt_destroy(ltt_model* m);
+
+/* model.load_state_dict (txt2img.py:106): one call per state_dict entry, reference key names and shapes
+ * (SURVEY.md Appendix B); `data` is an fp32 DEVICE or HOST pointer (is_host != 0).  Unknown keys return -5. */
+int ltt_load_param(ltt_model* m, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
+/* Repack everything loaded so far into the device-native fp16 layouts; must precede the first forward.  May be
+ * called again after more ltt_load_param calls (weights changed). */
+int ltt_finalize(ltt_model* m);
+/* UNetModel.restore_first_conv_from_SD (openaimodel.py:393-405): substitute input_blocks.0.0 (weight [Cm,4,3,3],
+ * bias [Cm], fp32 device or host).  Permanent, like the reference. */
+int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int is_host);
+
+/* Per-image conditioning (everything UNetModel.forward derives from the non-x inputs, openaimodel.py:413-446):
+ * context [B,77,ctx], relations [B,R,ctx], boxes [B,max_objs,4], masks [B,max_objs], pos_emb [B,max_objs,in_dim],
+ * all fp32.  `n_grounded` leading batch elements use the given grounding, the rest use the null grounding input
+ * (GroundingNetInput.get_null_input) -- that is how a [cond ; uncond] CFG batch is expressed.  Computes and caches
+ * PositionNet tokens and all step-invariant K/V projections. */
+int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const float* relations, int n_rel,
+                         const float* boxes, const float* masks, const float* pos_emb, int B, int n_grounded,
+                         int H, int W, void* stream);
+
+/* UNetModel.forward (openaimodel.py:413-459) with the cached conditioning: x [B,4,H,W] fp32 NCHW, timesteps [B]
+ * (fp32 values of the integer steps), gate scale as written by set_alpha_scale (txt2img.py:46-50);
+ * eps_out [B,4,H,W] fp32 NCHW (values are fp16-rounded, as the autocast reference returns). */
+int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, float alpha_scale, float* eps_out,
+                     void* stream);
+
+/* PLMSSampler.plms_sampling (plms.py:64-163) for a batch whose conditioning was set with
+ * ltt_set_conditioning(B = 2*Bimg, n_grounded = Bimg) when guidance != 1 (else B = Bimg):
+ * x_inout [Bimg,4,H,W] fp32 start noise -> final latent.  host arrays of length S (index order of the sampler's
+ * tables, i.e. ascending t): timesteps, alphas (ddim_alphas), alphas_prev, sqrt_one_minus_alphas; alpha_sched[S] =
+ * per-iteration gate scale (alpha_generator, txt2img.py:59-93); when it hits 0 the SD first conv (if set via
+ * sd_conv_weight/bias, may be NULL) is substituted as plms.py:86-87 does. */
+int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* timesteps_host,
+                    const float* alphas_host, const float* alphas_prev_host, const float* sqrt_1m_alphas_host,
+                    const float* alpha_sched_host, float guidance, const float* sd_conv_weight,
+                    const float* sd_conv_bias, void* stream);
+
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int64_t ltt_launch_count(const ltt_model* m);
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Operator-level API (the same kernels, exposed one by one for parity tests and profiling)
+ * -------------------------------------------------------------------------------------------------------------- */
+
+/* nn.Linear / 1x1 conv:  out[M,N] = epilogue(a[M,K] . w[N,K]^T).  a, w fp16; K % 64 == 0, N % 8 == 0.
+ * epilogue: y = acc + bias; act (SiLU, or GEGLU: w rows packed by ltt_op_pack_geglu, out has N/2 columns);
+ * if has_gate y *= gate; if res: y += res.  (attention.py:38-65,108-112; openaimodel.py:172-194) */
+int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, const float* bias, int act,
+                  const void* res, int res_dtype, int ldr, float gate, int has_gate, void* out, int out_dtype, int ldo,
+                  void* stream);
+/* [8C, K] fp32 GEGLU projection weight -> fp16 rows interleaved per 128-row tile (64 value rows, 64 gate rows) */
+int ltt_op_pack_geglu(const float* w, int rows, int K, void* out_f16, void* stream);
+/* OIHW fp32 3x3 conv weight [Cout, Cin, 3, 3] -> fp16 [Cout][tap][Cin] */
+int ltt_op_pack_conv3x3(const float* w, int Cout, int Cin, void* out_f16, void* stream);
+/* nn.Conv2d(C, N, 3, padding=1) on NHWC fp16 (openaimodel.py:155-185): out NHWC fp16 [B,H,W,N];
+ * optional per-batch additive vector rowvec [B,N] fp16 (the ResBlock time-embedding add, :220-222) */
+int ltt_op_conv3x3(const void* x, int B, int H, int W, int C, const void* w_packed, int N, const float* bias,
+                   const void* rowvec, void* out, void* stream);
+/* fused q/k/v projection writing attention-ready layouts: q,k [B, rows, heads*dpad] (head padded), vt [B, C, pitch] */
+int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int heads, int dpad, void* q, int rows_q,
+               void* k, int rows_k, void* vt, int pitch_v, void* stream);
+/* softmax(q k^T scale) v  (attention.py:127-141,164-176), out [B, nq, heads*dhead] fp16 */
+int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
+                     int heads, int dhead, int dpad, int nq, int nk, float scale, void* out, int ldo, void* stream);
+/* GroupNorm(32) [+ SiLU] on the channel concat of up to two NHWC fp16 tensors (util.py:211-229, attention.py:78) */
+int ltt_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* gamma,
+                     const float* beta, float eps, int silu, void* out, void* stream);
+/* nn.LayerNorm(C) over rows (fp16 or fp32 in) -> fp16 and/or fp32 out */
+int ltt_op_layernorm(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
+                     void* out16, float* out32, void* stream);
+/* RelationCrossAttention pooling / scatter pieces (attention.py:315-359) */
+int ltt_op_rela_rects(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, void* stream);
+int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, int w, int C, void* feats16, void* stream);
+int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
+                        int mo, int h, int w, int C, float* out, void* stream);
+/* 30 x 10 relation cross-attention core (warp shuffles) */
+int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
+                           float scale, void* out, void* stream);
+/* PositionNet input rows [rows, in_dim + 8*nfreq] fp16 (text_grounding_net.py:26-41, util.py:12-26) */
+int ltt_op_posnet_input(const float* boxes, const float* masks, const float* emb, const float* null_txt,
+                        const float* null_pos, int rows, int in_dim, int nfreq, void* out16, void* stream);
+/* timestep_embedding (util.py:161-181) -> fp16 [B, dim] */
+int ltt_op_timestep_embedding(const float* t, int B, int dim, void* out16, void* stream);
+/* CFG combine + PLMS update (plms.py:110-163); see small_ops.cu plms_update_kernel for `mode` */
+int ltt_op_plms_update(const float* eps_c, const float* eps_u, float guidance, int use_cfg, int mode, const float* x,
+                       float* e_t_out, const float* e_first, const float* old1, const float* old2, const float* old3,
+                       float a_t, float a_prev, float sqrt_1m_at, float* x_out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTT_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of libltt_b200.so (the C-ABI declared in include/ltt_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback.  Import fails loudly when the shared object is
+missing (build it with ``python -c "import __graft_entry__ as g; g.build()"`` or ``layoutllm_t2i_b200/csrc/build.sh``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libltt_b200.so")
+
+
+class LttError(RuntimeError):
+    pass
+
+
+class UNetConfig(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("out_channels", C.c_int), ("model_channels", C.c_int),
+                ("num_res_blocks", C.c_int), ("n_levels", C.c_int), ("channel_mult", C.c_int * 8),
+                ("n_attn_res", C.c_int), ("attention_resolutions", C.c_int * 8), ("num_heads", C.c_int),
+                ("context_dim", C.c_int), ("grounding_in_dim", C.c_int), ("grounding_out_dim", C.c_int),
+                ("fourier_freqs", C.c_int), ("max_objs", C.c_int)]
+
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes); mirrors include/ltt_b200.h one to one
+_SIGS = {
+    "ltt_last_error": (C.c_char_p, []),
+    "ltt_version": (C.c_char_p, []),
+    "ltt_create": (_i, [C.POINTER(UNetConfig), _i, C.POINTER(_vp)]),
+    "ltt_destroy": (None, [_vp]),
+    "ltt_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "ltt_finalize": (_i, [_vp]),
+    "ltt_set_first_conv": (_i, [_vp, _vp, _vp, _i]),
+    "ltt_set_conditioning": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ltt_unet_forward": (_i, [_vp, _vp, _vp, _f, _vp, _vp]),
+    "ltt_plms_sample": (_i, [_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
+                             C.POINTER(_f), _f, _vp, _vp, _vp]),
+    "ltt_launch_count": (_i64, [_vp]),
+    "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
+    "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),
+    "ltt_op_pack_conv3x3": (_i, [_vp, _i, _i, _vp, _vp]),
+    "ltt_op_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ltt_op_qkv": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "ltt_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "ltt_op_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
+    "ltt_op_layernorm": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
+    "ltt_op_rela_rects": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ltt_op_rela_pool": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ltt_op_rela_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ltt_op_small_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "ltt_op_posnet_input": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ltt_op_timestep_embedding": (_i, [_vp, _i, _i, _vp, _vp]),
+    "ltt_op_plms_update": (_i, [_vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _i64, _vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise LttError(f"{LIB_PATH} is missing: the sm_100a extension must be built (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().ltt_last_error().decode(errors="replace")
+        raise LttError(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t) -> C.c_void_p:
+    """Device (or host) pointer of a torch tensor, None -> NULL."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

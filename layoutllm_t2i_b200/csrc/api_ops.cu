@@ -1,0 +1,138 @@
+// Operator-level C-ABI entry points (include/ltt_b200.h): thin argument marshalling onto the kernel launchers.
+#include "../../include/ltt_b200.h"
+#include "ltt_ops.h"
+
+using namespace ltt;
+
+namespace ltt {
+// process-wide split-K scratch for operator-level calls (model handles own theirs)
+static GemmWorkspace g_ws;
+static int g_sms = 0;
+int ensure_global_ws() {
+    if (g_ws.partials) return 0;
+    int dev = 0;
+    LTT_CUDA_OK(cudaGetDevice(&dev));
+    LTT_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    g_ws.partial_bytes = (size_t)64 << 20;
+    g_ws.n_counters = 4096;
+    LTT_CUDA_OK(cudaMalloc(&g_ws.partials, g_ws.partial_bytes));
+    LTT_CUDA_OK(cudaMalloc(&g_ws.counters, g_ws.n_counters * sizeof(int)));
+    LTT_CUDA_OK(cudaMemset(g_ws.counters, 0, g_ws.n_counters * sizeof(int)));
+    return 0;
+}
+const GemmWorkspace& global_ws() { return g_ws; }
+int global_sms() { return g_sms; }
+}  // namespace ltt
+
+extern "C" {
+
+const char* ltt_last_error(void) { return last_error(); }
+const char* ltt_version(void) { return "ltt_b200 0.1 sm_100a"; }
+
+int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, const float* bias, int act,
+                  const void* res, int res_dtype, int ldr, float gate, int has_gate, void* out, int out_dtype, int ldo,
+                  void* stream) {
+    if (int rc = ensure_global_ws()) return rc;
+    GemmProblem p{};
+    p.B = 1; p.H = 1; p.W = M; p.N = N; p.nsrc = 1;
+    p.src[0] = GemmSrc{(const __half*)a, K, lda, 1};
+    p.w = (const __half*)w; p.Ktot = K;
+    p.epi.bias = bias; p.epi.act = act; p.epi.res = res; p.epi.res_dtype = res_dtype; p.epi.ldr = ldr;
+    p.epi.gate = gate; p.epi.has_gate = has_gate; p.epi.out = out; p.epi.out_dtype = out_dtype; p.epi.ldo = ldo;
+    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+}
+
+int ltt_op_pack_geglu(const float* w, int rows, int K, void* out_f16, void* stream) {
+    return pack_rows_launch(w, rows, K, (__half*)out_f16, 0, 1, (cudaStream_t)stream);
+}
+
+int ltt_op_pack_conv3x3(const float* w, int Cout, int Cin, void* out_f16, void* stream) {
+    return pack_conv_launch(w, Cout, Cin, 9, 0, Cin, (__half*)out_f16, 9 * Cin, 0, (cudaStream_t)stream);
+}
+
+int ltt_op_conv3x3(const void* x, int B, int H, int W, int C, const void* w_packed, int N, const float* bias,
+                   const void* rowvec, void* out, void* stream) {
+    if (int rc = ensure_global_ws()) return rc;
+    GemmProblem p{};
+    p.B = B; p.H = H; p.W = W; p.N = N; p.nsrc = 1;
+    p.src[0] = GemmSrc{(const __half*)x, C, C, 9};
+    p.w = (const __half*)w_packed; p.Ktot = 9 * C;
+    p.epi.bias = bias; p.epi.rowvec = (const __half*)rowvec; p.epi.ld_rowvec = N;
+    p.epi.out = out; p.epi.out_dtype = DT_F16; p.epi.ldo = N;
+    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+}
+
+int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int heads, int dpad, void* q, int rows_q,
+               void* k, int rows_k, void* vt, int pitch_v, void* stream) {
+    if (int rc = ensure_global_ws()) return rc;
+    GemmProblem p{};
+    p.B = B; p.H = 1; p.W = tokens; p.N = 3 * C; p.nsrc = 1;
+    p.src[0] = GemmSrc{(const __half*)a, C, C, 1};
+    p.w = (const __half*)w_qkv; p.Ktot = C;
+    p.epi.out_mode = OUT_QKV; p.epi.q = (__half*)q; p.epi.k = (__half*)k; p.epi.vt = (__half*)vt;
+    p.epi.C = C; p.epi.dhead = C / heads; p.epi.dpad = dpad; p.epi.rows_q = rows_q; p.epi.rows_k = rows_k;
+    p.epi.pitch_v = pitch_v; p.epi.tokens = tokens;
+    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+}
+
+int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
+                     int heads, int dhead, int dpad, int nq, int nk, float scale, void* out, int ldo, void* stream) {
+    AttnProblem p{};
+    p.B = B; p.heads = heads; p.dhead = dhead; p.dpad = dpad; p.nq = nq; p.nk = nk;
+    p.q = (const __half*)q; p.rows_q = rows_q; p.k = (const __half*)k; p.rows_k = rows_k;
+    p.vt = (const __half*)vt; p.pitch_v = pitch_v; p.out = (__half*)out; p.ldo = ldo; p.scale = scale;
+    return attn_tc_launch(p, (cudaStream_t)stream);
+}
+
+int ltt_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* gamma,
+                     const float* beta, float eps, int silu, void* out, void* stream) {
+    static double* stats = nullptr;
+    static int cap = 0;
+    if (cap < B) {
+        if (stats) cudaFree(stats);
+        LTT_CUDA_OK(cudaMalloc(&stats, (size_t)B * 64 * sizeof(double)));
+        cap = B;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = gn_stats_launch((const __half*)x0, c0, c0, (const __half*)x1, c1, c1, B, HW, 32, stats, st)) return rc;
+    return gn_apply_launch((const __half*)x0, c0, c0, (const __half*)x1, c1, c1, B, HW, 32, stats, gamma, beta, eps, silu,
+                           (__half*)out, st);
+}
+
+int ltt_op_layernorm(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
+                     void* out16, float* out32, void* stream) {
+    return layernorm_launch(x, x_dtype, M, C, gamma, beta, eps, (__half*)out16, out32, (cudaStream_t)stream);
+}
+
+int ltt_op_rela_rects(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, void* stream) {
+    return rela_rects_launch(boxes, masks, B, mo, h, w, rects, (cudaStream_t)stream);
+}
+int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, int w, int C, void* feats16, void* stream) {
+    return rela_pool_launch(hid, rects, B, mo, h, w, C, (__half*)feats16, (cudaStream_t)stream);
+}
+int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
+                        int mo, int h, int w, int C, float* out, void* stream) {
+    return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+                               (cudaStream_t)stream);
+}
+int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
+                           float scale, void* out, void* stream) {
+    return small_attn_launch((const __half*)q, heads * d, (const __half*)k, (const __half*)v, heads * d, B, nq, nk, heads, d, scale,
+                             (__half*)out, (cudaStream_t)stream);
+}
+int ltt_op_posnet_input(const float* boxes, const float* masks, const float* emb, const float* null_txt,
+                        const float* null_pos, int rows, int in_dim, int nfreq, void* out16, void* stream) {
+    return posnet_input_launch(boxes, masks, emb, null_txt, null_pos, rows, in_dim, nfreq, (__half*)out16,
+                               (cudaStream_t)stream);
+}
+int ltt_op_timestep_embedding(const float* t, int B, int dim, void* out16, void* stream) {
+    return timestep_embed_launch(t, B, dim, (__half*)out16, (cudaStream_t)stream);
+}
+int ltt_op_plms_update(const float* eps_c, const float* eps_u, float guidance, int use_cfg, int mode, const float* x,
+                       float* e_t_out, const float* e_first, const float* old1, const float* old2, const float* old3,
+                       float a_t, float a_prev, float sqrt_1m_at, float* x_out, int64_t n, void* stream) {
+    return plms_update_launch(eps_c, eps_u, guidance, use_cfg, mode, x, e_t_out, e_first, old1, old2, old3, a_t, a_prev,
+                              sqrt_1m_at, x_out, (size_t)n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// Flash-style attention core on tcgen05 for sm_100a: S = Q K^T and O += P V both run on the tensor cores with the
+// S tiles (double buffered) and the O accumulator resident in TMEM; softmax is online in the exp2 domain with a
+// lazy (thresholded) rescale of O, so O is touched by the CUDA cores only when a row maximum jumps.
+//
+// One CTA = 128 query rows of one (batch, head).  warp 0: TMA producer (Q once, K / V^T tiles double buffered),
+// warp 1: tcgen05.mma issuer, warps 2..5: one softmax thread per query row (TMEM lane).  P is written to shared
+// memory in the 128-B-swizzled K-major layout and consumed as the A operand of the PV MMA; V arrives transposed
+// ([C, keys], keys contiguous -- written that way by the QKV projection's epilogue) so it is a K-major B operand.
+// Head dims 40 / 80 / 160 run as K = 48 / 80 / 160 for QK^T (zero padded columns) and N = 48 / 80 / 160 for PV.
+//
+// Replaces the einsum / softmax / einsum triple of the reference's attention modules
+// (/root/reference/GLIGEN/ldm/modules/attention.py:127-141 CrossAttention, :164-176 SelfAttention), which
+// materialise the [B*8, N, N] score matrix.
+#include "ltt_kernels.h"
+#include "ltt_ptx.cuh"
+
+namespace ltt {
+
+constexpr int ATT_THREADS = 192;
+
+struct AttnDeviceArgs {
+    CUtensorMap qmap, kmap, vmap;
+    int nq, nk, dhead, dpad;
+    __half* out;
+    int ldo;
+    float scale_log2;
+};
+
+template <int DPAD, int DV, int BKV>
+struct AttnCfg {
+    static constexpr int NKC = DPAD / 64;           // 64-column chunks of Q / K rows
+    static constexpr int KSTEPS = DV / 16;          // k16 steps of QK^T (d rounded up to 16)
+    static constexpr int NVC = BKV / 64;            // 64-key chunks of a KV tile
+    static constexpr int Q_BYTES = NKC * 128 * 128;
+    static constexpr int K_BYTES = NKC * BKV * 128;
+    static constexpr int V_BYTES = NVC * DV * 128;
+    static constexpr int P_BYTES = NVC * 128 * 128;
+    static constexpr int OFF_K = Q_BYTES;
+    static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+    static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
+    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+    static constexpr int TM_S = 0, TM_O = 2 * BKV;
+};
+
+template <int DPAD, int DV, int BKV>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
+    using C = AttnCfg<DPAD, DV, BKV>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* k_full = bars + 1;        // 2
+    uint64_t* k_empty = bars + 3;       // 2
+    uint64_t* v_full = bars + 5;        // 2
+    uint64_t* v_empty = bars + 7;       // 2
+    uint64_t* s_full = bars + 9;        // 2
+    uint64_t* s_empty = bars + 11;      // 2  (count 128)
+    uint64_t* p_full = bars + 13;       // 1  (count 128)
+    uint64_t* pv_done = bars + 14;      // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+    const int nt = (args.nk + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.qmap);
+        tma_prefetch_desc(&args.kmap);
+        tma_prefetch_desc(&args.vmap);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 128);
+        }
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, C::Q_BYTES);
+            for (int c = 0; c < C::NKC; ++c)
+                tma_load_3d(smem + c * (128 * 128), &args.qmap, q_full, head * DPAD + c * 64, q0, b);
+            for (int j = 0; j < nt; ++j) {
+                const int st = j & 1;
+                const uint32_t par = ((j >> 1) & 1) ^ 1;
+                mbar_wait(&k_empty[st], par);
+                mbar_expect_tx(&k_full[st], C::K_BYTES);
+                for (int c = 0; c < C::NKC; ++c)
+                    tma_load_3d(smem + C::OFF_K + st * C::K_BYTES + c * (BKV * 128), &args.kmap, &k_full[st],
+                                head * DPAD + c * 64, j * BKV, b);
+                mbar_wait(&v_empty[st], par);
+                mbar_expect_tx(&v_full[st], C::V_BYTES);
+                for (int c = 0; c < C::NVC; ++c)
+                    tma_load_3d(smem + C::OFF_V + st * C::V_BYTES + c * (DV * 128), &args.vmap, &v_full[st],
+                                j * BKV + c * 64, head * args.dhead, b);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BKV);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(DV);
+        const uint32_t sq = smem_u32(smem);
+        const uint32_t sk = smem_u32(smem + C::OFF_K);
+        const uint32_t sv = smem_u32(smem + C::OFF_V);
+        const uint32_t sp = smem_u32(smem + C::OFF_P);
+        auto issue_qk = [&](int j) {
+            const int st = j & 1;
+            mbar_wait(&k_full[st], (j >> 1) & 1);
+            if (j >= 2) mbar_wait(&s_empty[st], ((j >> 1) - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                    const uint64_t ad = umma_desc_sw128(sq + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+                    const uint64_t bd = umma_desc_sw128(sk + st * C::K_BYTES + (kk >> 2) * (BKV * 128)) + 2 * (kk & 3);
+                    umma_f16(tmem_base + C::TM_S + st * BKV, ad, bd, idesc_qk, kk != 0);
+                }
+                umma_commit(&k_empty[st]);
+                umma_commit(&s_full[st]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_qk(0);
+        for (int j = 0; j < nt; ++j) {
+            if (j + 1 < nt) issue_qk(j + 1);
+            const int st = j & 1;
+            mbar_wait(&v_full[st], (j >> 1) & 1);
+            mbar_wait(p_full, j & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < BKV / 16; ++kk) {
+                    const uint64_t ad = umma_desc_sw128(sp + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+                    const uint64_t bd = umma_desc_sw128(sv + st * C::V_BYTES + (kk >> 2) * (DV * 128)) + 2 * (kk & 3);
+                    umma_f16(tmem_base + C::TM_O, ad, bd, idesc_pv, (j | kk) != 0);
+                }
+                umma_commit(&v_empty[st]);
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+        uint8_t* sP = smem + C::OFF_P;
+        float m_used = -INFINITY, l = 0.f;
+        const float sc = args.scale_log2;
+        for (int j = 0; j < nt; ++j) {
+            const int st = j & 1;
+            mbar_wait(&s_full[st], (j >> 1) & 1);
+            tc_fence_after();
+            float s[BKV];
+#pragma unroll
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + C::TM_S + st * BKV + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            mbar_arrive(&s_empty[st]);
+            const int kvalid = args.nk - j * BKV;   // >= 1
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < BKV; ++i) {
+                s[i] = (i < kvalid) ? s[i] * sc : -INFINITY;
+                mx = fmaxf(mx, s[i]);
+            }
+            const bool need = mx > m_used + 8.0f;
+            const float m_new = need ? mx : m_used;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {
+                    const float f = need ? exp2f(m_used - m_new) : 1.0f;
+                    l *= f;
+#pragma unroll
+                    for (int c = 0; c < DV; c += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(trow + C::TM_O + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+                        tmem_st16(trow + C::TM_O + c, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            m_used = m_new;
+            float rs = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < BKV / 8; ++c8) {
+                __half2 h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float p0 = exp2f(s[c8 * 8 + 2 * i] - m_used);
+                    const float p1 = exp2f(s[c8 * 8 + 2 * i + 1] - m_used);
+                    rs += p0 + p1;
+                    h[i] = __floats2half2_rn(p0, p1);
+                }
+                const int kc = c8 >> 3, u = c8 & 7;
+                *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
+                    *reinterpret_cast<uint4*>(h);
+            }
+            l += rs;
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (nt - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const bool valid = (q0 + r) < args.nq;
+        __half* orow = args.out + ((size_t)b * args.nq + q0 + r) * args.ldo + head * args.dhead;
+#pragma unroll
+        for (int c = 0; c < DV; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + C::TM_O + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+                const int col = c + h8 * 8;
+                if (valid && col < args.dhead) {
+                    __half2 h[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        h[i] = __floats2half2_rn(__uint_as_float(v[h8 * 8 + 2 * i]) * inv,
+                                                 __uint_as_float(v[h8 * 8 + 2 * i + 1]) * inv);
+                    *reinterpret_cast<uint4*>(orow + col) = *reinterpret_cast<uint4*>(h);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int DPAD, int DV, int BKV>
+static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
+    using C = AttnCfg<DPAD, DV, BKV>;
+    static bool configured = false;
+    if (!configured) {
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        configured = true;
+    }
+    attn_tc_kernel<DPAD, DV, BKV><<<grid, ATT_THREADS, C::TOTAL, stream>>>(a);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
+    AttnDeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    const int rowlen = p.heads * p.dpad;
+    int bkv, dv;
+    if (p.dhead == 40 && p.dpad == 64) { bkv = 128; dv = 48; }
+    else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
+    else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
+    else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
+    else if (p.dhead == 16 && p.dpad == 64) { bkv = 128; dv = 16; }
+    else {
+        set_error("attention: unsupported head dim %d (dpad %d)", p.dhead, p.dpad);
+        return -1;
+    }
+    if (p.nk < 1 || p.nq < 1 || p.pitch_v % 8 != 0) {
+        set_error("attention: bad sizes nq=%d nk=%d pitch_v=%d", p.nq, p.nk, p.pitch_v);
+        return -1;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)rowlen, (uint64_t)p.nq, (uint64_t)p.B};
+        uint64_t str[2] = {(uint64_t)rowlen, (uint64_t)rowlen * p.rows_q};
+        uint32_t box[3] = {64, 128, 1};
+        int rc = make_tmap_f16(&a.qmap, p.q, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)rowlen, (uint64_t)p.nk, (uint64_t)p.B};
+        uint64_t str[2] = {(uint64_t)rowlen, (uint64_t)rowlen * p.rows_k};
+        uint32_t box[3] = {64, (uint32_t)bkv, 1};
+        int rc = make_tmap_f16(&a.kmap, p.k, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const int Cc = p.heads * p.dhead;
+        uint64_t dims[3] = {(uint64_t)p.nk, (uint64_t)Cc, (uint64_t)p.B};
+        uint64_t str[2] = {(uint64_t)p.pitch_v, (uint64_t)p.pitch_v * Cc};
+        uint32_t box[3] = {64, (uint32_t)dv, 1};
+        int rc = make_tmap_f16(&a.vmap, p.vt, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    a.nq = p.nq; a.nk = p.nk; a.dhead = p.dhead; a.dpad = p.dpad;
+    a.out = p.out; a.ldo = p.ldo;
+    a.scale_log2 = p.scale * 1.4426950408889634f;
+    dim3 grid((p.nq + 127) / 128, p.heads, p.B);
+    if (dv == 48) return attn_launch_variant<64, 48, 128>(a, grid, stream);
+    if (dv == 80) return attn_launch_variant<128, 80, 128>(a, grid, stream);
+    if (dv == 160) return attn_launch_variant<192, 160, 64>(a, grid, stream);
+    return attn_launch_variant<64, 16, 128>(a, grid, stream);
+}
+
+}  // namespace ltt

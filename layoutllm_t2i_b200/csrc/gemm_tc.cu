@@ -1,0 +1,509 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * Wp[n, k]      fp16 x fp16 -> fp32 in TMEM
+//
+// One CTA computes a 128 x BN output tile.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
+// tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  A-tiles are fetched by
+// 4-D TMA boxes (64 channels x tw x th x tb pixels = 128 rows) straight out of the NHWC activation; the nine taps of
+// a 3x3 convolution are nine shifted boxes accumulated into the same TMEM tile, padding comes from TMA's
+// out-of-bounds zero fill, so no im2col buffer ever exists.  Channel-concatenated inputs and the ResBlock's 1x1
+// skip convolution are extra A sources appended along K.  gridDim.z > 1 = split-K: partial tiles go to an fp32
+// workspace and the last CTA to arrive (atomic ticket) sums the slabs in fixed order and runs the epilogue.
+//
+// Replaces (reference, /root/reference/GLIGEN/ldm/modules): every nn.Linear / nn.Conv2d on the UNet path --
+// attention.py:108-112,153-157 (q/k/v/out projections), :38-65 (GEGLU feed-forward), :425-433 (proj_in/out),
+// diffusionmodules/openaimodel.py:155-194 (ResBlock convs, emb_layers, skip), :57-114 (Up/Downsample convs).
+#include <cstdarg>
+#include <cstdio>
+
+#include "ltt_kernels.h"
+#include "ltt_ptx.cuh"
+
+namespace ltt {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int GEMM_THREADS = 192;
+
+struct GemmDeviceArgs {
+    CUtensorMap amap[3];
+    CUtensorMap bmap;
+    int nsrc;
+    int taps[3];
+    int kchunks[3];
+    int iters_total;
+    int B, H, W, N;
+    int tw, th, tiles_x, tiles_y;
+    int splits;
+    float* partials;
+    int* counters;
+    GemmEpilogue epi;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers/tmem slot + alignment slack
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+
+struct RowInfo {
+    int m;       // global row
+    int b;       // batch element
+    bool valid;
+};
+
+// Fused epilogue on 8 consecutive output columns [n, n+8) of row `ri` (values = raw fp32 accumulators; for GEGLU
+// v = value half, g = gate half).  Rounding points follow the fp16-autocast reference: each Linear/Conv output is
+// rounded to fp16 before the next elementwise op.
+__device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout,
+                                                float (&v)[8], const float (&g)[8]) {
+    if (!ri.valid || n >= Nout) return;
+    if (e.act == ACT_GEGLU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float val = r16(v[i] + (e.bias ? e.bias[n + i] : 0.f));
+            float gat = r16(g[i] + (e.bias ? e.bias[Nout + n + i] : 0.f));
+            v[i] = r16(val * r16(gelu_erf_f(gat)));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float y = v[i] + (e.bias ? e.bias[n + i] : 0.f);
+            if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
+            if (e.rowvec) y = r16(y + __half2float(e.rowvec[(size_t)ri.b * e.ld_rowvec + n + i]));
+            if (e.act == ACT_SILU) y = r16(silu_f(y));
+            v[i] = y;
+        }
+    }
+    if (e.has_gate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r16(e.gate * v[i]);
+    }
+    if (e.out_mode == OUT_QKV) {
+        const int which = n / e.C + e.qkv_base, c = n % e.C;
+        const int t = ri.m - ri.b * e.tokens;
+        if (which == 2) {
+            __half* dst = e.vt + ((size_t)ri.b * e.C + c) * e.pitch_v + t;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[(size_t)i * e.pitch_v] = __float2half_rn(v[i]);
+        } else {
+            const int head = c / e.dhead, j = c % e.dhead;
+            __half* base = which == 0 ? e.q + ((size_t)ri.b * e.rows_q + t) * (size_t)(e.dpad * (e.C / e.dhead))
+                                      : e.k + ((size_t)ri.b * e.rows_k + t) * (size_t)(e.dpad * (e.C / e.dhead));
+            __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(base + head * e.dpad + j) = *reinterpret_cast<uint4*>(h);
+        }
+        return;
+    }
+    if (e.res) {
+        if (e.res_dtype == DT_F16) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.res) + (size_t)ri.m * e.ldr + n);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 f = __half22float2(rh[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+            }
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + (size_t)ri.m * e.ldr + n);
+            float4 a = rp[0], b4 = rp[1];
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
+        }
+    }
+    if (e.out_dtype == DT_F16) {
+        __half2 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+    } else {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
+        op[0] = make_float4(v[0], v[1], v[2], v[3]);
+        op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
+    using SM = GemmSmem<BN, STAGES>;
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int mt = blockIdx.y;
+    const int tiles_img = args.tiles_x * args.tiles_y;
+    const int tile_b = mt / tiles_img, trem = mt % tiles_img;
+    const int tb = BM / (args.tw * args.th);
+    const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
+
+    // split-K range of this CTA
+    const int per = (args.iters_total + args.splits - 1) / args.splits;
+    const int it0 = blockIdx.z * per;
+    const int it1 = min(args.iters_total, it0 + per);
+    const int niter = it1 - it0;   // host guarantees >= 1 for every z
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < args.nsrc; ++s) tma_prefetch_desc(&args.amap[s]);
+        tma_prefetch_desc(&args.bmap);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // decode (source, tap, chunk) of the first iteration
+            int s = 0, tap = 0, chunk = 0;
+            {
+                int rem = it0;
+                while (s < args.nsrc - 1 && rem >= args.taps[s] * args.kchunks[s]) {
+                    rem -= args.taps[s] * args.kchunks[s];
+                    ++s;
+                }
+                tap = rem / args.kchunks[s];
+                chunk = rem % args.kchunks[s];
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = it0; it < it1; ++it) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+                uint8_t* sa = smem + stage * SM::STAGE_BYTES;
+                int dx = 0, dy = 0;
+                if (args.taps[s] == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap % 3 - 1;
+                }
+                tma_load_4d(sa, &args.amap[s], &full_bar[stage], chunk * BK, x0 + dx, y0 + dy, b0);
+                tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
+                if (++chunk == args.kchunks[s]) {
+                    chunk = 0;
+                    if (++tap == args.taps[s]) {
+                        tap = 0;
+                        ++s;
+                    }
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_f16(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < niter; ++i) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa);
+                const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                umma_commit(&empty_bar[stage]);
+                if (i == niter - 1) umma_commit(acc_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue warps (2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;            // tile row
+        RowInfo ri;
+        {
+            const int pix = args.tw * args.th;
+            const int ib = r / pix, rr = r % pix;
+            const int iy = rr / args.tw, ix = rr % args.tw;
+            const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
+            ri.valid = (b < args.B) && (y < args.H) && (x < args.W);
+            ri.b = b;
+            ri.m = (b * args.H + y) * args.W + x;
+        }
+        const GemmEpilogue& e = args.epi;
+        const bool geglu = e.act == ACT_GEGLU;
+        const int Nout = geglu ? args.N / 2 : args.N;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+
+        bool do_epilogue = true;
+        const float* slab0 = nullptr;
+        if (args.splits > 1) {
+            const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+            float* slab = args.partials + ((size_t)tile_id * args.splits + blockIdx.z) * (size_t)(BM * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) slab[(size_t)(c + i) * BM + r] = __uint_as_float(v[i]);
+            }
+            __threadfence();
+            named_bar_sync(1, 128);
+            if (threadIdx.x == 64) {
+                const int old = atomicAdd(&args.counters[tile_id], 1);
+                const int last = (old == args.splits - 1);
+                if (last) args.counters[tile_id] = 0;   // ready for the next launch / graph replay
+                *flag_slot = last;
+            }
+            named_bar_sync(1, 128);
+            do_epilogue = (*flag_slot != 0);
+            __threadfence();
+            slab0 = args.partials + (size_t)tile_id * args.splits * (size_t)(BM * BN);
+        }
+
+        if (do_epilogue) {
+            // For GEGLU the packed weight rows put, per BN tile, BN/2 value rows followed by their BN/2 gate rows.
+            const int ncols = geglu ? BN / 2 : BN;
+            const int nbase = geglu ? n0 / 2 : n0;
+#pragma unroll 1
+            for (int c = 0; c < ncols; c += 16) {
+                float va[16], ga[16];
+                if (args.splits > 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float acc = 0.f, accg = 0.f;
+                        for (int z = 0; z < args.splits; ++z) {
+                            const float* sl = slab0 + (size_t)z * (BM * BN);
+                            acc += __ldcg(&sl[(size_t)(c + i) * BM + r]);
+                            if (geglu) accg += __ldcg(&sl[(size_t)(BN / 2 + c + i) * BM + r]);
+                        }
+                        va[i] = acc;
+                        ga[i] = accg;
+                    }
+                } else {
+                    uint32_t v[16];
+                    tmem_ld16(trow + c, v);
+                    if (geglu) {
+                        uint32_t g[16];
+                        tmem_ld16(trow + BN / 2 + c, g);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) ga[i] = __uint_as_float(g[i]);
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) va[i] = __uint_as_float(v[i]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v8[8], g8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v8[i] = va[h * 8 + i];
+                        g8[i] = geglu ? ga[h * 8 + i] : 0.f;
+                    }
+                    epilogue_group8(e, ri, nbase + c + h * 8, Nout, v8, g8);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+static char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                  const uint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+        return -3;
+    }
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_elems[i - 1] * 2;
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u base %p",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                  rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+        return -4;
+    }
+    return 0;
+}
+
+static void pick_tile(int B, int H, int W, int* tw, int* th) {
+    // 128 rows = tb images x th rows x tw pixels (powers of two); maximise the fraction of valid rows
+    double best = -1.0;
+    for (int w = 128; w >= 4; w >>= 1) {
+        int h = 128 / w;
+        while (h > 1 && h / 2 >= H) h >>= 1;
+        const int b = 128 / (w * h);
+        const double u = ((double)W / (((W + w - 1) / w) * w)) * ((double)H / (((H + h - 1) / h) * h)) *
+                         ((double)B / (((B + b - 1) / b) * b));
+        if (u > best + 1e-9) {
+            best = u;
+            *tw = w;
+            *th = h;
+        }
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_variant(const GemmDeviceArgs& a, dim3 grid, cudaStream_t stream) {
+    using SM = GemmSmem<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        configured = true;
+    }
+    gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(a);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, cudaStream_t stream) {
+    GemmDeviceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = p.B; a.H = p.H; a.W = p.W; a.N = p.N;
+    a.nsrc = p.nsrc;
+    pick_tile(p.B, p.H, p.W, &a.tw, &a.th);
+    const int tb = BM / (a.tw * a.th);
+    a.tiles_x = (p.W + a.tw - 1) / a.tw;
+    a.tiles_y = (p.H + a.th - 1) / a.th;
+    const int tiles_b = (p.B + tb - 1) / tb;
+    const int mtiles = a.tiles_x * a.tiles_y * tiles_b;
+    int iters = 0, ktot = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+        const GemmSrc& g = p.src[s];
+        if (g.channels % BK != 0 || (g.taps != 1 && g.taps != 9) || g.ld % 8 != 0) {
+            set_error("gemm: bad source %d (channels %d, taps %d, ld %d)", s, g.channels, g.taps, g.ld);
+            return -1;
+        }
+        a.taps[s] = g.taps;
+        a.kchunks[s] = g.channels / BK;
+        iters += g.taps * a.kchunks[s];
+        ktot += g.taps * g.channels;
+        uint64_t dims[4] = {(uint64_t)g.channels, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+        uint64_t str[3] = {(uint64_t)g.ld, (uint64_t)g.ld * p.W, (uint64_t)g.ld * p.W * p.H};
+        uint32_t box[4] = {(uint32_t)BK, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)tb};
+        int rc = make_tmap_f16(&a.amap[s], g.ptr, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    if (ktot != p.Ktot || p.N % 8 != 0) {
+        set_error("gemm: K mismatch (%d vs %d) or N %% 8 (N=%d)", ktot, p.Ktot, p.N);
+        return -1;
+    }
+    a.iters_total = iters;
+    a.epi = p.epi;
+
+    // tile width: keep N tiles exact where possible (320 = 2 x 160), GEGLU needs value|gate halves inside a tile.
+    int BN;
+    const bool geglu = p.epi.act == ACT_GEGLU;
+    if (geglu) BN = 128;
+    else if (p.N % 160 == 0 && p.N % 128 != 0) BN = 160;
+    else if (p.N <= 64) BN = 64;
+    else BN = 128;
+    const int ntiles = (p.N + BN - 1) / BN;
+
+    // split-K when the tile grid cannot fill the machine (small-M, weight-streaming layers)
+    int splits = 1;
+    const int ctas = mtiles * ntiles;
+    if (ctas < num_sms && iters >= 8) {
+        splits = (2 * num_sms + ctas - 1) / ctas;
+        if (splits > iters / 4) splits = iters / 4;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+        // every z must own at least one iteration
+        int per = (iters + splits - 1) / splits;
+        splits = (iters + per - 1) / per;
+        const size_t need = (size_t)ctas * splits * BM * BN * sizeof(float);
+        if (need > ws.partial_bytes || ctas > ws.n_counters) splits = 1;
+    }
+    a.splits = splits;
+    a.partials = ws.partials;
+    a.counters = ws.counters;
+
+    {
+        uint64_t dims[2] = {(uint64_t)p.Ktot, (uint64_t)p.N};
+        uint64_t str[1] = {(uint64_t)p.Ktot};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+        int rc = make_tmap_f16(&a.bmap, p.w, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    dim3 grid(ntiles, mtiles, splits);
+    switch (BN) {
+        case 64: return launch_variant<64, 4>(a, grid, stream);
+        case 128: return launch_variant<128, 3>(a, grid, stream);
+        case 160: return launch_variant<160, 3>(a, grid, stream);
+    }
+    set_error("gemm: no kernel variant for BN=%d", BN);
+    return -1;
+}
+
+}  // namespace ltt

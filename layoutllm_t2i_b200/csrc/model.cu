@@ -1,0 +1,1053 @@
+// Model-level C-ABI: the whole layout-conditioned UNet forward and the PLMS loop as a fixed launch sequence over
+// library-owned fp16 weights and workspaces.
+//
+// Mirrors (reference, /root/reference/GLIGEN/ldm): UNetModel.__init__/forward
+// modules/diffusionmodules/openaimodel.py:235-459, ResBlock :211-231, Up/Downsample :57-114, SpatialTransformer /
+// BasicTransformerBlock / GatedSelfAttentionDense / RelationCrossAttention modules/attention.py:204-446, PositionNet
+// modules/diffusionmodules/text_grounding_net.py:26-43, PLMSSampler models/diffusion/plms.py:64-163.
+//
+// Layout in HBM: activations NHWC fp16 (token tensors [B, N, C] are the same memory), the transformer residual
+// stream switches to fp32 after the relation fusion exactly where CUDA autocast does in the reference; weights are
+// repacked once (ltt_finalize) to K-major fp16 [N, K] matrices in the K order the TMA gather walks.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ltt_b200.h"
+#include "ltt_ops.h"
+
+namespace ltt {
+
+#define RC(expr)                \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc) return _rc;    \
+    } while (0)
+
+struct Param {
+    float* dev = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct Norm { const float* g = nullptr; const float* b = nullptr; };
+struct Lin { __half* w = nullptr; const float* bias = nullptr; int N = 0, K = 0; };
+
+struct ResW {
+    std::string p;
+    int cin = 0, cout = 0;
+    Norm gn1, gn2;
+    Lin conv1, conv2;      // conv2 carries the 1x1 skip columns when has_skip
+    bool has_skip = false;
+    int emb_off = 0;
+};
+
+struct StW {
+    std::string p;
+    int C = 0, heads = 0, d = 0, dpad = 0;
+    Norm gn, ln1, ln2, ln3, f_ln1, f_ln2, r_ln1, r_ln2, r_ln3;
+    Lin proj_in, proj_out, a1_qkv, a1_out, a2_q, a2_kv, a2_out, ff1, ff2;
+    Lin f_linear, f_qkv, f_out, f_ff1, f_ff2;
+    Lin r_q, r_kv, r_out, r_ff1, r_ff2;
+    float f_ta = 0, f_td = 0, r_ta = 0, r_td = 0;   // tanh(alpha)
+    // per-conditioning caches
+    __half *c2_k = nullptr, *c2_vt = nullptr, *fg_k = nullptr, *fg_vt = nullptr, *r_kvbuf = nullptr;
+};
+
+struct ConvW { std::string p; int C = 0; Lin conv; };
+
+enum LayerKind { L_CONV_IN, L_RES, L_ST, L_DOWN, L_UP };
+struct Layer { LayerKind kind; int idx; };
+
+struct Arena {
+    std::vector<void*> ptrs;
+    int alloc(void** out, size_t bytes, bool zero = false) {
+        void* p = nullptr;
+        LTT_CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16));
+        if (zero) LTT_CUDA_OK(cudaMemset(p, 0, bytes ? bytes : 16));
+        ptrs.push_back(p);
+        *out = p;
+        return 0;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+}  // namespace ltt
+
+using namespace ltt;
+
+struct ltt_model {
+    ltt_unet_config cfg;
+    int device = 0, sms = 148;
+    std::map<std::string, Param> params;
+    bool finalized = false;
+    Arena warena;                     // packed weights
+    Arena carena;                     // conditioning + workspaces (rebuilt when the batch geometry changes)
+
+    // plan
+    std::vector<std::vector<Layer>> in_blocks, out_blocks;
+    std::vector<Layer> mid;
+    std::vector<ResW> res;
+    std::vector<StW> st;
+    std::vector<ConvW> downs, ups;
+    int emb_total = 0;
+    Lin te0, te2, emb_all, pn0, pn2, pn4;
+    const float *null_txt = nullptr, *null_pos = nullptr;
+    const float *conv_in_w = nullptr, *conv_in_b = nullptr;
+    float *sd_conv_w = nullptr, *sd_conv_b = nullptr;
+    Norm out_gn;
+    __half* out_w = nullptr;
+    const float* out_b = nullptr;
+    int n_levels = 0;
+    std::vector<int> level_ch;
+
+    // conditioning / workspace state
+    int B = 0, H = 0, W = 0, n_grounded = 0, ctx_len = 0, n_rel = 0;
+    __half *ctx16 = nullptr, *rel16 = nullptr, *objs16 = nullptr;
+    float *boxes_f = nullptr, *masks_f = nullptr, *emb_f = nullptr;
+    std::vector<int*> rects;          // per level
+    std::vector<__half*> skips;
+    std::vector<size_t> skip_elems;
+    __half *act0 = nullptr, *act1 = nullptr, *tnorm = nullptr;
+    __half *xa = nullptr, *xb = nullptr, *xc = nullptr, *ln16 = nullptr, *ao = nullptr, *ffbuf = nullptr;
+    float *hid32 = nullptr, *xe32 = nullptr, *xf32 = nullptr;
+    __half *feats = nullptr, *feats2 = nullptr, *feats3 = nullptr, *featln = nullptr, *featq = nullptr, *featao = nullptr,
+           *featff = nullptr;
+    std::map<int, __half*> qbuf, kbuf;   // keyed by dpad
+    __half* vtbuf = nullptr;
+    int rows_k_max = 0;
+    double* gn_stats = nullptr;
+    __half *temb16 = nullptr, *te_h = nullptr, *semb = nullptr, *ev_all = nullptr;
+    float *x_in = nullptr, *t_in = nullptr, *eps_buf = nullptr;
+    float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
+    GemmWorkspace ws;
+    int64_t launches = 0;
+};
+
+namespace ltt {
+
+// ------------------------------------------------------------------------------------------------------ parameters
+static const Param* find(ltt_model* m, const std::string& key) {
+    auto it = m->params.find(key);
+    if (it == m->params.end()) {
+        set_error("missing parameter '%s' (load_state_dict incomplete)", key.c_str());
+        return nullptr;
+    }
+    return &it->second;
+}
+#define GETP(var, key)                   \
+    const Param* var = find(m, (key));   \
+    if (!var) return -6;
+
+static int pack_linear(ltt_model* m, const std::string& wkey, const char* bkey_or_null, Lin* out, int geglu = 0) {
+    GETP(w, wkey)
+    if (w->shape.size() < 2) {
+        set_error("parameter '%s' is not a matrix", wkey.c_str());
+        return -6;
+    }
+    const int N = (int)w->shape[0];
+    const int K = (int)(w->numel / N);
+    void* p;
+    RC(m->warena.alloc(&p, (size_t)N * K * 2));
+    RC(pack_rows_launch(w->dev, N, K, (__half*)p, 0, geglu, 0));
+    out->w = (__half*)p; out->N = N; out->K = K; out->bias = nullptr;
+    if (bkey_or_null) {
+        GETP(b, std::string(bkey_or_null))
+        out->bias = b->dev;
+    }
+    return 0;
+}
+static int lin(ltt_model* m, const std::string& p, Lin* out, bool bias = true, int geglu = 0) {
+    const std::string bk = p + ".bias";
+    return pack_linear(m, p + ".weight", bias ? bk.c_str() : nullptr, out, geglu);
+}
+static int norm(ltt_model* m, const std::string& p, Norm* n) {
+    GETP(g, p + ".weight")
+    GETP(b, p + ".bias")
+    n->g = g->dev; n->b = b->dev;
+    return 0;
+}
+// concatenate the rows of several [Ci, K] matrices into one packed [sum Ci, K] fp16 matrix
+static int pack_concat(ltt_model* m, const std::vector<std::string>& keys, Lin* out) {
+    int N = 0, K = 0;
+    std::vector<const Param*> ps;
+    for (auto& k : keys) {
+        GETP(w, k)
+        ps.push_back(w);
+        N += (int)w->shape[0];
+        K = (int)(w->numel / w->shape[0]);
+    }
+    void* p;
+    RC(m->warena.alloc(&p, (size_t)N * K * 2));
+    int off = 0;
+    for (auto* w : ps) {
+        RC(pack_rows_launch(w->dev, (int)w->shape[0], K, (__half*)p, off, 0, 0));
+        off += (int)w->shape[0];
+    }
+    out->w = (__half*)p; out->N = N; out->K = K; out->bias = nullptr;
+    return 0;
+}
+static int scalar_tanh(ltt_model* m, const std::string& key, float* out) {
+    GETP(a, key)
+    float v = 0;
+    LTT_CUDA_OK(cudaMemcpy(&v, a->dev, sizeof(float), cudaMemcpyDeviceToHost));
+    *out = tanhf(v);
+    return 0;
+}
+
+static int build_res(ltt_model* m, const std::string& p, int cin, int cout, int c_first) {
+    ResW r;
+    r.p = p; r.cin = cin; r.cout = cout;
+    RC(norm(m, p + ".in_layers.0", &r.gn1));
+    RC(norm(m, p + ".out_layers.0", &r.gn2));
+    {   // conv1 reads the materialised GroupNorm output (one source, all cin channels)
+        GETP(w, p + ".in_layers.2.weight")
+        GETP(b, p + ".in_layers.2.bias")
+        void* q;
+        RC(m->warena.alloc(&q, (size_t)cout * 9 * cin * 2));
+        RC(pack_conv_launch(w->dev, cout, cin, 9, 0, cin, (__half*)q, 9 * cin, 0, 0));
+        r.conv1 = Lin{(__half*)q, b->dev, cout, 9 * cin};
+    }
+    r.has_skip = cin != cout;
+    {
+        GETP(w, p + ".out_layers.3.weight")
+        GETP(b, p + ".out_layers.3.bias")
+        const int K = 9 * cout + (r.has_skip ? cin : 0);
+        void* q;
+        RC(m->warena.alloc(&q, (size_t)cout * K * 2));
+        RC(pack_conv_launch(w->dev, cout, cout, 9, 0, cout, (__half*)q, K, 0, 0));
+        const float* bias = b->dev;
+        if (r.has_skip) {
+            GETP(sw, p + ".skip_connection.weight")
+            GETP(sb, p + ".skip_connection.bias")
+            // skip columns follow the source split of the (possibly concatenated) block input
+            RC(pack_conv_launch(sw->dev, cout, cin, 1, 0, c_first, (__half*)q, K, 9 * cout, 0));
+            if (c_first < cin)
+                RC(pack_conv_launch(sw->dev, cout, cin, 1, c_first, cin - c_first, (__half*)q, K, 9 * cout + c_first, 0));
+            std::vector<float> hb(cout), hs(cout);
+            LTT_CUDA_OK(cudaMemcpy(hb.data(), b->dev, cout * 4, cudaMemcpyDeviceToHost));
+            LTT_CUDA_OK(cudaMemcpy(hs.data(), sb->dev, cout * 4, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < cout; ++i) hb[i] += hs[i];
+            void* cb;
+            RC(m->warena.alloc(&cb, cout * 4));
+            LTT_CUDA_OK(cudaMemcpy(cb, hb.data(), cout * 4, cudaMemcpyHostToDevice));
+            bias = (const float*)cb;
+        }
+        r.conv2 = Lin{(__half*)q, bias, cout, K};
+    }
+    r.emb_off = m->emb_total;
+    m->emb_total += cout;
+    m->res.push_back(r);
+    return 0;
+}
+
+static int dpad_of(int d) { return d <= 64 ? 64 : (d <= 128 ? 128 : 192); }
+
+static int build_st(ltt_model* m, const std::string& p, int C) {
+    StW s;
+    s.p = p; s.C = C; s.heads = m->cfg.num_heads; s.d = C / s.heads; s.dpad = dpad_of(s.d);
+    const std::string t = p + ".transformer_blocks.0";
+    RC(norm(m, p + ".norm", &s.gn));
+    RC(lin(m, p + ".proj_in", &s.proj_in));
+    RC(lin(m, p + ".proj_out", &s.proj_out));
+    RC(norm(m, t + ".norm1", &s.ln1));
+    RC(norm(m, t + ".norm2", &s.ln2));
+    RC(norm(m, t + ".norm3", &s.ln3));
+    RC(pack_concat(m, {t + ".attn1.to_q.weight", t + ".attn1.to_k.weight", t + ".attn1.to_v.weight"}, &s.a1_qkv));
+    RC(lin(m, t + ".attn1.to_out.0", &s.a1_out));
+    RC(lin(m, t + ".attn2.to_q", &s.a2_q, false));
+    RC(pack_concat(m, {t + ".attn2.to_k.weight", t + ".attn2.to_v.weight"}, &s.a2_kv));
+    RC(lin(m, t + ".attn2.to_out.0", &s.a2_out));
+    RC(lin(m, t + ".ff.net.0.proj", &s.ff1, true, 1));
+    RC(lin(m, t + ".ff.net.2", &s.ff2));
+    const std::string f = t + ".fuser";
+    RC(lin(m, f + ".linear", &s.f_linear));
+    RC(norm(m, f + ".norm1", &s.f_ln1));
+    RC(norm(m, f + ".norm2", &s.f_ln2));
+    RC(pack_concat(m, {f + ".attn.to_q.weight", f + ".attn.to_k.weight", f + ".attn.to_v.weight"}, &s.f_qkv));
+    RC(lin(m, f + ".attn.to_out.0", &s.f_out));
+    RC(lin(m, f + ".ff.net.0.proj", &s.f_ff1, true, 1));
+    RC(lin(m, f + ".ff.net.2", &s.f_ff2));
+    RC(scalar_tanh(m, f + ".alpha_attn", &s.f_ta));
+    RC(scalar_tanh(m, f + ".alpha_dense", &s.f_td));
+    const std::string r = t + ".rela_fuse";
+    RC(norm(m, r + ".norm1", &s.r_ln1));
+    RC(norm(m, r + ".norm2", &s.r_ln2));
+    RC(norm(m, r + ".norm3", &s.r_ln3));
+    RC(lin(m, r + ".attn.to_q", &s.r_q, false));
+    RC(pack_concat(m, {r + ".attn.to_k.weight", r + ".attn.to_v.weight"}, &s.r_kv));
+    RC(lin(m, r + ".attn.to_out.0", &s.r_out));
+    RC(lin(m, r + ".ff.net.0.proj", &s.r_ff1, true, 1));
+    RC(lin(m, r + ".ff.net.2", &s.r_ff2));
+    RC(scalar_tanh(m, r + ".alpha_attn", &s.r_ta));
+    RC(scalar_tanh(m, r + ".alpha_dense", &s.r_td));
+    m->st.push_back(s);
+    return 0;
+}
+
+static int build_conv(ltt_model* m, const std::string& p, int C, std::vector<ConvW>* dst) {
+    ConvW c;
+    c.p = p; c.C = C;
+    GETP(w, p + ".weight")
+    GETP(b, p + ".bias")
+    void* q;
+    RC(m->warena.alloc(&q, (size_t)C * 9 * C * 2));
+    RC(pack_conv_launch(w->dev, C, C, 9, 0, C, (__half*)q, 9 * C, 0, 0));
+    c.conv = Lin{(__half*)q, b->dev, C, 9 * C};
+    dst->push_back(c);
+    return 0;
+}
+
+// Static layer list: mirrors the constructor loops of openaimodel.py:299-389.
+static int build_plan(ltt_model* m) {
+    const ltt_unet_config& c = m->cfg;
+    m->warena.release();
+    m->in_blocks.clear(); m->out_blocks.clear(); m->mid.clear();
+    m->res.clear(); m->st.clear(); m->downs.clear(); m->ups.clear();
+    m->emb_total = 0;
+    const int mc = c.model_channels;
+    auto in_attn = [&](int ds) {
+        for (int i = 0; i < c.n_attn_res; ++i)
+            if (c.attention_resolutions[i] == ds) return true;
+        return false;
+    };
+    {
+        GETP(w, "input_blocks.0.0.weight")
+        GETP(b, "input_blocks.0.0.bias")
+        m->conv_in_w = w->dev; m->conv_in_b = b->dev;
+    }
+    m->in_blocks.push_back({Layer{L_CONV_IN, 0}});
+    std::vector<int> chans{mc};
+    int ch = mc, ds = 1, idx = 1;
+    char buf[128];
+    for (int level = 0; level < c.n_levels; ++level) {
+        for (int i = 0; i < c.num_res_blocks; ++i) {
+            std::vector<Layer> ls;
+            snprintf(buf, sizeof(buf), "input_blocks.%d.0", idx);
+            const int cout = c.channel_mult[level] * mc;
+            RC(build_res(m, buf, ch, cout, ch));
+            ls.push_back(Layer{L_RES, (int)m->res.size() - 1});
+            ch = cout;
+            if (in_attn(ds)) {
+                snprintf(buf, sizeof(buf), "input_blocks.%d.1", idx);
+                RC(build_st(m, buf, ch));
+                ls.push_back(Layer{L_ST, (int)m->st.size() - 1});
+            }
+            m->in_blocks.push_back(ls);
+            chans.push_back(ch);
+            ++idx;
+        }
+        if (level != c.n_levels - 1) {
+            snprintf(buf, sizeof(buf), "input_blocks.%d.0.op", idx);
+            RC(build_conv(m, buf, ch, &m->downs));
+            m->in_blocks.push_back({Layer{L_DOWN, (int)m->downs.size() - 1}});
+            chans.push_back(ch);
+            ++idx;
+            ds *= 2;
+        }
+    }
+    RC(build_res(m, "middle_block.0", ch, ch, ch));
+    m->mid.push_back(Layer{L_RES, (int)m->res.size() - 1});
+    RC(build_st(m, "middle_block.1", ch));
+    m->mid.push_back(Layer{L_ST, (int)m->st.size() - 1});
+    RC(build_res(m, "middle_block.2", ch, ch, ch));
+    m->mid.push_back(Layer{L_RES, (int)m->res.size() - 1});
+    int oidx = 0;
+    for (int level = c.n_levels - 1; level >= 0; --level) {
+        for (int i = 0; i <= c.num_res_blocks; ++i) {
+            const int ich = chans.back();
+            chans.pop_back();
+            std::vector<Layer> ls;
+            snprintf(buf, sizeof(buf), "output_blocks.%d.0", oidx);
+            const int cout = c.channel_mult[level] * mc;
+            RC(build_res(m, buf, ch + ich, cout, ch));   // cat([h, skip]): h channels first (openaimodel.py:456)
+            ls.push_back(Layer{L_RES, (int)m->res.size() - 1});
+            ch = cout;
+            int j = 1;
+            if (in_attn(ds)) {
+                snprintf(buf, sizeof(buf), "output_blocks.%d.%d", oidx, j++);
+                RC(build_st(m, buf, ch));
+                ls.push_back(Layer{L_ST, (int)m->st.size() - 1});
+            }
+            if (level && i == c.num_res_blocks) {
+                snprintf(buf, sizeof(buf), "output_blocks.%d.%d.conv", oidx, j);
+                RC(build_conv(m, buf, ch, &m->ups));
+                ls.push_back(Layer{L_UP, (int)m->ups.size() - 1});
+                ds /= 2;
+            }
+            m->out_blocks.push_back(ls);
+            ++oidx;
+        }
+    }
+    RC(norm(m, "out.0", &m->out_gn));
+    {
+        GETP(w, "out.2.weight")
+        GETP(b, "out.2.bias")
+        void* q;
+        RC(m->warena.alloc(&q, (size_t)c.out_channels * 9 * mc * 2));
+        RC(pack_conv_launch(w->dev, c.out_channels, mc, 9, 0, mc, (__half*)q, 9 * mc, 0, 0));
+        m->out_w = (__half*)q; m->out_b = b->dev;
+    }
+    RC(lin(m, "time_embed.0", &m->te0));
+    RC(lin(m, "time_embed.2", &m->te2));
+    {   // all ResBlock emb_layers as one [sum Cout, 4*mc] matrix: one GEMM per forward
+        std::vector<std::string> keys;
+        for (auto& r : m->res) keys.push_back(r.p + ".emb_layers.1.weight");
+        RC(pack_concat(m, keys, &m->emb_all));
+        void* bb;
+        RC(m->warena.alloc(&bb, (size_t)m->emb_total * 4));
+        int off = 0;
+        for (auto& r : m->res) {
+            GETP(b, r.p + ".emb_layers.1.bias")
+            LTT_CUDA_OK(cudaMemcpy((float*)bb + off, b->dev, r.cout * 4, cudaMemcpyDeviceToDevice));
+            off += r.cout;
+        }
+        m->emb_all.bias = (const float*)bb;
+    }
+    RC(lin(m, "position_net.linears.0", &m->pn0));
+    RC(lin(m, "position_net.linears.2", &m->pn2));
+    RC(lin(m, "position_net.linears.4", &m->pn4));
+    {
+        GETP(a, "position_net.null_positive_feature")
+        GETP(b, "position_net.null_position_feature")
+        m->null_txt = a->dev; m->null_pos = b->dev;
+    }
+    LTT_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ launch helpers
+struct Run {
+    ltt_model* m;
+    cudaStream_t st;
+    int B;
+    int gemm(int H, int W, int N, std::initializer_list<GemmSrc> srcs, const Lin& w, const GemmEpilogue& epi, int Bov = -1) {
+        GemmProblem p{};
+        p.B = Bov > 0 ? Bov : B; p.H = H; p.W = W; p.N = N; p.nsrc = 0; p.Ktot = 0;
+        for (auto& s : srcs) {
+            p.src[p.nsrc++] = s;
+            p.Ktot += s.taps * s.channels;
+        }
+        if (p.Ktot != w.K || N != w.N) {
+            set_error("internal: GEMM shape mismatch N=%d/%d K=%d/%d", N, w.N, p.Ktot, w.K);
+            return -7;
+        }
+        p.w = w.w;
+        p.epi = epi;
+        if (!p.epi.bias) p.epi.bias = w.bias;
+        m->launches++;
+        return gemm_tc_launch(p, m->ws, m->sms, st);
+    }
+};
+
+static GemmEpilogue epi_out(void* out, int ldo, int dtype = DT_F16) {
+    GemmEpilogue e;
+    e.out = out; e.ldo = ldo; e.out_dtype = dtype;
+    return e;
+}
+
+static int groupnorm(ltt_model* m, cudaStream_t st, const __half* x0, int c0, const __half* x1, int c1, int B, int HW,
+                     const Norm& n, float eps, int silu, __half* out) {
+    RC(gn_stats_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, st));
+    RC(gn_apply_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, n.g, n.b, eps, silu, out, st));
+    m->launches += 3;
+    return 0;
+}
+
+// ResBlock._forward (openaimodel.py:211-231).  Input = concat(xa[ca], xb[cb]) (cb = 0: single tensor).
+static int run_res(Run& r, const ResW& w, const __half* xa, int ca, const __half* xb, int cb, int H, int W, __half* out) {
+    ltt_model* m = r.m;
+    const int B = r.B, HW = H * W;
+    RC(groupnorm(m, r.st, xa, ca, xb, cb, B, HW, w.gn1, 1e-5f, 1, m->tnorm));
+    GemmEpilogue e1 = epi_out(m->xc, w.cout);    // h (fp16) lives in xc scratch
+    e1.rowvec = m->ev_all + w.emb_off;
+    e1.ld_rowvec = m->emb_total;
+    RC(r.gemm(H, W, w.cout, {GemmSrc{m->tnorm, w.cin, w.cin, 9}}, w.conv1, e1));
+    RC(groupnorm(m, r.st, m->xc, w.cout, nullptr, 0, B, HW, w.gn2, 1e-5f, 1, m->tnorm));
+    GemmEpilogue e2 = epi_out(out, w.cout);
+    if (w.has_skip) {
+        if (cb)
+            RC(r.gemm(H, W, w.cout, {GemmSrc{m->tnorm, w.cout, w.cout, 9}, GemmSrc{xa, ca, ca, 1}, GemmSrc{xb, cb, cb, 1}}, w.conv2, e2));
+        else
+            RC(r.gemm(H, W, w.cout, {GemmSrc{m->tnorm, w.cout, w.cout, 9}, GemmSrc{xa, ca, ca, 1}}, w.conv2, e2));
+    } else {
+        e2.res = xa; e2.res_dtype = DT_F16; e2.ldr = ca;
+        RC(r.gemm(H, W, w.cout, {GemmSrc{m->tnorm, w.cout, w.cout, 9}}, w.conv2, e2));
+    }
+    return 0;
+}
+
+static GemmEpilogue epi_qkv(const StW& s, __half* q, int rows_q, __half* k, int rows_k, __half* vt, int pitch_v, int tokens,
+                            int base) {
+    GemmEpilogue e;
+    e.out_mode = OUT_QKV;
+    e.q = q; e.k = k; e.vt = vt;
+    e.C = s.C; e.dhead = s.d; e.dpad = s.dpad; e.rows_q = rows_q; e.rows_k = rows_k; e.pitch_v = pitch_v;
+    e.tokens = tokens; e.qkv_base = base;
+    return e;
+}
+
+static int attention(ltt_model* m, cudaStream_t st, const StW& s, int B, const __half* q, int rows_q, const __half* k,
+                     int rows_k, const __half* vt, int pitch_v, int nq, int nk, __half* out) {
+    AttnProblem p{};
+    p.B = B; p.heads = s.heads; p.dhead = s.d; p.dpad = s.dpad; p.nq = nq; p.nk = nk;
+    p.q = q; p.rows_q = rows_q; p.k = k; p.rows_k = rows_k; p.vt = vt; p.pitch_v = pitch_v;
+    p.out = out; p.ldo = s.C; p.scale = 1.0f / sqrtf((float)s.d);
+    m->launches++;
+    return attn_tc_launch(p, st);
+}
+
+static int ln(ltt_model* m, cudaStream_t st, const void* x, int dt, int M, int C, const Norm& n, __half* o16, float* o32) {
+    m->launches++;
+    return layernorm_launch(x, dt, M, C, n.g, n.b, 1e-5f, o16, o32, st);
+}
+
+// SpatialTransformer.forward + BasicTransformerBlock._forward (attention.py:394-446)
+static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, float alpha_scale, __half* out) {
+    ltt_model* m = r.m;
+    cudaStream_t st = r.st;
+    const int B = r.B, N = H * W, C = s.C, M = B * N;
+    const int mo = m->cfg.max_objs;
+    const int rows_k = m->rows_k_max, pitch_v = m->rows_k_max;
+    __half* qb = m->qbuf[s.dpad];
+    __half* kb = m->kbuf[s.dpad];
+    // GroupNorm (eps 1e-6) -> proj_in
+    RC(groupnorm(m, st, x_in, C, nullptr, 0, B, N, s.gn, 1e-6f, 0, m->tnorm));
+    RC(r.gemm(H, W, C, {GemmSrc{m->tnorm, C, C, 1}}, s.proj_in, epi_out(m->xa, C)));
+    // attn1
+    RC(ln(m, st, m->xa, DT_F16, M, C, s.ln1, m->ln16, nullptr));
+    RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.a1_qkv, epi_qkv(s, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, 0)));
+    RC(attention(m, st, s, B, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, N, m->ao));
+    {
+        GemmEpilogue e = epi_out(m->xb, C);
+        e.res = m->xa; e.ldr = C;
+        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a1_out, e));
+    }
+    __half* x16 = m->xb;   // fp16 stream after attn1 (+ fuser)
+    if (alpha_scale != 0.0f) {
+        // GatedSelfAttentionDense (attention.py:226-234): visual queries only, 30 cached grounding K/V rows appended
+        RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
+        RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_qkv, epi_qkv(s, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, 0)));
+        const int rowlen = s.heads * s.dpad;
+        RC(copy2d_launch(s.fg_k, (size_t)mo * rowlen, rowlen, kb + (size_t)N * rowlen, (size_t)rows_k * rowlen, rowlen, B, mo, rowlen, st));
+        RC(copy2d_launch(s.fg_vt, (size_t)C * 32, 32, m->vtbuf + N, (size_t)C * pitch_v, pitch_v, B, C, mo, st));
+        m->launches += 2;
+        RC(attention(m, st, s, B, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, N + mo, m->ao));
+        {
+            GemmEpilogue e = epi_out(m->xa, C);
+            e.res = m->xb; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_ta;
+            RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.f_out, e));
+        }
+        RC(ln(m, st, m->xa, DT_F16, M, C, s.f_ln2, m->ln16, nullptr));
+        {
+            GemmEpilogue e = epi_out(m->ffbuf, 4 * C);
+            e.act = ACT_GEGLU;
+            RC(r.gemm(H, W, 8 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_ff1, e));
+        }
+        {
+            GemmEpilogue e = epi_out(m->xb, C);
+            e.res = m->xa; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_td;
+            RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.f_ff2, e));
+        }
+        x16 = m->xb;
+    }
+    // RelationCrossAttention (attention.py:315-359) + the caller's (out + x) / 2 (:398)
+    RC(ln(m, st, x16, DT_F16, M, C, s.r_ln3, nullptr, m->hid32));
+    const int ng = m->n_grounded;
+    const __half* feats_final = nullptr;
+    if (ng > 0) {
+        RC(rela_pool_launch(m->hid32, m->rects[level], ng, mo, H, W, C, m->feats, st));
+        m->launches++;
+        const int R = ng * mo;
+        RC(ln(m, st, m->feats, DT_F16, R, C, s.r_ln1, m->featln, nullptr));
+        RC(r.gemm(1, R, C, {GemmSrc{m->featln, C, C, 1}}, s.r_q, epi_out(m->featq, C), 1));
+        RC(small_attn_launch(m->featq, C, s.r_kvbuf, s.r_kvbuf + C, 2 * C, ng, mo, m->n_rel, s.heads, s.d,
+                             1.0f / sqrtf((float)s.d), m->featao, st));
+        m->launches++;
+        {
+            GemmEpilogue e = epi_out(m->feats2, C);
+            e.res = m->feats; e.ldr = C; e.has_gate = 1; e.gate = s.r_ta;
+            RC(r.gemm(1, R, C, {GemmSrc{m->featao, C, C, 1}}, s.r_out, e, 1));
+        }
+        RC(ln(m, st, m->feats2, DT_F16, R, C, s.r_ln2, m->featln, nullptr));
+        {
+            GemmEpilogue e = epi_out(m->featff, 4 * C);
+            e.act = ACT_GEGLU;
+            RC(r.gemm(1, R, 8 * C, {GemmSrc{m->featln, C, C, 1}}, s.r_ff1, e, 1));
+        }
+        {
+            GemmEpilogue e = epi_out(m->feats3, C);
+            e.res = m->feats2; e.ldr = C; e.has_gate = 1; e.gate = s.r_td;
+            RC(r.gemm(1, R, C, {GemmSrc{m->featff, 4 * C, 4 * C, 1}}, s.r_ff2, e, 1));
+        }
+        feats_final = m->feats3;
+    }
+    RC(rela_scatter_launch(m->hid32, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, st));
+    m->launches++;
+    // attn2 over the cached text K/V
+    RC(ln(m, st, m->xe32, DT_F32, M, C, s.ln2, m->ln16, nullptr));
+    RC(r.gemm(H, W, C, {GemmSrc{m->ln16, C, C, 1}}, s.a2_q, epi_qkv(s, qb, N, nullptr, 0, nullptr, 0, N, 0)));
+    RC(attention(m, st, s, B, qb, N, s.c2_k, m->ctx_len, s.c2_vt, 128, N, m->ctx_len, m->ao));
+    {
+        GemmEpilogue e = epi_out(m->xf32, C, DT_F32);
+        e.res = m->xe32; e.res_dtype = DT_F32; e.ldr = C;
+        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a2_out, e));
+    }
+    // ff
+    RC(ln(m, st, m->xf32, DT_F32, M, C, s.ln3, m->ln16, nullptr));
+    {
+        GemmEpilogue e = epi_out(m->ffbuf, 4 * C);
+        e.act = ACT_GEGLU;
+        RC(r.gemm(H, W, 8 * C, {GemmSrc{m->ln16, C, C, 1}}, s.ff1, e));
+    }
+    {   // the fp32 stream is consumed only by proj_out, whose input autocast rounds to fp16
+        GemmEpilogue e = epi_out(m->xa, C);
+        e.res = m->xf32; e.res_dtype = DT_F32; e.ldr = C;
+        RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.ff2, e));
+    }
+    {
+        GemmEpilogue e = epi_out(out, C);
+        e.res = x_in; e.ldr = C;
+        RC(r.gemm(H, W, C, {GemmSrc{m->xa, C, C, 1}}, s.proj_out, e));
+    }
+    return 0;
+}
+
+static int forward_impl(ltt_model* m, const float* x, const float* t, float alpha_scale, float* eps_out, cudaStream_t st) {
+    if (!m->finalized || m->B == 0) {
+        set_error("ltt_unet_forward: call ltt_finalize and ltt_set_conditioning first");
+        return -8;
+    }
+    const ltt_unet_config& c = m->cfg;
+    const int B = m->B, mc = c.model_channels;
+    Run r{m, st, B};
+    // time embedding -> SiLU(emb) -> all emb_layers at once
+    RC(timestep_embed_launch(t, B, mc, m->temb16, st));
+    m->launches++;
+    {
+        GemmEpilogue e = epi_out(m->te_h, 4 * mc);
+        e.act = ACT_SILU;
+        RC(r.gemm(1, B, 4 * mc, {GemmSrc{m->temb16, mc, mc, 1}}, m->te0, e, 1));
+        GemmEpilogue e2 = epi_out(m->semb, 4 * mc);
+        e2.act = ACT_SILU;
+        RC(r.gemm(1, B, 4 * mc, {GemmSrc{m->te_h, 4 * mc, 4 * mc, 1}}, m->te2, e2, 1));
+        RC(r.gemm(1, B, m->emb_total, {GemmSrc{m->semb, 4 * mc, 4 * mc, 1}}, m->emb_all, epi_out(m->ev_all, m->emb_total), 1));
+    }
+    int H = m->H, W = m->W, level = 0, ch = mc;
+    __half* cur = nullptr;
+    std::vector<int> skip_ch, skip_h, skip_w;
+    int si = 0;
+    auto other = [&](const __half* p) { return p == m->act0 ? m->act1 : m->act0; };
+    auto run_layers = [&](const std::vector<Layer>& ls, const __half* in_a, int ca, const __half* in_b, int cb,
+                          __half* final_out, __half** result) -> int {
+        const __half* a = in_a;
+        int cha = ca;
+        const __half* b = in_b;
+        int chb = cb;
+        for (size_t i = 0; i < ls.size(); ++i) {
+            const bool last = i + 1 == ls.size();
+            __half* dst = (last && final_out) ? final_out : other(a);
+            if (dst == a) dst = other(a);
+            const Layer& L = ls[i];
+            if (L.kind == L_CONV_IN) {
+                RC(conv_in_launch(x, m->sd_conv_w ? m->sd_conv_w : m->conv_in_w, m->sd_conv_w ? m->sd_conv_b : m->conv_in_b,
+                                  B, c.in_channels, H, W, mc, dst, st));
+                m->launches++;
+                cha = mc;
+            } else if (L.kind == L_RES) {
+                const ResW& w = m->res[L.idx];
+                RC(run_res(r, w, a, cha, b, chb, H, W, dst));
+                cha = w.cout;
+            } else if (L.kind == L_ST) {
+                RC(run_st(r, m->st[L.idx], a, H, W, level, alpha_scale, dst));
+            } else if (L.kind == L_DOWN) {
+                const ConvW& w = m->downs[L.idx];
+                RC(im2col_s2_launch(a, m->tnorm, B, H, W, w.C, st));
+                m->launches++;
+                H /= 2; W /= 2; ++level;
+                RC(r.gemm(H, W, w.C, {GemmSrc{m->tnorm, 9 * w.C, 9 * w.C, 1}}, w.conv, epi_out(dst, w.C)));
+            } else if (L.kind == L_UP) {
+                const ConvW& w = m->ups[L.idx];
+                RC(upsample2x_launch(a, m->tnorm, B, H, W, w.C, st));
+                m->launches++;
+                H *= 2; W *= 2; --level;
+                RC(r.gemm(H, W, w.C, {GemmSrc{m->tnorm, w.C, w.C, 9}}, w.conv, epi_out(dst, w.C)));
+            }
+            a = dst; b = nullptr; chb = 0;
+        }
+        *result = const_cast<__half*>(a);
+        ch = cha;
+        return 0;
+    };
+    for (auto& ls : m->in_blocks) {
+        __half* res_ptr;
+        RC(run_layers(ls, cur, ch, nullptr, 0, m->skips[si], &res_ptr));
+        cur = res_ptr;
+        skip_ch.push_back(ch); skip_h.push_back(H); skip_w.push_back(W);
+        ++si;
+    }
+    {
+        __half* res_ptr;
+        RC(run_layers(m->mid, cur, ch, nullptr, 0, nullptr, &res_ptr));
+        cur = res_ptr;
+    }
+    for (auto& ls : m->out_blocks) {
+        --si;
+        __half* res_ptr;
+        RC(run_layers(ls, cur, ch, m->skips[si], skip_ch[si], nullptr, &res_ptr));
+        cur = res_ptr;
+    }
+    RC(groupnorm(m, st, cur, ch, nullptr, 0, B, H * W, m->out_gn, 1e-5f, 1, m->tnorm));
+    RC(conv_out_launch(m->tnorm, m->out_w, m->out_b, B, H, W, mc, c.out_channels, eps_out, st));
+    m->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ conditioning
+static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n_rel) {
+    m->carena.release();
+    m->qbuf.clear(); m->kbuf.clear(); m->rects.clear(); m->skips.clear();
+    const ltt_unet_config& c = m->cfg;
+    const int mc = c.model_channels, mo = c.max_objs;
+    m->B = B; m->H = H; m->W = W; m->ctx_len = ctx_len; m->n_rel = n_rel;
+    auto A = [&](auto** p, size_t bytes, bool zero = false) { return m->carena.alloc((void**)p, bytes, zero); };
+    // walk the plan for sizes
+    size_t max_act = 0, max_norm = 0, max_tok = 0, max_ff = 0, max_featff = 0;
+    int maxC = 0;
+    {
+        int h = H, w = W, ch = mc;
+        std::vector<int> sch;
+        auto visit = [&](const std::vector<Layer>& ls, int extra) {
+            int cin_extra = extra;
+            for (auto& L : ls) {
+                if (L.kind == L_CONV_IN) ch = mc;
+                else if (L.kind == L_RES) {
+                    const ResW& r = m->res[L.idx];
+                    max_norm = std::max(max_norm, (size_t)B * h * w * std::max(r.cin, r.cout));
+                    ch = r.cout;
+                    cin_extra = 0;
+                } else if (L.kind == L_ST) {
+                    const StW& s = m->st[L.idx];
+                    max_tok = std::max(max_tok, (size_t)B * h * w * s.C);
+                    max_ff = std::max(max_ff, (size_t)B * h * w * 4 * s.C);
+                    max_norm = std::max(max_norm, (size_t)B * h * w * s.C);
+                    max_featff = std::max(max_featff, (size_t)B * mo * 4 * s.C);
+                    maxC = std::max(maxC, s.C);
+                } else if (L.kind == L_DOWN) {
+                    max_norm = std::max(max_norm, (size_t)B * (h / 2) * (w / 2) * 9 * ch);
+                    h /= 2; w /= 2;
+                } else if (L.kind == L_UP) {
+                    h *= 2; w *= 2;
+                    max_norm = std::max(max_norm, (size_t)B * h * w * ch);
+                }
+                max_act = std::max(max_act, (size_t)B * h * w * ch);
+            }
+            (void)cin_extra;
+        };
+        for (auto& ls : m->in_blocks) {
+            visit(ls, 0);
+            __half* s;
+            RC(A(&s, (size_t)B * h * w * ch * 2));
+            m->skips.push_back(s);
+        }
+        visit(m->mid, 0);
+        for (auto& ls : m->out_blocks) visit(ls, 0);
+    }
+    RC(A(&m->act0, max_act * 2));
+    RC(A(&m->act1, max_act * 2));
+    RC(A(&m->tnorm, max_norm * 2));
+    RC(A(&m->xa, max_tok * 2));
+    RC(A(&m->xb, max_tok * 2));
+    RC(A(&m->xc, std::max(max_tok, max_act) * 2));
+    RC(A(&m->ln16, max_tok * 2));
+    RC(A(&m->ao, max_tok * 2));
+    RC(A(&m->ffbuf, max_ff * 2));
+    RC(A(&m->hid32, max_tok * 4));
+    RC(A(&m->xe32, max_tok * 4));
+    RC(A(&m->xf32, max_tok * 4));
+    const size_t fe = (size_t)B * mo * maxC;
+    RC(A(&m->feats, fe * 2)); RC(A(&m->feats2, fe * 2)); RC(A(&m->feats3, fe * 2));
+    RC(A(&m->featln, fe * 2)); RC(A(&m->featq, fe * 2)); RC(A(&m->featao, fe * 2));
+    RC(A(&m->featff, max_featff * 2));
+    // attention operand buffers: q/k per head padding (pad columns stay zero for ever), one V^T buffer
+    m->rows_k_max = (H * W + mo + 63) / 64 * 64;
+    size_t max_vt = 0;
+    for (auto& s : m->st) {
+        if (!m->qbuf.count(s.dpad)) {
+            __half *q, *k;
+            RC(A(&q, (size_t)B * H * W * s.heads * s.dpad * 2, true));
+            RC(A(&k, (size_t)B * m->rows_k_max * s.heads * s.dpad * 2, true));
+            m->qbuf[s.dpad] = q; m->kbuf[s.dpad] = k;
+        }
+        max_vt = std::max(max_vt, (size_t)B * s.C * m->rows_k_max);
+    }
+    RC(A(&m->vtbuf, max_vt * 2, true));
+    RC(A(&m->gn_stats, (size_t)B * 64 * sizeof(double)));
+    RC(A(&m->temb16, (size_t)B * mc * 2));
+    RC(A(&m->te_h, (size_t)B * 4 * mc * 2));
+    RC(A(&m->semb, (size_t)B * 4 * mc * 2));
+    RC(A(&m->ev_all, (size_t)B * m->emb_total * 2));
+    const size_t xin = (size_t)B * c.in_channels * H * W, xout = (size_t)B * c.out_channels * H * W;
+    RC(A(&m->x_in, xin * 4)); RC(A(&m->t_in, B * 4)); RC(A(&m->eps_buf, xout * 4));
+    RC(A(&m->pl_x, xin * 4)); RC(A(&m->pl_xsave, xin * 4));
+    for (int i = 0; i < 4; ++i) RC(A(&m->pl_e[i], xout * 4));
+    m->ws.partial_bytes = (size_t)96 << 20;
+    m->ws.n_counters = 8192;
+    RC(A(&m->ws.partials, m->ws.partial_bytes));
+    RC(A(&m->ws.counters, m->ws.n_counters * sizeof(int), true));
+    // conditioning tensors
+    RC(A(&m->ctx16, (size_t)B * ctx_len * c.context_dim * 2));
+    RC(A(&m->rel16, (size_t)B * n_rel * c.context_dim * 2));
+    RC(A(&m->objs16, (size_t)B * mo * c.grounding_out_dim * 2));
+    RC(A(&m->boxes_f, (size_t)B * mo * 4 * 4, true));
+    RC(A(&m->masks_f, (size_t)B * mo * 4, true));
+    RC(A(&m->emb_f, (size_t)B * mo * c.grounding_in_dim * 4, true));
+    for (int l = 0; l < c.n_levels; ++l) {
+        int* rc_;
+        RC(A(&rc_, (size_t)B * mo * 5 * sizeof(int), true));
+        m->rects.push_back(rc_);
+    }
+    for (auto& s : m->st) {
+        const int rowlen = s.heads * s.dpad;
+        RC(A(&s.c2_k, (size_t)B * ctx_len * rowlen * 2, true));
+        RC(A(&s.c2_vt, (size_t)B * s.C * 128 * 2, true));
+        RC(A(&s.fg_k, (size_t)B * mo * rowlen * 2, true));
+        RC(A(&s.fg_vt, (size_t)B * s.C * 32 * 2, true));
+        RC(A(&s.r_kvbuf, (size_t)B * n_rel * 2 * s.C * 2, true));
+    }
+    return 0;
+}
+
+}  // namespace ltt
+
+// =================================================================================================== C-ABI
+extern "C" {
+
+int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
+    if (!cfg || !out) {
+        set_error("ltt_create: null argument");
+        return -1;
+    }
+    if (cfg->n_levels < 1 || cfg->n_levels > 8 || cfg->model_channels % 64 || cfg->num_heads < 1 || cfg->context_dim % 64 ||
+        cfg->max_objs > 32 || cfg->max_objs < 1 || cfg->out_channels > 4 || cfg->grounding_in_dim % 64 ||
+        (cfg->grounding_in_dim + 8 * cfg->fourier_freqs) % 64 || cfg->grounding_out_dim != cfg->context_dim) {
+        set_error("ltt_create: unsupported UNet configuration");
+        return -1;
+    }
+    LTT_CUDA_OK(cudaSetDevice(device));
+    ltt_model* m = new ltt_model();
+    m->cfg = *cfg;
+    m->device = device;
+    LTT_CUDA_OK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device));
+    *out = m;
+    return 0;
+}
+
+void ltt_destroy(ltt_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    m->warena.release();
+    m->carena.release();
+    for (auto& kv : m->params) cudaFree(kv.second.dev);
+    if (m->sd_conv_w) cudaFree(m->sd_conv_w);
+    if (m->sd_conv_b) cudaFree(m->sd_conv_b);
+    delete m;
+}
+
+int ltt_load_param(ltt_model* m, const char* key, const float* data, const int64_t* shape, int ndim, int is_host) {
+    if (!m || !key || !data) {
+        set_error("ltt_load_param: null argument");
+        return -1;
+    }
+    Param& p = m->params[key];
+    size_t n = 1;
+    p.shape.assign(shape, shape + ndim);
+    for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+    if (p.dev && p.numel != n) {
+        cudaFree(p.dev);
+        p.dev = nullptr;
+    }
+    if (!p.dev) LTT_CUDA_OK(cudaMalloc(&p.dev, n * sizeof(float)));
+    p.numel = n;
+    LTT_CUDA_OK(cudaMemcpy(p.dev, data, n * sizeof(float), is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    m->finalized = false;
+    return 0;
+}
+
+int ltt_finalize(ltt_model* m) {
+    if (!m) return -1;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    RC(build_plan(m));
+    m->finalized = true;
+    m->B = 0;   // conditioning caches depend on the packed weights
+    return 0;
+}
+
+int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int is_host) {
+    if (!m) return -1;
+    const size_t nw = (size_t)m->cfg.model_channels * m->cfg.in_channels * 9, nb = m->cfg.model_channels;
+    if (!m->sd_conv_w) {
+        LTT_CUDA_OK(cudaMalloc(&m->sd_conv_w, nw * 4));
+        LTT_CUDA_OK(cudaMalloc(&m->sd_conv_b, nb * 4));
+    }
+    const cudaMemcpyKind k = is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    LTT_CUDA_OK(cudaMemcpy(m->sd_conv_w, weight, nw * 4, k));
+    LTT_CUDA_OK(cudaMemcpy(m->sd_conv_b, bias, nb * 4, k));
+    return 0;
+}
+
+int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const float* relations, int n_rel,
+                         const float* boxes, const float* masks, const float* pos_emb, int B, int n_grounded,
+                         int H, int W, void* stream) {
+    if (!m || !m->finalized) {
+        set_error("ltt_set_conditioning: model not finalized");
+        return -8;
+    }
+    const ltt_unet_config& c = m->cfg;
+    if (ctx_len > 128 || ctx_len < 1 || n_rel < 1 || n_rel > 32 || n_grounded > B || B < 1 ||
+        (H % (1 << (c.n_levels - 1))) || (W % (1 << (c.n_levels - 1)))) {
+        set_error("ltt_set_conditioning: unsupported sizes (ctx_len %d n_rel %d B %d H %d W %d)", ctx_len, n_rel, B, H, W);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    if (B != m->B || H != m->H || W != m->W || ctx_len != m->ctx_len || n_rel != m->n_rel) {
+        LTT_CUDA_OK(cudaDeviceSynchronize());
+        RC(setup_workspace(m, B, H, W, ctx_len, n_rel));
+    }
+    m->n_grounded = n_grounded;
+    const int mo = c.max_objs, cd = c.context_dim;
+    RC(cast_f32_f16_launch(context, m->ctx16, (size_t)B * ctx_len * cd, st));
+    RC(cast_f32_f16_launch(relations, m->rel16, (size_t)B * n_rel * cd, st));
+    LTT_CUDA_OK(cudaMemsetAsync(m->boxes_f, 0, (size_t)B * mo * 16, st));
+    LTT_CUDA_OK(cudaMemsetAsync(m->masks_f, 0, (size_t)B * mo * 4, st));
+    LTT_CUDA_OK(cudaMemsetAsync(m->emb_f, 0, (size_t)B * mo * c.grounding_in_dim * 4, st));
+    if (n_grounded > 0) {
+        LTT_CUDA_OK(cudaMemcpyAsync(m->boxes_f, boxes, (size_t)n_grounded * mo * 16, cudaMemcpyDeviceToDevice, st));
+        LTT_CUDA_OK(cudaMemcpyAsync(m->masks_f, masks, (size_t)n_grounded * mo * 4, cudaMemcpyDeviceToDevice, st));
+        LTT_CUDA_OK(cudaMemcpyAsync(m->emb_f, pos_emb, (size_t)n_grounded * mo * c.grounding_in_dim * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    Run r{m, st, B};
+    // PositionNet (text_grounding_net.py:26-43): scratch rows live in ffbuf / ln16
+    const int R = B * mo, pin = c.grounding_in_dim + 8 * c.fourier_freqs;
+    __half* pin16 = m->ffbuf;
+    __half* h1 = m->ln16;
+    __half* h2 = m->ao;
+    RC(posnet_input_launch(m->boxes_f, m->masks_f, m->emb_f, m->null_txt, m->null_pos, R, c.grounding_in_dim, c.fourier_freqs, pin16, st));
+    {
+        GemmEpilogue e = epi_out(h1, 512);
+        e.act = ACT_SILU;
+        RC(r.gemm(1, R, 512, {GemmSrc{pin16, pin, pin, 1}}, m->pn0, e, 1));
+        GemmEpilogue e2 = epi_out(h2, 512);
+        e2.act = ACT_SILU;
+        RC(r.gemm(1, R, 512, {GemmSrc{h1, 512, 512, 1}}, m->pn2, e2, 1));
+        RC(r.gemm(1, R, c.grounding_out_dim, {GemmSrc{h2, 512, 512, 1}}, m->pn4, epi_out(m->objs16, c.grounding_out_dim), 1));
+    }
+    int h = H, w = W;
+    for (int l = 0; l < c.n_levels; ++l) {
+        RC(rela_rects_launch(m->boxes_f, m->masks_f, B, mo, h, w, m->rects[l], st));
+        h /= 2; w /= 2;
+    }
+    for (auto& s : m->st) {
+        const int C = s.C;
+        // attn2 K/V of the text context (attention.py:122-143)
+        {
+            GemmEpilogue e = epi_qkv(s, nullptr, 0, s.c2_k, ctx_len, s.c2_vt, 128, ctx_len, 1);
+            RC(r.gemm(1, ctx_len, 2 * C, {GemmSrc{m->ctx16, cd, cd, 1}}, s.a2_kv, e));
+        }
+        // fuser: linear(objs) -> LN1 -> K/V rows of the 30 grounding tokens (attention.py:226-230)
+        RC(r.gemm(1, R, C, {GemmSrc{m->objs16, cd, cd, 1}}, s.f_linear, epi_out(h1, C), 1));
+        RC(ln(m, st, h1, DT_F16, R, C, s.f_ln1, h2, nullptr));
+        {
+            Lin kv = s.f_qkv;
+            kv.w = s.f_qkv.w + (size_t)C * C; kv.N = 2 * C;
+            GemmEpilogue e = epi_qkv(s, nullptr, 0, s.fg_k, mo, s.fg_vt, 32, mo, 1);
+            RC(r.gemm(1, mo, 2 * C, {GemmSrc{h2, C, C, 1}}, kv, e));
+        }
+        // relation K/V (attention.py:348-349)
+        RC(r.gemm(1, B * n_rel, 2 * C, {GemmSrc{m->rel16, cd, cd, 1}}, s.r_kv, epi_out(s.r_kvbuf, 2 * C), 1));
+    }
+    return 0;
+}
+
+int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, float alpha_scale, float* eps_out,
+                     void* stream) {
+    if (!m) return -1;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    return forward_impl(m, x, timesteps, alpha_scale, eps_out, (cudaStream_t)stream);
+}
+
+int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* timesteps_host,
+                    const float* alphas_host, const float* alphas_prev_host, const float* sqrt_1m_alphas_host,
+                    const float* alpha_sched_host, float guidance, const float* sd_conv_weight,
+                    const float* sd_conv_bias, void* stream) {
+    if (!m || !m->finalized || m->B == 0) {
+        set_error("ltt_plms_sample: model not ready");
+        return -8;
+    }
+    const bool cfg = guidance != 1.0f;
+    if (m->B != (cfg ? 2 * Bimg : Bimg)) {
+        set_error("ltt_plms_sample: conditioning batch %d does not match Bimg %d (guidance %g)", m->B, Bimg, guidance);
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    const ltt_unet_config& c = m->cfg;
+    const size_t n = (size_t)Bimg * c.in_channels * m->H * m->W;
+    std::vector<float> tvals(m->B);
+    auto eval = [&](const float* x, int tval) -> int {
+        // [cond ; uncond] batch of the same latent
+        LTT_CUDA_OK(cudaMemcpyAsync(m->x_in, x, n * 4, cudaMemcpyDeviceToDevice, st));
+        if (cfg) LTT_CUDA_OK(cudaMemcpyAsync(m->x_in + n, x, n * 4, cudaMemcpyDeviceToDevice, st));
+        for (auto& v : tvals) v = (float)tval;
+        LTT_CUDA_OK(cudaMemcpyAsync(m->t_in, tvals.data(), m->B * 4, cudaMemcpyHostToDevice, st));
+        LTT_CUDA_OK(cudaStreamSynchronize(st));   // tvals is pageable host memory reused next step
+        return 0;
+    };
+    LTT_CUDA_OK(cudaMemcpyAsync(m->pl_x, x_inout, n * 4, cudaMemcpyDeviceToDevice, st));
+    int nold = 0;
+    float* e_old[3] = {nullptr, nullptr, nullptr};   // most recent first
+    int ring = 0;
+    for (int i = 0; i < S; ++i) {
+        const int index = S - 1 - i;
+        const float scale = alpha_sched_host ? alpha_sched_host[i] : 1.0f;
+        if (alpha_sched_host && scale == 0.0f && sd_conv_weight && !m->sd_conv_w)
+            RC(ltt_set_first_conv(m, sd_conv_weight, sd_conv_bias, 0));
+        const int tv = timesteps_host[index];
+        const int tnext = timesteps_host[std::max(index - 1, 0)];
+        const float a_t = alphas_host[index], a_prev = alphas_prev_host[index], s1m = sqrt_1m_alphas_host[index];
+        RC(eval(m->pl_x, tv));
+        RC(forward_impl(m, m->x_in, m->t_in, scale, m->eps_buf, st));
+        float* e_cur = m->pl_e[ring];
+        if (nold == 0) {
+            // Euler predictor, second evaluation at t_next, e' = (e_t + e_next) / 2, step from the ORIGINAL x
+            RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 0, m->pl_x, e_cur, nullptr, nullptr, nullptr,
+                                  nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
+            RC(eval(m->pl_xsave, tnext));
+            RC(forward_impl(m, m->x_in, m->t_in, scale, m->eps_buf, st));
+            RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 1, m->pl_x, nullptr, e_cur, nullptr, nullptr,
+                                  nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
+        } else {
+            const int mode = nold == 1 ? 2 : (nold == 2 ? 3 : 4);
+            RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, mode, m->pl_x, e_cur, nullptr, e_old[0], e_old[1],
+                                  e_old[2], a_t, a_prev, s1m, m->pl_xsave, n, st));
+        }
+        m->launches += 1;
+        std::swap(m->pl_x, m->pl_xsave);
+        e_old[2] = e_old[1]; e_old[1] = e_old[0]; e_old[0] = e_cur;
+        if (nold < 3) ++nold;
+        ring = (ring + 1) & 3;
+    }
+    LTT_CUDA_OK(cudaMemcpyAsync(x_inout, m->pl_x, n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int64_t ltt_launch_count(const ltt_model* m) { return m ? m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// CUDA-core kernels of the UNet path (everything that is not a dense contraction): GroupNorm statistics / apply
+// (+SiLU), LayerNorm, first / last 3x3 convs with 4 channels, nearest upsample, stride-2 patch gather, timestep and
+// Fourier box embeddings, the relation-aware box pooling / scatter, the 30x10 relation attention (warp shuffles)
+// and the fused CFG + PLMS update.  All HBM/L2-bound elementwise or reduction work; coalesced on the channel axis.
+//
+// Reference semantics (paths under /root/reference/GLIGEN/ldm): GroupNorm32 util.py:211-229 (fp32 stats, eps 1e-5),
+// Normalize attention.py:78-79 (eps 1e-6), nn.LayerNorm eps 1e-5, timestep_embedding util.py:161-181,
+// FourierEmbedder util.py:12-26, PositionNet text_grounding_net.py:26-43, RelationCrossAttention
+// attention.py:315-359, p_sample_plms models/diffusion/plms.py:110-163.
+#include "ltt_ops.h"
+
+namespace ltt {
+
+__device__ __forceinline__ float r16f(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ float siluf(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// stats[b][g] = {sum, sumsq} in double (zeroed by the caller).  Input = channel concat of up to two NHWC tensors.
+__global__ void gn_stats_kernel(const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int c1,
+                                int ld1, int HW, int cpg, int strip, double* __restrict__ stats) {
+    __shared__ double sh[64];
+    const int b = blockIdx.y, C = c0 + c1, P = C >> 1;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
+    for (int cp = threadIdx.x; cp < P; cp += blockDim.x) {
+        const int c = cp * 2;
+        const __half* src;
+        int ld, cc;
+        if (c < c0) { src = x0; ld = ld0; cc = c; } else { src = x1; ld = ld1; cc = c - c0; }
+        float s = 0.f, ss = 0.f;
+        for (int p = p0; p < p1; ++p) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(src + ((size_t)b * HW + p) * ld + cc));
+            s += v.x + v.y;
+            ss += v.x * v.x + v.y * v.y;
+        }
+        const int g = c / cpg;
+        atomicAdd(&sh[2 * g], (double)s);
+        atomicAdd(&sh[2 * g + 1], (double)ss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&stats[(size_t)b * 64 + i], sh[i]);
+}
+
+// out[b, p, c] = act(r16((x - mean) * rstd * gamma + beta)), optionally reading x at (y/2, x/2) (nearest 2x
+// upsample of the *output* grid is NOT done here; see upsample2x).  fp16 NHWC out with pitch C.
+__global__ void gn_apply_kernel(const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int c1,
+                                int ld1, int HW, int cpg, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                __half* __restrict__ out, size_t total_pairs) {
+    const int C = c0 + c1, P = C >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (size_t)gridDim.x * blockDim.x) {
+        const int cp = (int)(i % P);
+        const size_t row = i / P;            // b*HW + p
+        const int b = (int)(row / HW);
+        const int c = cp * 2;
+        const __half* src;
+        int ld, cc;
+        if (c < c0) { src = x0; ld = ld0; cc = c; } else { src = x1; ld = ld1; cc = c - c0; }
+        const int g = c / cpg;
+        const double n = (double)cpg * HW;
+        const double mean = stats[(size_t)b * 64 + 2 * g] / n;
+        double var = stats[(size_t)b * 64 + 2 * g + 1] / n - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = rsqrtf((float)var + eps);
+        const float mu = (float)mean;
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(src + row * ld + cc));
+        float a = r16f((v.x - mu) * rstd * gamma[c] + beta[c]);
+        float d = r16f((v.y - mu) * rstd * gamma[c + 1] + beta[c + 1]);
+        if (silu) {
+            a = siluf(a);
+            d = siluf(d);
+        }
+        *reinterpret_cast<__half2*>(out + row * C + c) = __floats2half2_rn(a, d);
+    }
+}
+
+int gn_stats_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
+                    double* stats, cudaStream_t st) {
+    const int C = c0 + c1, cpg = C / groups;
+    if (groups != 32 || C % groups || (cpg & 1) || (c0 & 1)) {
+        set_error("groupnorm: unsupported C=%d groups=%d", C, groups);
+        return -1;
+    }
+    LTT_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)B * 64 * sizeof(double), st));
+    const int strip = HW >= 4096 ? 32 : (HW >= 1024 ? 16 : 8);
+    dim3 grid((HW + strip - 1) / strip, B);
+    gn_stats_kernel<<<grid, 256, 0, st>>>(x0, c0, ld0, x1, c1, ld1, HW, cpg, strip, stats);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
+                    const double* stats, const float* gamma, const float* beta, float eps, int silu, __half* out,
+                    cudaStream_t st) {
+    const int C = c0 + c1, cpg = C / groups;
+    const size_t total = (size_t)B * HW * (C / 2);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    gn_apply_kernel<<<blocks, 256, 0, st>>>(x0, c0, ld0, x1, c1, ld1, HW, cpg, stats, gamma, beta, eps, silu, out, total);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; fp32 statistics (two pass in registers); writes fp16 and/or fp32.
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __half* __restrict__ out16,
+                                 float* __restrict__ out32) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const T* xr = x + (size_t)row * C;
+    float v[40];   // C <= 1280
+    const int per = C / 32;   // host checks C % 32 == 0, per <= 40
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 40; ++i)
+        if (i < per) {
+            v[i] = (float)xr[i * 32 + lane];
+            s += v[i];
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 40; ++i)
+        if (i < per) {
+            const float d = v[i] - mean;
+            ss += d * d;
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+    for (int i = 0; i < 40; ++i)
+        if (i < per) {
+            const int c = i * 32 + lane;
+            const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            if (out16) out16[(size_t)row * C + c] = __float2half_rn(y);
+            if (out32) out32[(size_t)row * C + c] = y;
+        }
+}
+
+int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
+                     __half* out16, float* out32, cudaStream_t st) {
+    if (C % 32 || C / 32 > 40) {
+        set_error("layernorm: unsupported C=%d", C);
+        return -1;
+    }
+    const int wpb = 8;
+    const int blocks = (M + wpb - 1) / wpb;
+    if (x_dtype == DT_F16)
+        layernorm_kernel<__half><<<blocks, wpb * 32, 0, st>>>((const __half*)x, M, C, gamma, beta, eps, out16, out32);
+    else
+        layernorm_kernel<float><<<blocks, wpb * 32, 0, st>>>((const float*)x, M, C, gamma, beta, eps, out16, out32);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ first / last conv
+// input_blocks.0.0: Conv2d(4 -> Cout, 3x3, pad 1) on NCHW fp32 x; inputs and weights rounded to fp16 (autocast),
+// fp32 accumulate, NHWC fp16 out.  w: [Cout, Cin, 3, 3] fp32.
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               int B, int Cin, int H, int W, int Cout, __half* __restrict__ out) {
+    extern __shared__ float patch[];   // [Cin*9]
+    const int pix = blockIdx.x;        // b*H*W + y*W + x
+    const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
+    for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
+        const int ci = i / 9, t = i % 9, yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+        float v = 0.f;
+        if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = r16f(x[((size_t)(b * Cin + ci) * H + yy) * W + xs]);
+        patch[i] = v;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < Cin * 9; ++i) acc += patch[i] * r16f(w[(size_t)co * Cin * 9 + i]);
+        out[(size_t)pix * Cout + co] = __float2half_rn(acc + bias[co]);
+    }
+}
+
+int conv_in_launch(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
+                   __half* out, cudaStream_t st) {
+    conv_in_kernel<<<B * H * W, 128, Cin * 9 * sizeof(float), st>>>(x, w, bias, B, Cin, H, W, Cout, out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// out.2: Conv2d(C -> Cout(4), 3x3, pad 1) on NHWC fp16 input (already GN+SiLU), w packed [Cout][9][C] fp16,
+// NCHW fp32 out (values rounded to fp16 as the autocast reference returns half).  One warp per pixel.
+__global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                                int B, int H, int W, int C, int Cout, float* __restrict__ out) {
+    const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= B * H * W) return;
+    const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+        if (yy < 0 || yy >= H || xs < 0 || xs >= W) continue;
+        const __half* xr = x + ((size_t)(b * H + yy) * W + xs) * C;
+        for (int c = lane * 2; c < C; c += 64) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+#pragma unroll
+            for (int co = 0; co < 4; ++co)
+                if (co < Cout) {
+                    const float2 ww = __half22float2(*reinterpret_cast<const __half2*>(w + ((size_t)co * 9 + t) * C + c));
+                    acc[co] += v.x * ww.x + v.y * ww.y;
+                }
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    }
+    if (lane < Cout && lane < 4) {
+        float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        out[((size_t)(b * Cout + lane) * H + y) * W + xx] = r16f(a + bias[lane]);
+    }
+}
+
+int conv_out_launch(const __half* x, const __half* w, const float* bias, int B, int H, int W, int C, int Cout,
+                    float* out, cudaStream_t st) {
+    if (Cout > 4 || (C & 1)) {
+        set_error("conv_out: unsupported Cout=%d C=%d", Cout, C);
+        return -1;
+    }
+    const int wpb = 8, total = B * H * W;
+    conv_out_kernel<<<(total + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, w, bias, B, H, W, C, Cout, out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ resampling helpers
+// nearest 2x upsample, NHWC fp16, 16-byte vectors
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    const size_t total = (size_t)B * 4 * H * W * C8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        size_t p = i / C8;
+        const int ox = (int)(p % (2 * W));
+        p /= (2 * W);
+        const int oy = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        out[i] = in[((size_t)(b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c];
+    }
+}
+int upsample2x_launch(const __half* in, __half* out, int B, int H, int W, int C, cudaStream_t st) {
+    const size_t total = (size_t)B * 4 * H * W * (C / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    upsample2x_kernel<<<blocks, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// stride-2 pad-1 3x3 patch gather: out[(b, oy, ox)][tap*C + c] = in[b, 2oy-1+ky, 2ox-1+kx, c] (0 outside)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)B * Ho * Wo * 9 * C8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        size_t p = i / C8;
+        const int t = (int)(p % 9);
+        p /= 9;
+        const int ox = (int)(p % Wo);
+        p /= Wo;
+        const int oy = (int)(p % Ho);
+        const int b = (int)(p / Ho);
+        const int yy = 2 * oy - 1 + t / 3, xx = 2 * ox - 1 + t % 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = in[((size_t)(b * H + yy) * W + xx) * C8 + c];
+        out[i] = v;
+    }
+}
+int im2col_s2_launch(const __half* in, __half* out, int B, int H, int W, int C, cudaStream_t st) {
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    im2col_s2_kernel<<<blocks, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ embeddings
+// timestep_embedding: [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half), fp32 math, fp16 out [B, dim]
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+    const int half = dim / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+        const int b = i / half, k = i % half;
+        const float f = expf(-logf(10000.0f) * (float)k / (float)half);
+        const float a = t[b] * f;
+        out[(size_t)b * dim + k] = __float2half_rn(cosf(a));
+        out[(size_t)b * dim + half + k] = __float2half_rn(sinf(a));
+    }
+}
+int timestep_embed_launch(const float* t, int B, int dim, __half* out, cudaStream_t st) {
+    timestep_embed_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, st>>>(t, B, dim, out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// PositionNet input rows: [ emb*m + (1-m)*null_txt (768) | fourier(box)*m + (1-m)*null_pos (8 freqs x (sin4|cos4)) ]
+// One warp per box; lanes 0..31 cover the (freq, coord) pairs of the Fourier part via shuffles of the 4 coords.
+__global__ void posnet_input_kernel(const float* __restrict__ boxes, const float* __restrict__ masks,
+                                    const float* __restrict__ emb, const float* __restrict__ null_txt,
+                                    const float* __restrict__ null_pos, int rows, int in_dim, int nfreq,
+                                    __half* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float m = masks[row];
+    const int width = in_dim + nfreq * 8;
+    __half* o = out + (size_t)row * width;
+    for (int c = lane; c < in_dim; c += 32) o[c] = __float2half_rn(emb[(size_t)row * in_dim + c] * m + (1.f - m) * null_txt[c]);
+    const float coord = lane < 4 ? boxes[(size_t)row * 4 + lane] : 0.f;
+    for (int i = lane; i < nfreq * 4; i += 32) {
+        const int k = i / 4, j = i % 4;
+        const float x = __shfl_sync(0xffffffffu, coord, j);
+        const float f = powf(100.0f, (float)k / (float)nfreq);
+        const float a = f * x;
+        const int base = k * 8;
+        o[in_dim + base + j] = __float2half_rn(sinf(a) * m + (1.f - m) * null_pos[base + j]);
+        o[in_dim + base + 4 + j] = __float2half_rn(cosf(a) * m + (1.f - m) * null_pos[base + 4 + j]);
+    }
+}
+int posnet_input_launch(const float* boxes, const float* masks, const float* emb, const float* null_txt,
+                        const float* null_pos, int rows, int in_dim, int nfreq, __half* out, cudaStream_t st) {
+    if (nfreq * 4 > 32 * 4) {
+        set_error("posnet: too many frequencies");
+        return -1;
+    }
+    posnet_input_kernel<<<(rows + 3) / 4, 128, 0, st>>>(boxes, masks, emb, null_txt, null_pos, rows, in_dim, nfreq, out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ relation fusion
+// rects[b][i] = {top, bottom, left, right, valid}: reference truncation and first-break rules (attention.py:321-346)
+__global__ void rela_rects_kernel(const float* __restrict__ boxes, const float* __restrict__ masks, int B, int mo, int h,
+                                  int w, int* __restrict__ rects) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float nv = 0.f;
+    for (int i = 0; i < mo; ++i) nv += masks[(size_t)b * mo + i];
+    bool alive = true;
+    for (int i = 0; i < mo; ++i) {
+        const float* bx = boxes + ((size_t)b * mo + i) * 4;
+        int l = (int)(bx[0] * (float)w), t = (int)(bx[1] * (float)h);
+        int r = (int)fminf(bx[2] * (float)w, (float)w), bt = (int)fminf(bx[3] * (float)h, (float)h);
+        const bool ok = alive && ((float)i < nv) && (l != r) && (t != bt);
+        if (!ok) alive = false;
+        l = max(0, min(l, w)); r = max(0, min(r, w)); t = max(0, min(t, h)); bt = max(0, min(bt, h));
+        int* o = rects + ((size_t)b * mo + i) * 5;
+        o[0] = t; o[1] = bt; o[2] = l; o[3] = r; o[4] = (ok && r > l && bt > t) ? 1 : 0;
+    }
+}
+int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, cudaStream_t st) {
+    rela_rects_kernel<<<(B + 31) / 32, 32, 0, st>>>(boxes, masks, B, mo, h, w, rects);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// feats[b, i, :] = mean over the box of hid (fp32) -> fp16; zero for unused slots.  CTA = (64 channels, slot, b),
+// 16 pixel lanes x 16 channel quads, shuffle-free smem reduction over the pixel lanes.
+__global__ void rela_pool_kernel(const float* __restrict__ hid, const int* __restrict__ rects, int mo, int w, int HW,
+                                 int C, __half* __restrict__ feats) {
+    const int i = blockIdx.y, b = blockIdx.z, cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    const int c = blockIdx.x * 64 + cq * 4;
+    const int* rc = rects + ((size_t)b * mo + i) * 5;
+    __half* o = feats + ((size_t)b * mo + i) * C + c;
+    if (!rc[4]) {
+        if (pl == 0) *reinterpret_cast<uint2*>(o) = make_uint2(0, 0);
+        return;
+    }
+    const int t = rc[0], bt = rc[1], l = rc[2], r = rc[3];
+    const int rw = r - l, area = rw * (bt - t);
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int p = pl; p < area; p += 16) {
+        const int y = t + p / rw, x = l + p % rw;
+        const float4 v = *reinterpret_cast<const float4*>(hid + ((size_t)b * HW + y * w + x) * C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    __shared__ float4 red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (pl == 0) {
+        for (int k = 1; k < 16; ++k) {
+            const float4 v = red[k * 16 + cq];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const float inv = 1.0f / (float)area;
+        __half2 h0 = __floats2half2_rn(acc.x * inv, acc.y * inv), h1 = __floats2half2_rn(acc.z * inv, acc.w * inv);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(o) = u;
+    }
+}
+int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, int w, int C, __half* feats,
+                     cudaStream_t st) {
+    if (C % 64) {
+        set_error("rela_pool: C %% 64 != 0 (C=%d)", C);
+        return -1;
+    }
+    rela_pool_kernel<<<dim3(C / 64, mo, B), 256, 0, st>>>(hid, rects, mo, w, h * w, C, feats);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// out[b,p,:] = (hid + (1/mo) sum_{i: p in rect_i} feats[b,i,:] + x) / 2   (fp32).  feats == nullptr or b >= nb_feats
+// -> no boxes (uncond half): out = (hid + x) / 2.
+__global__ void rela_scatter_kernel(const float* __restrict__ hid, const __half* __restrict__ x,
+                                    const __half* __restrict__ feats, const int* __restrict__ rects, int nb_feats,
+                                    int mo, int w, int HW, int C, float* __restrict__ out) {
+    const int row = blockIdx.x, b = row / HW, p = row % HW, y = p / w, xx = p % w;
+    __shared__ int hit[32];
+    __shared__ int nhit;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (feats && b < nb_feats)
+            for (int i = 0; i < mo && i < 32; ++i) {
+                const int* rc = rects + ((size_t)b * mo + i) * 5;
+                if (rc[4] && y >= rc[0] && y < rc[1] && xx >= rc[2] && xx < rc[3]) hit[n++] = i;
+            }
+        nhit = n;
+    }
+    __syncthreads();
+    const float inv = 1.0f / (float)mo;
+    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int k = 0; k < nhit; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(feats + ((size_t)b * mo + hit[k]) * C + c));
+            acc.x += f.x;
+            acc.y += f.y;
+        }
+        const float2 hv = *reinterpret_cast<const float2*>(hid + (size_t)row * C + c);
+        const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)row * C + c));
+        float2 o;
+        o.x = ((hv.x + acc.x * inv) + xv.x) * 0.5f;
+        o.y = ((hv.y + acc.y * inv) + xv.y) * 0.5f;
+        *reinterpret_cast<float2*>(out + (size_t)row * C + c) = o;
+    }
+}
+int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, const int* rects, int nb_feats, int B,
+                        int mo, int h, int w, int C, float* out, cudaStream_t st) {
+    if (mo > 32) {
+        set_error("rela_scatter: more than 32 object slots");
+        return -1;
+    }
+    rela_scatter_kernel<<<B * h * w, 128, 0, st>>>(hid, x, feats, rects, nb_feats, mo, w, h * w, C, out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// 30-query x (<= 32)-key cross attention of the relation path.  One warp per (b, head, query): lane j owns key j;
+// the q.k dot products run over d with the K row read per lane, softmax by warp shuffles, PV with lanes over d.
+// q: [B, nq, C], k/v: [B, nk, C] fp16 row-major, out [B, nq, C] fp16.
+__global__ void small_attn_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
+                                  const __half* __restrict__ v, int ldkv, int nq, int nk, int heads, int d, float scale,
+                                  __half* __restrict__ out) {
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int qi = wid % nq, hh = (wid / nq) % heads, b = wid / (nq * heads);
+    const int C = heads * d;
+    const __half* qr = q + ((size_t)b * nq + qi) * ldq + hh * d;
+    float s = -INFINITY;
+    if (lane < nk) {
+        const __half* kr = k + ((size_t)b * nk + lane) * ldkv + hh * d;
+        float acc = 0.f;
+        for (int c = 0; c < d; c += 2) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(qr + c));
+            const float2 bb = __half22float2(*reinterpret_cast<const __half2*>(kr + c));
+            acc += a.x * bb.x + a.y * bb.y;
+        }
+        s = r16f(r16f(acc) * scale);   // reference: fp16 einsum result times scale in fp16
+    }
+    float mx = s;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float p = lane < nk ? __expf(s - mx) : 0.f;
+    float sum = p;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    p = r16f(p / sum);
+    for (int c = lane; c < d; c += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            const float pj = __shfl_sync(0xffffffffu, p, j);
+            acc += pj * __half2float(v[((size_t)b * nk + j) * ldkv + hh * d + c]);
+        }
+        out[((size_t)b * nq + qi) * C + hh * d + c] = __float2half_rn(acc);
+    }
+}
+int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int nq, int nk,
+                      int heads, int d, float scale, __half* out, cudaStream_t st) {
+    if (nk > 32 || (d & 1)) {
+        set_error("small_attn: nk=%d d=%d unsupported", nk, d);
+        return -1;
+    }
+    const int warps = B * heads * nq;   // multiple of 1
+    const int wpb = 4;
+    if (warps % wpb) {
+        small_attn_kernel<<<warps, 32, 0, st>>>(q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out);
+    } else {
+        small_attn_kernel<<<warps / wpb, wpb * 32, 0, st>>>(q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out);
+    }
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __float2half_rn(in[i]);
+}
+int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    cast_f32_f16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// generic strided 2-D fp16 copy: dst[b][r][c] = src[b][r][c], rows x cols per batch element
+__global__ void copy2d_kernel(const __half* __restrict__ src, size_t sb, int sld, __half* __restrict__ dst, size_t db,
+                              int dld, int B, int rows, int cols) {
+    const size_t total = (size_t)B * rows * cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        const size_t p = i / cols;
+        const int r = (int)(p % rows), b = (int)(p / rows);
+        dst[b * db + (size_t)r * dld + c] = src[b * sb + (size_t)r * sld + c];
+    }
+}
+int copy2d_launch(const __half* src, size_t sb, int sld, __half* dst, size_t db, int dld, int B, int rows, int cols,
+                  cudaStream_t st) {
+    const size_t total = (size_t)B * rows * cols;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    copy2d_kernel<<<blocks, 256, 0, st>>>(src, sb, sld, dst, db, dld, B, rows, cols);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// CFG + PLMS update (plms.py:110-163), one launch per sampler step.  All eps tensors hold fp16-representable values
+// (the autocast reference returns half), arithmetic on them is rounded to fp16 per op exactly as eager PyTorch does;
+// x stays fp32.  mode: 0 = first half of step 0 (Euler predictor: writes x_pred for the second evaluation),
+// 1 = second half of step 0 (e' = (e_t + e_next)/2), 2..4 = AB2/AB3/AB4.
+__global__ void plms_update_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u, float guidance,
+                                   int use_cfg, int mode, const float* __restrict__ x, float* __restrict__ e_t_out,
+                                   const float* __restrict__ e_first, const float* __restrict__ old1,
+                                   const float* __restrict__ old2, const float* __restrict__ old3, float a_t,
+                                   float a_prev, float sqrt_1m_at, float* __restrict__ x_out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float e = eps_c[i];
+        if (use_cfg) {
+            const float u = eps_u[i];
+            e = r16f(u + r16f(guidance * r16f(e - u)));
+        }
+        float ep;
+        if (mode == 0) {
+            e_t_out[i] = e;
+            ep = e;
+        } else if (mode == 1) {
+            ep = r16f(r16f(e_first[i] + e) * 0.5f);     // e_t kept from mode 0 in e_first; old_eps gets e_first
+        } else {
+            e_t_out[i] = e;
+            if (mode == 2) ep = r16f(r16f(r16f(3.f * e) - old1[i]) * 0.5f);
+            else if (mode == 3) ep = r16f(r16f(r16f(r16f(23.f * e) - r16f(16.f * old1[i])) + r16f(5.f * old2[i])) / 12.f);
+            else ep = r16f(r16f(r16f(r16f(r16f(55.f * e) - r16f(59.f * old1[i])) + r16f(37.f * old2[i])) - r16f(9.f * old3[i])) / 24.f);
+        }
+        const float pred_x0 = (x[i] - sqrt_1m_at * ep) / sqrtf(a_t);
+        const float dir = sqrtf(1.0f - a_prev) * ep;
+        x_out[i] = sqrtf(a_prev) * pred_x0 + dir;
+    }
+}
+int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, int use_cfg, int mode, const float* x,
+                       float* e_t_out, const float* e_first, const float* old1, const float* old2, const float* old3,
+                       float a_t, float a_prev, float sqrt_1m_at, float* x_out, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 4);
+    plms_update_kernel<<<blocks, 256, 0, st>>>(eps_c, eps_u, guidance, use_cfg, mode, x, e_t_out, e_first, old1, old2,
+                                                old3, a_t, a_prev, sqrt_1m_at, x_out, n);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weight repacking
+// conv weight [O, Cin, taps] fp32 (OIHW flattened) -> fp16 dst[o*Kdst + koff + tap*Cs + c] = w[o][cstart + c][tap]
+__global__ void pack_conv_kernel(const float* __restrict__ w, int O, int Cin, int taps, int cstart, int Cs,
+                                 __half* __restrict__ dst, int Kdst, int koff) {
+    const size_t total = (size_t)O * taps * Cs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cs);
+        const size_t p = i / Cs;
+        const int t = (int)(p % taps), o = (int)(p / taps);
+        dst[(size_t)o * Kdst + koff + t * Cs + c] = __float2half_rn(w[((size_t)o * Cin + cstart + c) * taps + t]);
+    }
+}
+int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int Cs, __half* dst, int Kdst, int koff,
+                     cudaStream_t st) {
+    const size_t total = (size_t)O * taps * Cs;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    pack_conv_kernel<<<blocks, 256, 0, st>>>(w, O, Cin, taps, cstart, Cs, dst, Kdst, koff);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// linear weight rows [rows, K] fp32 -> fp16 dst rows starting at row_off; geglu != 0 interleaves per 128-row tile:
+// packed row p = tile*128 + h*64 + i  <-  source row h*(rows/2) + tile*64 + i   (h = 0 value, 1 gate)
+__global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int K, __half* __restrict__ dst, int row_off,
+                                 int geglu) {
+    const size_t total = (size_t)rows * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const int p = (int)(i / K);
+        int src = p;
+        if (geglu) {
+            const int tile = p / 128, h = (p % 128) / 64, ii = p % 64;
+            src = h * (rows / 2) + tile * 64 + ii;
+        }
+        dst[((size_t)row_off + p) * K + k] = __float2half_rn(w[(size_t)src * K + k]);
+    }
+}
+int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, int geglu, cudaStream_t st) {
+    if (geglu && rows % 128) {
+        set_error("pack_rows: GEGLU rows %% 128 != 0 (%d)", rows);
+        return -1;
+    }
+    const size_t total = (size_t)rows * K;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    pack_rows_kernel<<<blocks, 256, 0, st>>>(w, rows, K, dst, row_off, geglu);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ltt

@@ -1,0 +1,211 @@
+"""Operator-level parity checks: each CUDA kernel, called through the C-ABI, against the torch oracle on the same
+seeded inputs.  Used by tests/test_ops_gpu.py (pytest -m gpu) and tools/gpu_check.py (prints every result)."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from layoutllm_t2i_b200 import _lib as L
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rn(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def linear(a16, w16, bias=None, act=0, res=None, gate=None, out_dtype=torch.float16):
+    M, K = a16.shape
+    N = w16.shape[0]
+    nout = N // 2 if act == 2 else N
+    out = torch.empty(M, nout, device=DEV, dtype=out_dtype)
+    L.check(L.lib().ltt_op_linear(L.ptr(a16), M, K, a16.stride(0), L.ptr(w16), N, L.ptr(bias), act, L.ptr(res),
+                                  0 if res is None or res.dtype == torch.float16 else 1,
+                                  0 if res is None else res.stride(0), 1.0 if gate is None else gate,
+                                  0 if gate is None else 1, L.ptr(out), 0 if out_dtype == torch.float16 else 1, nout,
+                                  L.stream_ptr()), "ltt_op_linear")
+    return out
+
+
+def check_linear(M, N, K, seed=0, bias=True, act=0, res_dtype=None, gate=None, out_dtype=torch.float16):
+    a = rn(M, K, seed=seed, dtype=torch.float16)
+    w = rn(N, K, seed=seed + 1, scale=1 / math.sqrt(K))
+    b = rn(N, seed=seed + 2, scale=0.1) if bias else None
+    nout = N // 2 if act == 2 else N
+    res = rn(M, nout, seed=seed + 3, dtype=res_dtype) if res_dtype is not None else None
+    if act == 2:
+        w16 = torch.empty(N, K, device=DEV, dtype=torch.float16)
+        L.check(L.lib().ltt_op_pack_geglu(L.ptr(w.contiguous()), N, K, L.ptr(w16), L.stream_ptr()), "pack_geglu")
+    else:
+        w16 = w.half()
+    y = linear(a, w16, b, act, res, gate, out_dtype)
+    ref = F.linear(a.float(), w.half().float(), b)
+    if act == 1:
+        ref = F.silu(ref)
+    elif act == 2:
+        v, g = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+    if gate is not None:
+        ref = ref * gate
+    if res is not None:
+        ref = ref + res.float()
+    return rel(y.float(), ref)
+
+
+def check_conv3x3(B, H, W, C, N, seed=0, rowvec=False):
+    x = rn(B, H, W, C, seed=seed, dtype=torch.float16)
+    w = rn(N, C, 3, 3, seed=seed + 1, scale=1 / math.sqrt(9 * C))
+    b = rn(N, seed=seed + 2, scale=0.1)
+    rv = rn(B, N, seed=seed + 3, dtype=torch.float16) if rowvec else None
+    wp = torch.empty(N, 9 * C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_pack_conv3x3(L.ptr(w.contiguous()), N, C, L.ptr(wp), L.stream_ptr()), "pack_conv")
+    out = torch.empty(B, H, W, N, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_conv3x3(L.ptr(x), B, H, W, C, L.ptr(wp), N, L.ptr(b), L.ptr(rv), L.ptr(out),
+                                   L.stream_ptr()), "conv3x3")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1)
+    if rowvec:
+        ref = ref + rv.float()[:, :, None, None]
+    return rel(out.float().permute(0, 3, 1, 2), ref)
+
+
+def dpad_of(d):
+    return {40: 64, 80: 128, 160: 192, 8: 64, 16: 64}[d]
+
+
+def attention_inputs(B, heads, d, nq, nk, seed=0):
+    """q,k in the head-padded layout, v transposed; plus the plain [B,n,C] versions for the oracle."""
+    C, dp = heads * d, dpad_of(d)
+    q = rn(B, nq, C, seed=seed, dtype=torch.float16)
+    k = rn(B, nk, C, seed=seed + 1, dtype=torch.float16)
+    v = rn(B, nk, C, seed=seed + 2, dtype=torch.float16)
+    rows_k = nk + 3
+    pitch = (nk + 63) // 64 * 64
+    qp = torch.zeros(B, nq, heads * dp, device=DEV, dtype=torch.float16)
+    kp = torch.zeros(B, rows_k, heads * dp, device=DEV, dtype=torch.float16)
+    qp.view(B, nq, heads, dp)[..., :d] = q.view(B, nq, heads, d)
+    kp.view(B, rows_k, heads, dp)[:, :nk, :, :d] = k.view(B, nk, heads, d)
+    kp[:, nk:] = 77.0          # stale rows beyond nk must be ignored
+    vt = torch.full((B, C, pitch), 55.0, device=DEV, dtype=torch.float16)
+    vt[:, :, :nk] = v.transpose(1, 2)
+    return q, k, v, qp, kp, vt, rows_k, pitch
+
+
+def attention_ref(q, k, v, heads):
+    B, nq, C = q.shape
+    d = C // heads
+    qh = q.float().view(B, nq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, d).transpose(1, 2)
+    p = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1)
+    return (p @ vh).transpose(1, 2).reshape(B, nq, C)
+
+
+def check_attention(B, heads, d, nq, nk, seed=0, qscale=1.0):
+    q, k, v, qp, kp, vt, rows_k, pitch = attention_inputs(B, heads, d, nq, nk, seed)
+    if qscale != 1.0:
+        q = q * qscale
+        qp = qp * qscale
+    C = heads * d
+    out = torch.zeros(B, nq, C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_attention(L.ptr(qp), nq, L.ptr(kp), rows_k, L.ptr(vt), pitch, B, heads, d, dpad_of(d), nq,
+                                     nk, d ** -0.5, L.ptr(out), C, L.stream_ptr()), "attention")
+    return rel(out.float(), attention_ref(q, k, v, heads))
+
+
+def check_qkv(B, tokens, C, heads, seed=0):
+    d = C // heads
+    dp = dpad_of(d)
+    a = rn(B, tokens, C, seed=seed, dtype=torch.float16)
+    w = rn(3 * C, C, seed=seed + 1, scale=1 / math.sqrt(C))
+    rows_k = tokens + 30
+    pitch = (rows_k + 63) // 64 * 64
+    q = torch.zeros(B, tokens, heads * dp, device=DEV, dtype=torch.float16)
+    k = torch.zeros(B, rows_k, heads * dp, device=DEV, dtype=torch.float16)
+    vt = torch.zeros(B, C, pitch, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_qkv(L.ptr(a), B, tokens, C, L.ptr(w.half()), heads, dp, L.ptr(q), tokens, L.ptr(k), rows_k,
+                               L.ptr(vt), pitch, L.stream_ptr()), "qkv")
+    ref = F.linear(a.float(), w.half().float())
+    rq, rk, rv = ref.split(C, dim=-1)
+    e1 = rel(q.view(B, tokens, heads, dp)[..., :d].reshape(B, tokens, C).float(), rq)
+    e2 = rel(k.view(B, rows_k, heads, dp)[:, :tokens, :, :d].reshape(B, tokens, C).float(), rk)
+    e3 = rel(vt[:, :, :tokens].transpose(1, 2).float(), rv)
+    pad_ok = float(q.view(B, tokens, heads, dp)[..., d:].abs().max()) == 0.0
+    return max(e1, e2, e3) if pad_ok else 1.0
+
+
+def check_groupnorm(B, HW, c0, c1, silu, eps, seed=0):
+    x0 = rn(B, HW, c0, seed=seed, dtype=torch.float16) + 0.5
+    x1 = rn(B, HW, c1, seed=seed + 1, dtype=torch.float16) * 2 if c1 else None
+    C = c0 + c1
+    g = 1 + 0.1 * rn(C, seed=seed + 2)
+    b = 0.1 * rn(C, seed=seed + 3)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_groupnorm(L.ptr(x0), c0, L.ptr(x1), c1, B, HW, L.ptr(g), L.ptr(b), eps, int(silu),
+                                     L.ptr(out), L.stream_ptr()), "groupnorm")
+    x = torch.cat([x0, x1], dim=-1) if c1 else x0
+    ref = F.group_norm(x.float().transpose(1, 2), 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref.half().float())
+    return rel(out.float().transpose(1, 2), ref)
+
+
+def check_layernorm(M, C, dtype, seed=0):
+    x = (rn(M, C, seed=seed) * 3 + 1).to(dtype)
+    g = 1 + 0.1 * rn(C, seed=seed + 1)
+    b = 0.1 * rn(C, seed=seed + 2)
+    o16 = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    o32 = torch.empty(M, C, device=DEV, dtype=torch.float32)
+    L.check(L.lib().ltt_op_layernorm(L.ptr(x), 0 if dtype == torch.float16 else 1, M, C, L.ptr(g), L.ptr(b), 1e-5,
+                                     L.ptr(o16), L.ptr(o32), L.stream_ptr()), "layernorm")
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    return max(rel(o32, ref), rel(o16.float(), ref) / 4)
+
+
+ALL = [
+    # name, fn, args, tolerance (rel-L2 vs fp32 math on the same fp16 inputs)
+    ("linear 256x128x64 (1 tile, 1 k-iter)", check_linear, dict(M=256, N=128, K=64, bias=False), 2e-3),
+    ("linear 4096x320x320 bias", check_linear, dict(M=4096, N=320, K=320), 2e-3),
+    ("linear 1000x640x1280 tail rows", check_linear, dict(M=1000, N=640, K=1280), 2e-3),
+    ("linear 128x1280x5120 split-K", check_linear, dict(M=128, N=1280, K=5120), 2e-3),
+    ("linear 60x320x1280 split-K small M", check_linear, dict(M=60, N=320, K=1280), 2e-3),
+    ("linear SiLU 90x512x832", check_linear, dict(M=90, N=512, K=832, act=1), 2e-3),
+    ("linear GEGLU 1024x2560x320", check_linear, dict(M=1024, N=2560, K=320, act=2), 2e-3),
+    ("linear GEGLU split-K 64x10240x1280", check_linear, dict(M=64, N=10240, K=1280, act=2), 2e-3),
+    ("linear gate+res16 1024x320x1280", check_linear, dict(M=1024, N=320, K=1280, res_dtype=torch.float16, gate=0.46), 2e-3),
+    ("linear res32->f32 512x640x640", check_linear, dict(M=512, N=640, K=640, res_dtype=torch.float32, out_dtype=torch.float32), 2e-3),
+    ("linear res32->f16 512x640x2560", check_linear, dict(M=512, N=640, K=2560, res_dtype=torch.float32), 2e-3),
+    ("conv3x3 1x64x64 320->320", check_conv3x3, dict(B=1, H=64, W=64, C=320, N=320), 2e-3),
+    ("conv3x3 2x32x32 640->640 +rowvec", check_conv3x3, dict(B=2, H=32, W=32, C=640, N=640, rowvec=True), 2e-3),
+    ("conv3x3 2x16x16 1280->1280 split-K", check_conv3x3, dict(B=2, H=16, W=16, C=1280, N=1280), 2e-3),
+    ("conv3x3 1x8x8 1280->1280 (tb=2 tile)", check_conv3x3, dict(B=1, H=8, W=8, C=1280, N=1280), 2e-3),
+    ("conv3x3 3x8x8 64->128", check_conv3x3, dict(B=3, H=8, W=8, C=64, N=128), 2e-3),
+    ("conv3x3 2x12x12 128->64 (ragged tile)", check_conv3x3, dict(B=2, H=12, W=12, C=128, N=64), 2e-3),
+    ("conv3x3 1x96x96 320->320", check_conv3x3, dict(B=1, H=96, W=96, C=320, N=320), 2e-3),
+    ("qkv 2x1024 C=640", check_qkv, dict(B=2, tokens=1024, C=640, heads=8), 2e-3),
+    ("qkv 1x4096 C=320", check_qkv, dict(B=1, tokens=4096, C=320, heads=8), 2e-3),
+    ("qkv 3x64 C=1280", check_qkv, dict(B=3, tokens=64, C=1280, heads=8), 2e-3),
+    ("qkv 2x256 C=64 (tiny heads)", check_qkv, dict(B=2, tokens=256, C=64, heads=8), 2e-3),
+    ("attention d=40 nq=256 nk=128 (1 tile)", check_attention, dict(B=1, heads=8, d=40, nq=256, nk=128), 3e-3),
+    ("attention d=40 nq=4096 nk=4126", check_attention, dict(B=1, heads=8, d=40, nq=4096, nk=4126), 3e-3),
+    ("attention d=80 nq=1024 nk=1054", check_attention, dict(B=2, heads=8, d=80, nq=1024, nk=1054), 3e-3),
+    ("attention d=160 nq=256 nk=286", check_attention, dict(B=2, heads=8, d=160, nq=256, nk=286), 3e-3),
+    ("attention d=160 nq=64 nk=77", check_attention, dict(B=1, heads=8, d=160, nq=64, nk=77), 3e-3),
+    ("attention d=40 nq=4096 nk=77", check_attention, dict(B=1, heads=8, d=40, nq=4096, nk=77), 3e-3),
+    ("attention d=80 peaky logits (rescale path)", check_attention, dict(B=1, heads=8, d=80, nq=300, nk=700, qscale=6.0), 5e-3),
+    ("attention d=8 nq=256 nk=286", check_attention, dict(B=2, heads=8, d=8, nq=256, nk=286), 3e-3),
+    ("attention d=16 nq=64 nk=94", check_attention, dict(B=2, heads=8, d=16, nq=64, nk=94), 3e-3),
+    ("groupnorm+silu 2x4096 320", check_groupnorm, dict(B=2, HW=4096, c0=320, c1=0, silu=True, eps=1e-5), 2e-3),
+    ("groupnorm concat 1x1024 1280+640", check_groupnorm, dict(B=1, HW=1024, c0=1280, c1=640, silu=True, eps=1e-5), 2e-3),
+    ("groupnorm eps1e-6 nosilu 2x64 1280", check_groupnorm, dict(B=2, HW=64, c0=1280, c1=0, silu=False, eps=1e-6), 2e-3),
+    ("layernorm f16 4096x320", check_layernorm, dict(M=4096, C=320, dtype=torch.float16), 1e-4),
+    ("layernorm f32 1000x1280", check_layernorm, dict(M=1000, C=1280, dtype=torch.float32), 1e-4),
+    ("layernorm f16 90x64", check_layernorm, dict(M=90, C=64, dtype=torch.float16), 1e-4),
+]
