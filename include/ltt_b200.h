@@ -86,6 +86,14 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t ltt_launch_count(const ltt_model* m);
 
+/* Debug taps (parity tests only): while a device buffer is registered, every ltt_unet_forward records named fp32
+ * copies of intermediate activations ([rows, cols] = pixel/token rows x channels) into it.  Names are the reference's
+ * module paths ("input_blocks.1.1", "input_blocks.1.1:attn1", ...).  buf == NULL switches recording off. */
+int ltt_debug_set_taps(ltt_model* m, float* buf, int64_t capacity_elems);
+int ltt_debug_tap_count(const ltt_model* m);
+int ltt_debug_tap_info(const ltt_model* m, int idx, char* name, int name_cap, int64_t* offset, int64_t* rows,
+                       int64_t* cols);
+
 /* ----------------------------------------------------------------------------------------------------------------
  * Operator-level API (the same kernels, exposed one by one for parity tests and profiling)
  * -------------------------------------------------------------------------------------------------------------- */

@@ -40,6 +40,9 @@ _SIGS = {
     "ltt_plms_sample": (_i, [_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), _f, _vp, _vp, _vp]),
     "ltt_launch_count": (_i64, [_vp]),
+    "ltt_debug_set_taps": (_i, [_vp, _vp, _i64]),
+    "ltt_debug_tap_count": (_i, [_vp]),
+    "ltt_debug_tap_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
     "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),
     "ltt_op_pack_conv3x3": (_i, [_vp, _i, _i, _vp, _vp]),

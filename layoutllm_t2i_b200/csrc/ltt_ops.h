@@ -30,6 +30,7 @@ int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, 
 int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int nq, int nk,
                       int heads, int d, float scale, __half* out, cudaStream_t st);
 int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st);
+int cast_f16_f32_launch(const __half* in, float* out, size_t n, cudaStream_t st);
 int copy2d_launch(const __half* src, size_t sb, int sld, __half* dst, size_t db, int dld, int B, int rows, int cols,
                   cudaStream_t st);
 int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, int use_cfg, int mode, const float* x,

@@ -118,7 +118,7 @@ struct ltt_model {
     float *hid32 = nullptr, *xe32 = nullptr, *xf32 = nullptr;
     __half *feats = nullptr, *feats2 = nullptr, *feats3 = nullptr, *featln = nullptr, *featq = nullptr, *featao = nullptr,
            *featff = nullptr;
-    std::map<int, __half*> qbuf, kbuf;   // keyed by dpad
+    std::map<int, __half*> qbuf, kbuf;   // keyed by head dim (pad columns of a buffer must stay zero)
     __half* vtbuf = nullptr;
     int rows_k_max = 0;
     double* gn_stats = nullptr;
@@ -127,6 +127,11 @@ struct ltt_model {
     float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
     GemmWorkspace ws;
     int64_t launches = 0;
+    // debug taps (ltt_debug_set_taps): named fp32 copies of intermediate activations
+    struct Tap { std::string name; int64_t offset, rows, cols; };
+    float* tap_buf = nullptr;
+    int64_t tap_cap = 0, tap_used = 0;
+    std::vector<Tap> taps;
 };
 
 namespace ltt {
@@ -421,6 +426,19 @@ static int build_plan(ltt_model* m) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------ debug taps
+static int tap(ltt_model* m, cudaStream_t st, const std::string& name, const void* p, int dtype, int64_t rows, int64_t cols) {
+    if (!m->tap_buf) return 0;
+    const int64_t n = rows * cols;
+    if (m->tap_used + n > m->tap_cap) return 0;   // silently stop recording when the buffer is full
+    float* dst = m->tap_buf + m->tap_used;
+    if (dtype == DT_F16) RC(cast_f16_f32_launch((const __half*)p, dst, (size_t)n, st));
+    else LTT_CUDA_OK(cudaMemcpyAsync(dst, p, n * 4, cudaMemcpyDeviceToDevice, st));
+    m->taps.push_back(ltt_model::Tap{name, m->tap_used, rows, cols});
+    m->tap_used += n;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------ launch helpers
 struct Run {
     ltt_model* m;
@@ -468,6 +486,7 @@ static int run_res(Run& r, const ResW& w, const __half* xa, int ca, const __half
     e1.rowvec = m->ev_all + w.emb_off;
     e1.ld_rowvec = m->emb_total;
     RC(r.gemm(H, W, w.cout, {GemmSrc{m->tnorm, w.cin, w.cin, 9}}, w.conv1, e1));
+    RC(tap(m, r.st, w.p + ":h", m->xc, DT_F16, (int64_t)B * HW, w.cout));
     RC(groupnorm(m, r.st, m->xc, w.cout, nullptr, 0, B, HW, w.gn2, 1e-5f, 1, m->tnorm));
     GemmEpilogue e2 = epi_out(out, w.cout);
     if (w.has_skip) {
@@ -514,8 +533,8 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     const int B = r.B, N = H * W, C = s.C, M = B * N;
     const int mo = m->cfg.max_objs;
     const int rows_k = m->rows_k_max, pitch_v = m->rows_k_max;
-    __half* qb = m->qbuf[s.dpad];
-    __half* kb = m->kbuf[s.dpad];
+    __half* qb = m->qbuf[s.d];
+    __half* kb = m->kbuf[s.d];
     // GroupNorm (eps 1e-6) -> proj_in
     RC(groupnorm(m, st, x_in, C, nullptr, 0, B, N, s.gn, 1e-6f, 0, m->tnorm));
     RC(r.gemm(H, W, C, {GemmSrc{m->tnorm, C, C, 1}}, s.proj_in, epi_out(m->xa, C)));
@@ -529,6 +548,8 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a1_out, e));
     }
     __half* x16 = m->xb;   // fp16 stream after attn1 (+ fuser)
+    RC(tap(m, st, s.p + ":proj_in", m->xa, DT_F16, M, C));
+    RC(tap(m, st, s.p + ":attn1", m->xb, DT_F16, M, C));
     if (alpha_scale != 0.0f) {
         // GatedSelfAttentionDense (attention.py:226-234): visual queries only, 30 cached grounding K/V rows appended
         RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
@@ -556,6 +577,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         }
         x16 = m->xb;
     }
+    RC(tap(m, st, s.p + ":fuser", x16, DT_F16, M, C));
     // RelationCrossAttention (attention.py:315-359) + the caller's (out + x) / 2 (:398)
     RC(ln(m, st, x16, DT_F16, M, C, s.r_ln3, nullptr, m->hid32));
     const int ng = m->n_grounded;
@@ -589,6 +611,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     }
     RC(rela_scatter_launch(m->hid32, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, st));
     m->launches++;
+    RC(tap(m, st, s.p + ":rela", m->xe32, DT_F32, M, C));
     // attn2 over the cached text K/V
     RC(ln(m, st, m->xe32, DT_F32, M, C, s.ln2, m->ln16, nullptr));
     RC(r.gemm(H, W, C, {GemmSrc{m->ln16, C, C, 1}}, s.a2_q, epi_qkv(s, qb, N, nullptr, 0, nullptr, 0, N, 0)));
@@ -598,6 +621,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         e.res = m->xe32; e.res_dtype = DT_F32; e.ldr = C;
         RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a2_out, e));
     }
+    RC(tap(m, st, s.p + ":attn2", m->xf32, DT_F32, M, C));
     // ff
     RC(ln(m, st, m->xf32, DT_F32, M, C, s.ln3, m->ln16, nullptr));
     {
@@ -610,6 +634,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         e.res = m->xf32; e.res_dtype = DT_F32; e.ldr = C;
         RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.ff2, e));
     }
+    RC(tap(m, st, s.p + ":ff", m->xa, DT_F16, M, C));
     {
         GemmEpilogue e = epi_out(out, C);
         e.res = x_in; e.ldr = C;
@@ -626,6 +651,8 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
     const ltt_unet_config& c = m->cfg;
     const int B = m->B, mc = c.model_channels;
     Run r{m, st, B};
+    m->taps.clear();
+    m->tap_used = 0;
     // time embedding -> SiLU(emb) -> all emb_layers at once
     RC(timestep_embed_launch(t, B, mc, m->temb16, st));
     m->launches++;
@@ -679,6 +706,11 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
                 RC(r.gemm(H, W, w.C, {GemmSrc{m->tnorm, w.C, w.C, 9}}, w.conv, epi_out(dst, w.C)));
             }
             a = dst; b = nullptr; chb = 0;
+            if (m->tap_buf) {
+                const std::string nm = L.kind == L_CONV_IN ? "input_blocks.0.0" : L.kind == L_RES ? m->res[L.idx].p
+                                     : L.kind == L_ST ? m->st[L.idx].p : L.kind == L_DOWN ? m->downs[L.idx].p : m->ups[L.idx].p;
+                RC(tap(m, st, nm, dst, DT_F16, (int64_t)B * H * W, cha));
+            }
         }
         *result = const_cast<__half*>(a);
         ch = cha;
@@ -778,11 +810,11 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     m->rows_k_max = (H * W + mo + 63) / 64 * 64;
     size_t max_vt = 0;
     for (auto& s : m->st) {
-        if (!m->qbuf.count(s.dpad)) {
+        if (!m->qbuf.count(s.d)) {
             __half *q, *k;
             RC(A(&q, (size_t)B * H * W * s.heads * s.dpad * 2, true));
             RC(A(&k, (size_t)B * m->rows_k_max * s.heads * s.dpad * 2, true));
-            m->qbuf[s.dpad] = q; m->kbuf[s.dpad] = k;
+            m->qbuf[s.d] = q; m->kbuf[s.d] = k;
         }
         max_vt = std::max(max_vt, (size_t)B * s.C * m->rows_k_max);
     }
@@ -1049,5 +1081,24 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
 }
 
 int64_t ltt_launch_count(const ltt_model* m) { return m ? m->launches : 0; }
+
+int ltt_debug_set_taps(ltt_model* m, float* buf, int64_t capacity_elems) {
+    if (!m) return -1;
+    m->tap_buf = buf;
+    m->tap_cap = buf ? capacity_elems : 0;
+    m->tap_used = 0;
+    m->taps.clear();
+    return 0;
+}
+int ltt_debug_tap_count(const ltt_model* m) { return m ? (int)m->taps.size() : 0; }
+int ltt_debug_tap_info(const ltt_model* m, int idx, char* name, int name_cap, int64_t* offset, int64_t* rows, int64_t* cols) {
+    if (!m || idx < 0 || idx >= (int)m->taps.size()) return -1;
+    const auto& t = m->taps[idx];
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", t.name.c_str());
+    if (offset) *offset = t.offset;
+    if (rows) *rows = t.rows;
+    if (cols) *cols = t.cols;
+    return 0;
+}
 
 }  // extern "C"

@@ -522,6 +522,17 @@ int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st)
     return 0;
 }
 
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __half2float(in[i]);
+}
+int cast_f16_f32_launch(const __half* in, float* out, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    cast_f16_f32_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // generic strided 2-D fp16 copy: dst[b][r][c] = src[b][r][c], rows x cols per batch element
 __global__ void copy2d_kernel(const __half* __restrict__ src, size_t sb, int sld, __half* __restrict__ dst, size_t db,
                               int dld, int B, int rows, int cols) {

@@ -234,25 +234,35 @@ def relation_fusion(sd: SD, p: str, x: Tensor, relations: Tensor, boxes: Tensor,
 
 
 def transformer_block(sd: SD, p: str, x: Tensor, context: Tensor, objs: Tensor, relations: Tensor,
-                      boxes: Tensor, masks: Tensor, h: int, w: int, heads: int, scale: float) -> Tensor:
+                      boxes: Tensor, masks: Tensor, h: int, w: int, heads: int, scale: float,
+                      taps: Optional[dict] = None, tap_prefix: str = "") -> Tensor:
     """BasicTransformerBlock._forward (attention.py:394-402)."""
+    def rec(name, v):
+        if taps is not None:
+            taps[tap_prefix + ":" + name] = v
+    rec("proj_in", x)
     x = self_attention(sd, p + ".attn1", layer_norm(sd, p + ".norm1", x), heads) + x
+    rec("attn1", x)
     x = gated_self_attention(sd, p + ".fuser", x, objs, heads, scale)
+    rec("fuser", x)
     x = (relation_fusion(sd, p + ".rela_fuse", x, relations, boxes, masks, h, w, heads) + x) / 2
+    rec("rela", x)
     x = cross_attention(sd, p + ".attn2", layer_norm(sd, p + ".norm2", x), context, heads) + x
+    rec("attn2", x)
     x = geglu_ff(sd, p + ".ff", layer_norm(sd, p + ".norm3", x)) + x
+    rec("ff", x)
     return x
 
 
 def spatial_transformer(sd: SD, p: str, x: Tensor, context, objs, relations, boxes, masks,
-                        heads: int, scale: float) -> Tensor:
+                        heads: int, scale: float, taps: Optional[dict] = None) -> Tensor:
     """SpatialTransformer.forward (attention.py:436-446); GroupNorm eps 1e-6 (:78-79)."""
     B, C, H, W = x.shape
     y = F.group_norm(x, N_GROUPS, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
     y = F.conv2d(y, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     y = y.permute(0, 2, 3, 1).reshape(B, H * W, C)
     y = transformer_block(sd, p + ".transformer_blocks.0", y, context, objs, relations, boxes, masks,
-                          H, W, heads, scale)
+                          H, W, heads, scale, taps, p)
     y = y.reshape(B, H, W, C).permute(0, 3, 1, 2)
     y = F.conv2d(y, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     return y + x
@@ -310,7 +320,7 @@ def unet_forward(sd: SD, cfg: dict, inp: dict, scale: float = 1.0,
             elif kind == "res":
                 h = res_block(sd, p, h, emb)
             elif kind == "st":
-                h = spatial_transformer(sd, p, h, context, objs, relations, boxes, masks, meta["heads"], scale)
+                h = spatial_transformer(sd, p, h, context, objs, relations, boxes, masks, meta["heads"], scale, taps)
             elif kind == "down":          # Downsample: conv3x3 stride 2 pad 1 (openaimodel.py:103-114)
                 h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
             elif kind == "up":            # Upsample: nearest x2 then conv3x3 (openaimodel.py:75-85)

@@ -1,0 +1,163 @@
+"""Model-level parity checks: the whole UNet forward / PLMS loop through the C-ABI (layoutllm_t2i_b200.engine)
+against the oracle (oracle/*.py) and the committed reference goldens.  Used by tests/test_model_gpu.py and
+tools/gpu_model_check.py."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from layoutllm_t2i_b200.engine import Engine
+from oracle import plms_oracle as po
+from oracle import unet_oracle as uo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+TINY = dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[2, 1],
+            num_res_blocks=1, channel_mult=[1, 2], num_heads=8, transformer_depth=1, context_dim=768,
+            fuser_type="gatedSA", grounding_in_dim=768, grounding_out_dim=768, fourier_freqs=8)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def to_dev(d):
+    if isinstance(d, dict):
+        return {k: to_dev(v) for k, v in d.items()}
+    return d.to(DEV) if torch.is_tensor(d) else d
+
+
+_ENGINES = {}
+
+
+def engine_for(cfg: dict, seed: int, tag: str = ""):
+    key = (repr(sorted((k, repr(v)) for k, v in cfg.items())), seed, tag)
+    if key not in _ENGINES:
+        sd = uo.synthetic_state_dict(cfg, seed=seed)
+        e = Engine(cfg, 0)
+        e.load_state_dict(sd)
+        e.finalize()
+        _ENGINES[key] = (e, sd)
+    return _ENGINES[key]
+
+
+def cfg_batch(syn, B):
+    """[cond ; uncond] conditioning of a CFG pair (reference plms.py:116-122)."""
+    ctx = torch.cat([syn["context"][:B], syn["uc"][:B]])
+    relations = torch.cat([syn["relations"][:B], syn["relations"][:B]])
+    return ctx, relations
+
+
+def oracle_eps(sd, cfg, syn, t, scale, cond, autocast, first_conv=None):
+    B = syn["x"].shape[0]
+    inp = dict(x=syn["x"], timesteps=torch.full((B,), t, dtype=torch.long, device=syn["x"].device),
+               relations=syn["relations"], context=syn["context"] if cond else syn["uc"])
+    if cond:
+        inp["grounding_input"] = syn["grounding"]
+    with torch.no_grad():
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.float16):
+                return uo.unet_forward(sd, cfg, inp, scale=scale, first_conv=first_conv).float()
+        return uo.unet_forward(sd, cfg, inp, scale=scale, first_conv=first_conv)
+
+
+def engine_eps_pair(e, syn, t, scale, H, W):
+    """cond and uncond eps from ONE [cond ; uncond] engine batch."""
+    B = syn["x"].shape[0]
+    ctx, relations = cfg_batch(syn, B)
+    e.set_conditioning(ctx, relations, syn["grounding"], H, W)
+    x2 = torch.cat([syn["x"], syn["x"]])
+    tt = torch.full((2 * B,), float(t), device=DEV)
+    out = e.forward(x2, tt, scale)
+    return out[:B], out[B:]
+
+
+def check_tiny_vs_reference_golden():
+    """Engine (fp16 kernels) against the fp32 outputs of the REFERENCE modules (tests/golden/tiny_unet.pt)."""
+    g = torch.load(os.path.join(GOLD, "tiny_unet.pt"), weights_only=False)
+    cfg = g["cfg"]
+    e, sd = engine_for(cfg, g["seed"])
+    syn = uo.synthetic_inputs(**g["syn_args"])
+    b, i, box = g["box_override"]
+    syn["grounding"]["boxes"][b, i] = torch.tensor(box)
+    syn = to_dev(syn)
+    worst = 0.0
+    for t in (981, 1):
+        for s in (1, 0):
+            ec, eu = engine_eps_pair(e, syn, t, float(s), 16, 16)
+            worst = max(worst, rel(ec, g[f"eps_cond_t{t}_s{s}"]), rel(eu, g[f"eps_unc_t{t}_s{s}"]))
+    return worst
+
+
+def check_unet_vs_oracle(cfg, seed, B, H, W, n_boxes, t, scale, autocast=True, degenerate=False):
+    """max over (cond, uncond) of rel-L2(engine, oracle on the GPU [autocast fp16 or fp32])."""
+    e, sd = engine_for(cfg, seed)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=n_boxes, seed=4321)
+    if degenerate and n_boxes >= 2:
+        syn["grounding"]["boxes"][B - 1, 1] = torch.tensor([0.30, 0.2, 0.3001, 0.9])
+    syn = to_dev(syn)
+    ec, eu = engine_eps_pair(e, syn, t, scale, H, W)
+    oc = oracle_eps(sd_dev, cfg, syn, t, scale, True, autocast)
+    ou = oracle_eps(sd_dev, cfg, syn, t, scale, False, autocast)
+    return max(rel(ec, oc), rel(eu, ou))
+
+
+def check_cond_only_batch(cfg, seed, B, H, W, n_boxes, t):
+    """A batch with grounding on every row (guidance == 1 path) and one with none."""
+    e, sd = engine_for(cfg, seed)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = to_dev(uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=n_boxes, seed=77))
+    tt = torch.full((B,), float(t), device=DEV)
+    e.set_conditioning(syn["context"], syn["relations"], syn["grounding"], H, W)
+    a = rel(e.forward(syn["x"], tt, 1.0), oracle_eps(sd_dev, cfg, syn, t, 1.0, True, True))
+    e.set_conditioning(syn["uc"], syn["relations"], None, H, W)
+    b = rel(e.forward(syn["x"], tt, 1.0), oracle_eps(sd_dev, cfg, syn, t, 1.0, False, True))
+    return max(a, b)
+
+
+def check_plms_vs_oracle(cfg, seed, B, H, W, S, guidance=7.5, first_conv_seed=5, per_step_tol=None):
+    """Free-running PLMS loop in the library against oracle.plms_sample driving the oracle UNet (autocast fp16).
+    Returns rel-L2 of the final latent."""
+    e, sd = engine_for(cfg, seed, "plms")     # own engine: the first-conv swap is permanent, as in the reference
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = to_dev(uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=3, seed=555))
+    mc = cfg["model_channels"]
+    gg = torch.Generator().manual_seed(first_conv_seed)
+    fc = dict(weight=(0.2 * torch.randn(mc, 4, 3, 3, generator=gg)).to(DEV), bias=(0.02 * torch.randn(mc, generator=gg)).to(DEV))
+
+    def model_eps(x, t, cond, scale, restored):
+        s2 = dict(syn, x=x)
+        return oracle_eps(sd_dev, cfg, s2, int(t[0]), float(scale), cond, True, fc if restored else None)
+
+    ref = po.plms_sample(model_eps, syn["x"].clone(), S=S, guidance=guidance)
+    ts, a_t, a_prev, s1m = po.plms_tables(S, po.alphas_cumprod())
+    ctx, relations = cfg_batch(syn, B)
+    if guidance == 1:
+        ctx, relations = syn["context"], syn["relations"]
+    e.set_conditioning(ctx, relations, syn["grounding"], H, W)
+    out = e.plms_sample(syn["x"], ts, a_t, a_prev, s1m, po.alpha_schedule(S), guidance, (fc["weight"], fc["bias"]))
+    return rel(out, ref)
+
+
+FULL = uo.default_unet_config()
+
+ALL = [
+    ("tiny UNet vs reference golden (fp32)", check_tiny_vs_reference_golden, {}, 5e-3),
+    ("tiny UNet vs autocast oracle, alpha=1", check_unet_vs_oracle,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, degenerate=True), 3e-3),
+    ("tiny UNet vs autocast oracle, alpha=0, 24x16 latent", check_unet_vs_oracle,
+     dict(cfg=TINY, seed=7, B=3, H=24, W=16, n_boxes=5, t=401, scale=0.0), 3e-3),
+    ("tiny UNet cond-only / null-only batches", check_cond_only_batch, dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=30, t=21), 3e-3),
+    ("tiny PLMS 5 steps, CFG 7.5", check_plms_vs_oracle, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5), 5e-3),
+    ("full UNet 64x64 B=1 2 boxes t=981 alpha=1 vs autocast oracle (config 1)", check_unet_vs_oracle,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=2, t=981, scale=1.0), 3e-3),
+    ("full UNet 64x64 B=1 6 boxes t=481 alpha=0 vs autocast oracle", check_unet_vs_oracle,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=6, t=481, scale=0.0), 3e-3),
+    ("full UNet 64x64 B=1 vs fp32 oracle", check_unet_vs_oracle,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=2, t=981, scale=1.0, autocast=False), 5e-3),
+]
