@@ -144,6 +144,88 @@ def check_plms_vs_oracle(cfg, seed, B, H, W, S, guidance=7.5, first_conv_seed=5,
     return rel(out, ref)
 
 
+# ------------------------------------------------------------------------------------------------ drop-in module tree
+def dropin_unet(cfg, seed):
+    import sys
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "layoutllm_t2i_b200", "dropin")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    from grounding_input.text_layout_tokinzer_input import GroundingNetInput
+    from ldm.util import instantiate_from_config
+    m = instantiate_from_config(dict(
+        target="ldm.modules.diffusionmodules.openaimodel.UNetModel",
+        params=dict(image_size=cfg["image_size"], in_channels=4, out_channels=4, model_channels=cfg["model_channels"],
+                    attention_resolutions=cfg["attention_resolutions"], num_res_blocks=cfg["num_res_blocks"],
+                    channel_mult=cfg["channel_mult"], num_heads=8, transformer_depth=1, context_dim=768,
+                    fuser_type="gatedSA", use_checkpoint=True,
+                    grounding_tokenizer=dict(target="ldm.modules.diffusionmodules.text_grounding_net.PositionNet",
+                                             params=dict(in_dim=768, out_dim=768)))))
+    sd = uo.synthetic_state_dict(cfg, seed=seed)
+    m.load_state_dict(sd, strict=False)           # as reference txt2img.py:106
+    m = m.to(DEV).eval()
+    m.grounding_tokenizer_input = GroundingNetInput()
+    return m, sd
+
+
+def ref_style_set_alpha_scale(model, alpha_scale):
+    """set_alpha_scale as the reference's callers define it (txt2img.py:46-50)."""
+    from ldm.modules.attention import GatedCrossAttentionDense, GatedSelfAttentionDense
+    for module in model.modules():
+        if type(module) == GatedCrossAttentionDense or type(module) == GatedSelfAttentionDense:
+            module.scale = alpha_scale
+
+
+def check_dropin_forward(cfg, seed, B, H, W, t):
+    """UNetModel.forward(dict) of the drop-in tree, cond then uncond call as the reference sampler issues them."""
+    m, sd = dropin_unet(cfg, seed)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = to_dev(uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=4, seed=31))
+    g = m.grounding_tokenizer_input.prepare(dict(boxes=syn["grounding"]["boxes"], masks=syn["grounding"]["masks"],
+                                                 text_embeddings=syn["grounding"]["positive_embeddings"]), None)
+    ts = torch.full((B,), t, device=DEV, dtype=torch.long)
+    cond = dict(x=syn["x"], timesteps=ts, context=syn["context"], relations=syn["relations"], grounding_input=g,
+                inpainting_extra_input=None, grounding_extra_input=None)
+    unc = dict(x=syn["x"], timesteps=ts, context=syn["uc"], relations=syn["relations"],
+               inpainting_extra_input=None, grounding_extra_input=None)
+    worst = 0.0
+    for scale in (1.0, 0.0):
+        ref_style_set_alpha_scale(m, scale)
+        worst = max(worst, rel(m(cond), oracle_eps(sd_dev, cfg, syn, t, scale, True, True)),
+                    rel(m(unc), oracle_eps(sd_dev, cfg, syn, t, scale, False, True)))
+    return worst
+
+
+def check_dropin_sampler(cfg, seed, B, H, W, S, mode):
+    """PLMSSampler.sample of the drop-in tree (fused or stepwise) against the oracle sampler + oracle UNet."""
+    from functools import partial
+    from ldm.models.diffusion.ldm import LatentDiffusion
+    from ldm.models.diffusion.plms import PLMSSampler
+    m, sd = dropin_unet(cfg, seed)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = to_dev(uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=3, seed=555))
+    mc_ = cfg["model_channels"]
+    gg = torch.Generator().manual_seed(5)
+    fcw, fcb = 0.2 * torch.randn(mc_, 4, 3, 3, generator=gg), 0.02 * torch.randn(mc_, generator=gg)
+    m.set_sd_first_conv(fcw, fcb)
+    fc = dict(weight=fcw.to(DEV), bias=fcb.to(DEV))
+
+    def model_eps(x, t, cond, scale, restored):
+        return oracle_eps(sd_dev, cfg, dict(syn, x=x), int(t[0]), float(scale), cond, True, fc if restored else None)
+
+    ref = po.plms_sample(model_eps, syn["x"].clone(), S=S, guidance=7.5)
+    diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).to(DEV)
+    sampler = PLMSSampler(diffusion, m, alpha_generator_func=partial(po.alpha_schedule, kind=(0.3, 0.0, 0.7)),
+                          set_alpha_scale=ref_style_set_alpha_scale)
+    sampler.mode = mode
+    g = m.grounding_tokenizer_input.prepare(dict(boxes=syn["grounding"]["boxes"], masks=syn["grounding"]["masks"],
+                                                 text_embeddings=syn["grounding"]["positive_embeddings"]), None)
+    inp = dict(x=syn["x"].clone(), timesteps=None, context=syn["context"], relations=syn["relations"], grounding_input=g,
+               inpainting_extra_input=None, grounding_extra_input=None)
+    out = sampler.sample(S=S, shape=tuple(syn["x"].shape), input=inp, uc=syn["uc"], guidance_scale=7.5)
+    assert m.fuser_scale() == 0.0 and m._sd_conv_active and inp["x"] is out
+    return rel(out, ref)
+
+
 FULL = uo.default_unet_config()
 
 ALL = [
@@ -154,6 +236,10 @@ ALL = [
      dict(cfg=TINY, seed=7, B=3, H=24, W=16, n_boxes=5, t=401, scale=0.0), 3e-3),
     ("tiny UNet cond-only / null-only batches", check_cond_only_batch, dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=30, t=21), 3e-3),
     ("tiny PLMS 5 steps, CFG 7.5", check_plms_vs_oracle, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5), 5e-3),
+    ("drop-in UNetModel.forward(dict), cond + uncond, both gate values", check_dropin_forward,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, t=601), 3e-3),
+    ("drop-in PLMSSampler.sample fused, 5 steps", check_dropin_sampler, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5, mode="fused"), 5e-3),
+    ("drop-in PLMSSampler.sample stepwise, 5 steps", check_dropin_sampler, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5, mode="stepwise"), 5e-3),
     ("full UNet 64x64 B=1 2 boxes t=981 alpha=1 vs autocast oracle (config 1)", check_unet_vs_oracle,
      dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=2, t=981, scale=1.0), 3e-3),
     ("full UNet 64x64 B=1 6 boxes t=481 alpha=0 vs autocast oracle", check_unet_vs_oracle,
