@@ -86,6 +86,13 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t ltt_launch_count(const ltt_model* m);
 
+/* Per-kernel-class device timing for bench.py's roofline: while enabled, every launch of a class is bracketed by CUDA
+ * events on the launch stream.  ltt_profile_report synchronises and returns, for class cls (0 = tcgen05 GEMM/implicit
+ * conv, 1 = tcgen05 attention, 2 = GroupNorm, 3 = LayerNorm, 4 = whole UNet forward), the summed event time [ms], the
+ * algorithmic FLOPs (2*M*N*K; 4*nq*nk*d per head) and bytes, and the launch count since ltt_profile_enable(m, 1). */
+int ltt_profile_enable(ltt_model* m, int on);
+int ltt_profile_report(ltt_model* m, int cls, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* Debug taps (parity tests only): while a device buffer is registered, every ltt_unet_forward records named fp32
  * copies of intermediate activations ([rows, cols] = pixel/token rows x channels) into it.  Names are the reference's
  * module paths ("input_blocks.1.1", "input_blocks.1.1:attn1", ...).  buf == NULL switches recording off. */

@@ -40,6 +40,8 @@ _SIGS = {
     "ltt_plms_sample": (_i, [_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), _f, _vp, _vp, _vp]),
     "ltt_launch_count": (_i64, [_vp]),
+    "ltt_profile_enable": (_i, [_vp, _i]),
+    "ltt_profile_report": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "ltt_debug_set_taps": (_i, [_vp, _vp, _i64]),
     "ltt_debug_tap_count": (_i, [_vp]),
     "ltt_debug_tap_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -35,9 +35,7 @@ struct GemmDeviceArgs {
     int iters_total;
     int B, H, W, N;
     int tw, th, tiles_x, tiles_y;
-    int splits;
-    float* partials;
-    int* counters;
+    int mtiles, ntiles, splits;   // splits > 1: one cluster of `splits` CTAs per tile, K range split by cluster rank
     GemmEpilogue epi;
 };
 
@@ -45,8 +43,9 @@ template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers/tmem slot + alignment slack
+    static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;           // BN floats
+    static constexpr int BAR_OFFSET = BIAS_OFFSET + BN * 4;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;              // + barriers/tmem slot + alignment slack
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
@@ -59,25 +58,62 @@ struct RowInfo {
     bool valid;
 };
 
-// Fused epilogue on 8 consecutive output columns [n, n+8) of row `ri` (values = raw fp32 accumulators; for GEGLU
-// v = value half, g = gate half).  Rounding points follow the fp16-autocast reference: each Linear/Conv output is
-// rounded to fp16 before the next elementwise op.
-__device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout,
-                                                float (&v)[8], const float (&g)[8]) {
+// Residual / time-embedding operands of one row for 32 consecutive output columns, fetched BEFORE the accumulator
+// is read so their latency hides behind the TMEM load (and behind the previous chunk's arithmetic).
+struct RowOperands {
+    uint4 res[8];      // fp16: res[0..3] hold 32 halves; fp32: res[0..7] hold 32 floats
+    uint4 rv[4];       // 32 halves of the per-batch row vector
+};
+
+__device__ __forceinline__ void fetch_operands(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, RowOperands& o) {
+    if (!ri.valid || n >= Nout || e.out_mode == OUT_QKV) return;
+    // Nout is a multiple of 8; a 32-column chunk may end past Nout only in whole groups of 8
+    if (e.res) {
+        if (e.res_dtype == DT_F16) {
+            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.res) + (size_t)ri.m * e.ldr + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (n + 8 * i < Nout) o.res[i] = p[i];
+        } else {
+            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.res) + (size_t)ri.m * e.ldr + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (n + 4 * i < Nout) o.res[i] = p[i];
+        }
+    }
+    if (e.rowvec) {
+        const uint4* p = reinterpret_cast<const uint4*>(e.rowvec + (size_t)ri.b * e.ld_rowvec + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (n + 8 * i < Nout) o.rv[i] = p[i];
+    }
+}
+
+// Fused epilogue on 8 consecutive output columns [n, n+8) of row `ri`: v = raw fp32 accumulators (GEGLU: value half,
+// g = gate half), bv / bg = the matching bias values (already in registers), j = index of the group inside the
+// 32-column chunk whose operands are in `o`.  Rounding points follow the fp16-autocast reference: each Linear/Conv
+// output is rounded to fp16 before the next elementwise op.
+__device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
+                                                const float (&g)[8], const float (&bv)[8], const float (&bg)[8],
+                                                const RowOperands& o, int j) {
     if (!ri.valid || n >= Nout) return;
     if (e.act == ACT_GEGLU) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float val = r16(v[i] + (e.bias ? e.bias[n + i] : 0.f));
-            float gat = r16(g[i] + (e.bias ? e.bias[Nout + n + i] : 0.f));
+            const float val = r16(v[i] + bv[i]);
+            const float gat = r16(g[i] + bg[i]);
             v[i] = r16(val * r16(gelu_erf_f(gat)));
         }
     } else {
+        const __half2* rvh = reinterpret_cast<const __half2*>(&o.rv[j]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float y = v[i] + (e.bias ? e.bias[n + i] : 0.f);
+            float y = v[i] + bv[i];
             if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
-            if (e.rowvec) y = r16(y + __half2float(e.rowvec[(size_t)ri.b * e.ld_rowvec + n + i]));
+            if (e.rowvec) {
+                const float2 f = __half22float2(rvh[i >> 1]);
+                y = r16(y + ((i & 1) ? f.y : f.x));
+            }
             if (e.act == ACT_SILU) y = r16(silu_f(y));
             v[i] = y;
         }
@@ -94,29 +130,28 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[(size_t)i * e.pitch_v] = __float2half_rn(v[i]);
         } else {
-            const int head = c / e.dhead, j = c % e.dhead;
+            const int head = c / e.dhead, jj = c % e.dhead;
             __half* base = which == 0 ? e.q + ((size_t)ri.b * e.rows_q + t) * (size_t)(e.dpad * (e.C / e.dhead))
                                       : e.k + ((size_t)ri.b * e.rows_k + t) * (size_t)(e.dpad * (e.C / e.dhead));
             __half2 h[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            *reinterpret_cast<uint4*>(base + head * e.dpad + j) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(base + head * e.dpad + jj) = *reinterpret_cast<uint4*>(h);
         }
         return;
     }
     if (e.res) {
         if (e.res_dtype == DT_F16) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.res) + (size_t)ri.m * e.ldr + n);
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+            const __half2* rh = reinterpret_cast<const __half2*>(&o.res[j]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float2 f = __half22float2(rh[i]);
+                const float2 f = __half22float2(rh[i]);
                 v[2 * i] += f.x;
                 v[2 * i + 1] += f.y;
             }
         } else {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + (size_t)ri.m * e.ldr + n);
-            float4 a = rp[0], b4 = rp[1];
+            const float4 a = *reinterpret_cast<const float4*>(&o.res[2 * j]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&o.res[2 * j + 1]);
             v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
             v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
         }
@@ -133,31 +168,30 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
     }
 }
 
+// Persistent, warp-specialised kernel.  Work unit = (output tile 128 x BN, K split).  Each CTA walks units
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA issuer run ahead of the epilogue warps by up
+// to one unit because the fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of unit u
+// overlaps the main loop of unit u + 1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
     using SM = GemmSmem<BN, STAGES>;
-    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* bias_s = reinterpret_cast<float*>(smem + SM::BIAS_OFFSET);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-    int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+    uint64_t* acc_full = empty_bar + STAGES;     // 2
+    uint64_t* acc_empty = acc_full + 2;          // 2 (count 128)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int mt = blockIdx.y;
+    // Split-K mode (splits > 1): the grid is exactly one cluster per tile, every CTA runs ONE unit (tile = cluster id,
+    // K range = cluster rank) and the partial accumulators are reduced through distributed shared memory.
+    const int total_units = args.mtiles * args.ntiles * args.splits;
+    const int per = (args.iters_total + args.splits - 1) / args.splits;   // host guarantees every z gets >= 1 iteration
     const int tiles_img = args.tiles_x * args.tiles_y;
-    const int tile_b = mt / tiles_img, trem = mt % tiles_img;
     const int tb = BM / (args.tw * args.th);
-    const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
-
-    // split-K range of this CTA
-    const int per = (args.iters_total + args.splits - 1) / args.splits;
-    const int it0 = blockIdx.z * per;
-    const int it1 = min(args.iters_total, it0 + per);
-    const int niter = it1 - it0;   // host guarantees >= 1 for every z
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < args.nsrc; ++s) tma_prefetch_desc(&args.amap[s]);
@@ -166,7 +200,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(acc_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -177,40 +214,47 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            // decode (source, tap, chunk) of the first iteration
-            int s = 0, tap = 0, chunk = 0;
-            {
-                int rem = it0;
-                while (s < args.nsrc - 1 && rem >= args.taps[s] * args.kchunks[s]) {
-                    rem -= args.taps[s] * args.kchunks[s];
-                    ++s;
-                }
-                tap = rem / args.kchunks[s];
-                chunk = rem % args.kchunks[s];
-            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = it0; it < it1; ++it) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-                uint8_t* sa = smem + stage * SM::STAGE_BYTES;
-                int dx = 0, dy = 0;
-                if (args.taps[s] == 9) {
-                    dy = tap / 3 - 1;
-                    dx = tap % 3 - 1;
-                }
-                tma_load_4d(sa, &args.amap[s], &full_bar[stage], chunk * BK, x0 + dx, y0 + dy, b0);
-                tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
-                if (++chunk == args.kchunks[s]) {
-                    chunk = 0;
-                    if (++tap == args.taps[s]) {
-                        tap = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+                const int z = unit % args.splits, tile = unit / args.splits;
+                const int n0 = (tile % args.ntiles) * BN, mt = tile / args.ntiles;
+                const int tile_b = mt / tiles_img, trem = mt % tiles_img;
+                const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
+                const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
+                // decode (source, tap, chunk) of the first iteration
+                int s = 0, tap = 0, chunk = 0;
+                {
+                    int rem = it0;
+                    while (s < args.nsrc - 1 && rem >= args.taps[s] * args.kchunks[s]) {
+                        rem -= args.taps[s] * args.kchunks[s];
                         ++s;
                     }
+                    tap = rem / args.kchunks[s];
+                    chunk = rem % args.kchunks[s];
                 }
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                for (int it = it0; it < it1; ++it) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * SM::STAGE_BYTES;
+                    int dx = 0, dy = 0;
+                    if (args.taps[s] == 9) {
+                        dy = tap / 3 - 1;
+                        dx = tap % 3 - 1;
+                    }
+                    tma_load_4d(sa, &args.amap[s], &full_bar[stage], chunk * BK, x0 + dx, y0 + dy, b0);
+                    tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
+                    if (++chunk == args.kchunks[s]) {
+                        chunk = 0;
+                        if (++tap == args.taps[s]) {
+                            tap = 0;
+                            ++s;
+                        }
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -218,122 +262,205 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         constexpr uint32_t idesc = umma_idesc_f16(BN);
         int stage = 0;
         uint32_t phase = 0;
-        for (int i = 0; i < niter; ++i) {
-            mbar_wait(&full_bar[stage], phase);
+        int u = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
+            const int z = unit % args.splits;
+            const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
+            const int niter = it1 - it0;
+            const int buf = u & 1;
+            mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128(sa);
-                const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
+            const uint32_t tacc = tmem_base + buf * BN;
+            for (int i = 0; i < niter; ++i) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-                umma_commit(&empty_bar[stage]);
-                if (i == niter - 1) umma_commit(acc_bar);
-            }
-            __syncwarp();
-            if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (i == niter - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else {
         // ---------------------------------------------------------------- epilogue warps (2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;            // tile row
-        RowInfo ri;
-        {
-            const int pix = args.tw * args.th;
-            const int ib = r / pix, rr = r % pix;
-            const int iy = rr / args.tw, ix = rr % args.tw;
-            const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
-            ri.valid = (b < args.B) && (y < args.H) && (x < args.W);
-            ri.b = b;
-            ri.m = (b * args.H + y) * args.W + x;
-        }
+        const int et = threadIdx.x - 64;        // 0..127
         const GemmEpilogue& e = args.epi;
         const bool geglu = e.act == ACT_GEGLU;
         const int Nout = geglu ? args.N / 2 : args.N;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-
-        bool do_epilogue = true;
-        const float* slab0 = nullptr;
-        if (args.splits > 1) {
-            const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-            float* slab = args.partials + ((size_t)tile_id * args.splits + blockIdx.z) * (size_t)(BM * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(trow + c, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) slab[(size_t)(c + i) * BM + r] = __uint_as_float(v[i]);
+        int u = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
+            const int z = unit % args.splits, tile = unit / args.splits;
+            const int n0 = (tile % args.ntiles) * BN, mt = tile / args.ntiles;
+            const int buf = u & 1;
+            RowInfo ri;
+            {
+                const int tile_b = mt / tiles_img, trem = mt % tiles_img;
+                const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
+                const int pix = args.tw * args.th;
+                const int ib = r / pix, rr = r % pix;
+                const int iy = rr / args.tw, ix = rr % args.tw;
+                const int b = b0 + ib, y = y0 + iy, x = x0 + ix;
+                ri.valid = (b < args.B) && (y < args.H) && (x < args.W);
+                ri.b = b;
+                ri.m = (b * args.H + y) * args.W + x;
             }
-            __threadfence();
-            named_bar_sync(1, 128);
-            if (threadIdx.x == 64) {
-                const int old = atomicAdd(&args.counters[tile_id], 1);
-                const int last = (old == args.splits - 1);
-                if (last) args.counters[tile_id] = 0;   // ready for the next launch / graph replay
-                *flag_slot = last;
-            }
-            named_bar_sync(1, 128);
-            do_epilogue = (*flag_slot != 0);
-            __threadfence();
-            slab0 = args.partials + (size_t)tile_id * args.splits * (size_t)(BM * BN);
-        }
-
-        if (do_epilogue) {
-            // For GEGLU the packed weight rows put, per BN tile, BN/2 value rows followed by their BN/2 gate rows.
+            // output-column geometry of this tile.  GEGLU: the packed weight rows hold, per 128-row group, 64 value
+            // rows followed by their 64 gate rows, so a BN tile carries BN/128 groups and BN/2 output columns.
             const int ncols = geglu ? BN / 2 : BN;
             const int nbase = geglu ? n0 / 2 : n0;
-#pragma unroll 1
-            for (int c = 0; c < ncols; c += 16) {
-                float va[16], ga[16];
-                if (args.splits > 1) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float acc = 0.f, accg = 0.f;
-                        for (int z = 0; z < args.splits; ++z) {
-                            const float* sl = slab0 + (size_t)z * (BM * BN);
-                            acc += __ldcg(&sl[(size_t)(c + i) * BM + r]);
-                            if (geglu) accg += __ldcg(&sl[(size_t)(BN / 2 + c + i) * BM + r]);
-                        }
-                        va[i] = acc;
-                        ga[i] = accg;
-                    }
-                } else {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c, v);
+            // stage the bias of this tile in shared memory (value half, then gate half for GEGLU)
+            named_bar_sync(2, 128);             // previous unit's readers are done with bias_s
+            for (int c = et; c < BN; c += 128) {
+                float bvv = 0.f;
+                if (e.bias) {
                     if (geglu) {
-                        uint32_t g[16];
-                        tmem_ld16(trow + BN / 2 + c, g);
+                        const int half = c / ncols, cc = c % ncols;
+                        if (nbase + cc < Nout) bvv = e.bias[half * Nout + nbase + cc];
+                    } else if (n0 + c < Nout) {
+                        bvv = e.bias[n0 + c];
+                    }
+                }
+                bias_s[c] = bvv;
+            }
+            RowOperands opA, opB;
+            if (args.splits == 1) fetch_operands(e, ri, nbase, Nout, opA);
+            named_bar_sync(2, 128);
+            const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+            mbar_wait(&acc_full[buf], (u >> 1) & 1);
+            tc_fence_after();
+
+            if (args.splits > 1) {
+                // ---- cluster split-K: dump the partial accumulator to this CTA's shared memory ([col][row] fp32, in the
+                // idle pipeline stages: every TMA load has landed and every MMA has retired once acc_full fires), then
+                // reduce a column slice over all ranks through DSMEM in fixed rank order (deterministic).
+                float* part = reinterpret_cast<float*>(smem);
+                fence_async_smem();
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) part[(c + i) * BM + r] = __uint_as_float(v[i]);
+                }
+                tc_fence_before();
+                cluster_sync_all();                                   // #1: all partial tiles are in shared memory
+                const int S = args.splits;
+                const int groups = ncols / 8;                         // 8-column output groups of this tile
+                const int g0 = (groups * z) / S, g1 = (groups * (z + 1)) / S;
+                const uint32_t part_addr = smem_u32(part);
+                uint32_t peer[8];
+#pragma unroll
+                for (int zz = 0; zz < 8; ++zz) peer[zz] = zz < S ? dsmem_map(part_addr, zz) : 0u;
+#pragma unroll 1
+                for (int g = g0; g < g1; ++g) {
+                    const int c = g * 8;
+                    const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
+                    RowOperands o;
+                    // operands of this 8-column group go to slot 0 of the chunk-shaped operand struct
+                    if (ri.valid && nbase + c < Nout && e.out_mode != OUT_QKV) {
+                        if (e.res) {
+                            if (e.res_dtype == DT_F16) {
+                                o.res[0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.res) + (size_t)ri.m * e.ldr + nbase + c);
+                            } else {
+                                const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.res) + (size_t)ri.m * e.ldr + nbase + c);
+                                o.res[0] = pp[0];
+                                o.res[1] = pp[1];
+                            }
+                        }
+                        if (e.rowvec) o.rv[0] = *reinterpret_cast<const uint4*>(e.rowvec + (size_t)ri.b * e.ld_rowvec + nbase + c);
+                    }
+                    float v8[8], g8[8], bv[8], bg[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v8[i] = 0.f;
+                        g8[i] = 0.f;
+                        bv[i] = bias_s[c + i];
+                        bg[i] = geglu ? bias_s[ncols + c + i] : 0.f;
+                    }
+#pragma unroll
+                    for (int zz = 0; zz < 8; ++zz) {
+                        if (zz < S) {
+                            float t8[8], u8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                t8[i] = dsmem_ld_f32(peer[zz] + (uint32_t)(((vcol + i) * BM + r) * 4));
+                                u8[i] = geglu ? dsmem_ld_f32(peer[zz] + (uint32_t)(((vcol + 64 + i) * BM + r) * 4)) : 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v8[i] += t8[i];
+                                g8[i] += u8[i];
+                            }
+                        }
+                    }
+                    epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0);
+                }
+            } else {
+                // one 32-column chunk: accumulators -> fused epilogue -> global
+                auto process = [&](int c, const RowOperands& o) {
+                    float va[32], ga[32];
+                    // column of the value / gate accumulator inside the tile for output column c + i
+                    const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
+                    uint32_t v[32];
+                    tmem_ld32(trow + vcol, v);
+                    if (geglu) {
+                        uint32_t g[32];
+                        tmem_ld32(trow + vcol + 64, g);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) ga[i] = __uint_as_float(g[i]);
+                        for (int i = 0; i < 32; ++i) ga[i] = __uint_as_float(g[i]);
                     } else {
                         tmem_ld_wait();
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) va[i] = __uint_as_float(v[i]);
-                }
+                    for (int i = 0; i < 32; ++i) va[i] = __uint_as_float(v[i]);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v8[8], g8[8];
+                    for (int h = 0; h < 4; ++h) {
+                        float v8[8], g8[8], bv[8], bg[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v8[i] = va[h * 8 + i];
-                        g8[i] = geglu ? ga[h * 8 + i] : 0.f;
+                        for (int i = 0; i < 8; ++i) {
+                            v8[i] = va[h * 8 + i];
+                            g8[i] = geglu ? ga[h * 8 + i] : 0.f;
+                            bv[i] = bias_s[c + h * 8 + i];
+                            bg[i] = geglu ? bias_s[ncols + c + h * 8 + i] : 0.f;
+                        }
+                        epilogue_group8(e, ri, nbase + c + h * 8, Nout, v8, g8, bv, bg, o, h);
                     }
-                    epilogue_group8(e, ri, nbase + c + h * 8, Nout, v8, g8);
+                };
+#pragma unroll 1
+                for (int c = 0; c < ncols; c += 64) {
+                    if (c + 32 < ncols) fetch_operands(e, ri, nbase + c + 32, Nout, opB);
+                    process(c, opA);
+                    if (c + 32 < ncols) {
+                        if (c + 64 < ncols) fetch_operands(e, ri, nbase + c + 64, Nout, opA);
+                        process(c + 32, opB);
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[buf]);
             }
         }
-        tc_fence_before();
     }
+    __syncwarp();
+    if (args.splits > 1) {
+        if (warp < 2) cluster_sync_all();   // #1 (the epilogue warps arrived inside their role)
+        cluster_sync_all();                 // #2: no CTA leaves while a peer may still read its partial tile
+    }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -414,18 +541,82 @@ static void pick_tile(int B, int H, int W, int* tw, int* th) {
     }
 }
 
+// One kernel variant: picks the split-K cluster size and launches.
 template <int BN, int STAGES>
-static int launch_variant(const GemmDeviceArgs& a, dim3 grid, cudaStream_t stream) {
+struct Variant {
     using SM = GemmSmem<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-        configured = true;
+    static int configure() {
+        static bool configured = false;
+        if (!configured) {
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            configured = true;
+        }
+        return 0;
     }
-    gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(a);
-    LTT_CUDA_OK(cudaGetLastError());
-    return 0;
-}
+    // how many clusters of size S can be resident at once (1 CTA per SM, clusters stay inside a GPC)
+    static int max_clusters(int S) {
+        static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (cache[S]) return cache[S];
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(S * 64, 1, 1);
+        cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = SM::TOTAL;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = S;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            n = -1;
+        }
+        cache[S] = n > 0 ? n : -1;
+        return cache[S];
+    }
+    static int launch(GemmDeviceArgs& a, int ctas, int iters, int num_sms, cudaStream_t stream) {
+        if (int rc = configure()) return rc;
+        // split-K over a thread-block cluster when the tile grid leaves most SMs idle (small-M, weight-streaming
+        // layers): the largest cluster size whose clusters are all co-resident, with >= 2 k-iterations per rank
+        int S = 1;
+        if (ctas * 2 <= num_sms && iters >= 4) {
+            for (int c = 8; c >= 2; --c) {
+                if (c * 2 > iters) continue;
+                const int per = (iters + c - 1) / c;
+                if ((iters + per - 1) / per != c) continue;       // every rank must own at least one iteration
+                if (max_clusters(c) >= ctas) {
+                    S = c;
+                    break;
+                }
+            }
+        }
+        a.splits = S;
+        if (S == 1) {
+            const int grid = ctas < num_sms ? ctas : num_sms;
+            gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(a);
+        } else {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(ctas * S, 1, 1);
+            cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = SM::TOTAL;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = S;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, a));
+        }
+        LTT_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+};
 
 int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, cudaStream_t stream) {
     GemmDeviceArgs a;
@@ -462,33 +653,26 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     a.iters_total = iters;
     a.epi = p.epi;
 
-    // tile width: keep N tiles exact where possible (320 = 2 x 160), GEGLU needs value|gate halves inside a tile.
+    // tile width: widest UMMA N that divides N (fewer operand bytes per flop); single-m-tile problems stream weights
+    // from DRAM, so they get narrow tiles (more CTAs pulling bandwidth).  GEGLU tiles are groups of 128 packed rows.
     int BN;
     const bool geglu = p.epi.act == ACT_GEGLU;
-    if (geglu) BN = 128;
-    else if (p.N % 160 == 0 && p.N % 128 != 0) BN = 160;
-    else if (p.N <= 64) BN = 64;
+    if (geglu) BN = (p.N % 256 == 0 && mtiles > 1) ? 256 : 128;
+    else if (mtiles == 1 && p.N % 64 == 0) BN = 64;
+    else if (p.N % 256 == 0) BN = 256;
+    else if (p.N % 160 == 0) BN = 160;
+    else if (p.N % 128 == 0) BN = 128;
+    else if (p.N <= 64 || p.N % 64 == 0) BN = 64;
     else BN = 128;
+    if (geglu && p.N % 128 != 0) {
+        set_error("gemm: GEGLU needs N %% 128 == 0 (N=%d)", p.N);
+        return -1;
+    }
     const int ntiles = (p.N + BN - 1) / BN;
 
-    // split-K when the tile grid cannot fill the machine (small-M, weight-streaming layers)
-    int splits = 1;
     const int ctas = mtiles * ntiles;
-    if (ctas < num_sms && iters >= 8) {
-        splits = (2 * num_sms + ctas - 1) / ctas;
-        if (splits > iters / 4) splits = iters / 4;
-        if (splits > 32) splits = 32;
-        if (splits < 1) splits = 1;
-        // every z must own at least one iteration
-        int per = (iters + splits - 1) / splits;
-        splits = (iters + per - 1) / per;
-        const size_t need = (size_t)ctas * splits * BM * BN * sizeof(float);
-        if (need > ws.partial_bytes || ctas > ws.n_counters) splits = 1;
-    }
-    a.splits = splits;
-    a.partials = ws.partials;
-    a.counters = ws.counters;
-
+    a.mtiles = mtiles;
+    a.ntiles = ntiles;
     {
         uint64_t dims[2] = {(uint64_t)p.Ktot, (uint64_t)p.N};
         uint64_t str[1] = {(uint64_t)p.Ktot};
@@ -496,11 +680,12 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
         int rc = make_tmap_f16(&a.bmap, p.w, 2, dims, str, box);
         if (rc) return rc;
     }
-    dim3 grid(ntiles, mtiles, splits);
+    (void)ws;
     switch (BN) {
-        case 64: return launch_variant<64, 4>(a, grid, stream);
-        case 128: return launch_variant<128, 3>(a, grid, stream);
-        case 160: return launch_variant<160, 3>(a, grid, stream);
+        case 64: return Variant<64, 6>::launch(a, ctas, iters, num_sms, stream);
+        case 128: return Variant<128, 6>::launch(a, ctas, iters, num_sms, stream);
+        case 160: return Variant<160, 5>::launch(a, ctas, iters, num_sms, stream);
+        case 256: return Variant<256, 4>::launch(a, ctas, iters, num_sms, stream);
     }
     set_error("gemm: no kernel variant for BN=%d", BN);
     return -1;

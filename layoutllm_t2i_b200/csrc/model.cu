@@ -127,6 +127,10 @@ struct ltt_model {
     float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
     GemmWorkspace ws;
     int64_t launches = 0;
+    // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
+    struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
     // debug taps (ltt_debug_set_taps): named fp32 copies of intermediate activations
     struct Tap { std::string name; int64_t offset, rows, cols; };
     float* tap_buf = nullptr;
@@ -426,6 +430,25 @@ static int build_plan(ltt_model* m) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------ profiling
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_GN = 2, PC_LN = 3, PC_FORWARD = 4, PC_COUNT = 5 };
+struct ProfScope {
+    ltt_model* m;
+    cudaStream_t st;
+    int idx = -1;
+    ProfScope(ltt_model* m_, cudaStream_t st_, int cls, double flops, double bytes) : m(m_), st(st_) {
+        if (!m->prof_on) return;
+        ltt_model::ProfRec r{cls, flops, bytes, nullptr, nullptr};
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+        cudaEventRecord(r.e0, st);
+        m->prof.push_back(r);
+        idx = (int)m->prof.size() - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(m->prof[idx].e1, st);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------------ debug taps
 static int tap(ltt_model* m, cudaStream_t st, const std::string& name, const void* p, int dtype, int64_t rows, int64_t cols) {
     if (!m->tap_buf) return 0;
@@ -459,6 +482,11 @@ struct Run {
         p.epi = epi;
         if (!p.epi.bias) p.epi.bias = w.bias;
         m->launches++;
+        const double Mrows = (double)p.B * p.H * p.W;
+        const double nout = p.epi.act == ACT_GEGLU ? N / 2 : N;
+        ProfScope ps(m, st, PC_GEMM, 2.0 * Mrows * N * p.Ktot,
+                     2.0 * (Mrows * p.Ktot / (srcs.begin()->taps == 9 ? 9.0 : 1.0) + (double)N * p.Ktot) +
+                         Mrows * nout * (p.epi.out_dtype == DT_F32 ? 4.0 : 2.0));
         return gemm_tc_launch(p, m->ws, m->sms, st);
     }
 };
@@ -471,6 +499,7 @@ static GemmEpilogue epi_out(void* out, int ldo, int dtype = DT_F16) {
 
 static int groupnorm(ltt_model* m, cudaStream_t st, const __half* x0, int c0, const __half* x1, int c1, int B, int HW,
                      const Norm& n, float eps, int silu, __half* out) {
+    ProfScope ps(m, st, PC_GN, 0.0, (double)B * HW * (c0 + c1) * 2.0 * 3.0);
     RC(gn_stats_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, st));
     RC(gn_apply_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, n.g, n.b, eps, silu, out, st));
     m->launches += 3;
@@ -518,11 +547,14 @@ static int attention(ltt_model* m, cudaStream_t st, const StW& s, int B, const _
     p.q = q; p.rows_q = rows_q; p.k = k; p.rows_k = rows_k; p.vt = vt; p.pitch_v = pitch_v;
     p.out = out; p.ldo = s.C; p.scale = 1.0f / sqrtf((float)s.d);
     m->launches++;
+    ProfScope ps(m, st, PC_ATTN, 4.0 * B * s.heads * (double)nq * nk * s.d,
+                 2.0 * B * s.C * (2.0 * nq + 2.0 * nk));
     return attn_tc_launch(p, st);
 }
 
 static int ln(ltt_model* m, cudaStream_t st, const void* x, int dt, int M, int C, const Norm& n, __half* o16, float* o32) {
     m->launches++;
+    ProfScope ps(m, st, PC_LN, 0.0, (double)M * C * ((dt == DT_F32 ? 4.0 : 2.0) + (o16 ? 2.0 : 0.0) + (o32 ? 4.0 : 0.0)));
     return layernorm_launch(x, dt, M, C, n.g, n.b, 1e-5f, o16, o32, st);
 }
 
@@ -653,6 +685,7 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
     Run r{m, st, B};
     m->taps.clear();
     m->tap_used = 0;
+    ProfScope ps_fw(m, st, PC_FORWARD, 0.0, 0.0);
     // time embedding -> SiLU(emb) -> all emb_layers at once
     RC(timestep_embed_launch(t, B, mc, m->temb16, st));
     m->launches++;
@@ -1081,6 +1114,35 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
 }
 
 int64_t ltt_launch_count(const ltt_model* m) { return m ? m->launches : 0; }
+
+int ltt_profile_enable(ltt_model* m, int on) {
+    if (!m) return -1;
+    for (auto& r : m->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    m->prof.clear();
+    m->prof_on = on != 0;
+    return 0;
+}
+
+int ltt_profile_report(ltt_model* m, int cls, double* ms, double* flops, double* bytes, int64_t* launches) {
+    if (!m || cls < 0 || cls >= PC_COUNT) return -1;
+    LTT_CUDA_OK(cudaDeviceSynchronize());
+    double t = 0, f = 0, b = 0;
+    int64_t n = 0;
+    for (auto& r : m->prof) {
+        if (r.cls != cls) continue;
+        float e = 0;
+        if (cudaEventElapsedTime(&e, r.e0, r.e1) != cudaSuccess) continue;
+        t += e; f += r.flops; b += r.bytes; ++n;
+    }
+    if (ms) *ms = t;
+    if (flops) *flops = f;
+    if (bytes) *bytes = b;
+    if (launches) *launches = n;
+    return 0;
+}
 
 int ltt_debug_set_taps(ltt_model* m, float* buf, int64_t capacity_elems) {
     if (!m) return -1;

@@ -133,6 +133,20 @@ class Engine:
                                               L.stream_ptr()), "ltt_plms_sample")
         return xx
 
+    PROFILE_CLASSES = ("gemm_tc", "attn_tc", "groupnorm", "layernorm", "forward")
+
+    def profile(self, on: bool) -> None:
+        L.check(self._lib.ltt_profile_enable(self._h, int(on)), "ltt_profile_enable")
+
+    def profile_report(self) -> dict:
+        """{class: {ms, flops, bytes, launches}} of the launches since profile(True) (CUDA events on the launch stream)."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_CLASSES):
+            ms, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+            L.check(self._lib.ltt_profile_report(self._h, i, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)), "ltt_profile_report")
+            out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=n.value)
+        return out
+
     def forward_with_taps(self, x, timesteps, alpha_scale=1.0, capacity_elems=1 << 28):
         """Debug: forward + {name: fp32 [rows, cols]} of the intermediate activations (parity tests)."""
         buf = torch.empty(capacity_elems, device=self.device)
