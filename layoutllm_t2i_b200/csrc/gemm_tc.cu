@@ -24,7 +24,8 @@ namespace ltt {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 2 epilogue warpgroups
+constexpr int EPI_THREADS = 256;
 
 struct GemmDeviceArgs {
     CUtensorMap amap[3];
@@ -58,40 +59,40 @@ struct RowInfo {
     bool valid;
 };
 
-// Residual / time-embedding operands of one row for 32 consecutive output columns, fetched BEFORE the accumulator
+// Residual / time-embedding operands of one row for 16 consecutive output columns, fetched BEFORE the accumulator
 // is read so their latency hides behind the TMEM load (and behind the previous chunk's arithmetic).
 struct RowOperands {
-    uint4 res[8];      // fp16: res[0..3] hold 32 halves; fp32: res[0..7] hold 32 floats
-    uint4 rv[4];       // 32 halves of the per-batch row vector
+    uint4 res[4];      // fp16: res[0..1] hold 16 halves; fp32: res[0..3] hold 16 floats
+    uint4 rv[2];       // 16 halves of the per-batch row vector
 };
 
 __device__ __forceinline__ void fetch_operands(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, RowOperands& o) {
     if (!ri.valid || n >= Nout || e.out_mode == OUT_QKV) return;
-    // Nout is a multiple of 8; a 32-column chunk may end past Nout only in whole groups of 8
+    // Nout is a multiple of 8; a 16-column chunk may end past Nout only in whole groups of 8
     if (e.res) {
         if (e.res_dtype == DT_F16) {
             const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.res) + (size_t)ri.m * e.ldr + n);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
                 if (n + 8 * i < Nout) o.res[i] = p[i];
         } else {
             const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.res) + (size_t)ri.m * e.ldr + n);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
                 if (n + 4 * i < Nout) o.res[i] = p[i];
         }
     }
     if (e.rowvec) {
         const uint4* p = reinterpret_cast<const uint4*>(e.rowvec + (size_t)ri.b * e.ld_rowvec + n);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
             if (n + 8 * i < Nout) o.rv[i] = p[i];
     }
 }
 
 // Fused epilogue on 8 consecutive output columns [n, n+8) of row `ri`: v = raw fp32 accumulators (GEGLU: value half,
 // g = gate half), bv / bg = the matching bias values (already in registers), j = index of the group inside the
-// 32-column chunk whose operands are in `o`.  Rounding points follow the fp16-autocast reference: each Linear/Conv
+// 16-column chunk whose operands are in `o`.  Rounding points follow the fp16-autocast reference: each Linear/Conv
 // output is rounded to fp16 before the next elementwise op.
 __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
                                                 const float (&g)[8], const float (&bv)[8], const float (&bg)[8],
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;     // 2
-    uint64_t* acc_empty = acc_full + 2;          // 2 (count 128)
+    uint64_t* acc_empty = acc_full + 2;          // 2 (count EPI_THREADS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
+            mbar_init(&acc_empty[i], EPI_THREADS);
         }
         mbar_fence_init();
     }
@@ -292,10 +293,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue warps (2..5)
+        // ---------------------------------------------------------------- epilogue warps (2..9): two warpgroups, each
+        // thread owns one tile row (TMEM lane) and its warpgroup's share of the 32-column chunks
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;            // tile row
-        const int et = threadIdx.x - 64;        // 0..127
+        const int wg = (warp - 2) >> 2;         // 0 / 1
+        const int et = threadIdx.x - 64;        // 0..255
         const GemmEpilogue& e = args.epi;
         const bool geglu = e.act == ACT_GEGLU;
         const int Nout = geglu ? args.N / 2 : args.N;
@@ -321,8 +324,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const int ncols = geglu ? BN / 2 : BN;
             const int nbase = geglu ? n0 / 2 : n0;
             // stage the bias of this tile in shared memory (value half, then gate half for GEGLU)
-            named_bar_sync(2, 128);             // previous unit's readers are done with bias_s
-            for (int c = et; c < BN; c += 128) {
+            named_bar_sync(2, EPI_THREADS);     // previous unit's readers are done with bias_s
+            for (int c = et; c < BN; c += EPI_THREADS) {
                 float bvv = 0.f;
                 if (e.bias) {
                     if (geglu) {
@@ -335,8 +338,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 bias_s[c] = bvv;
             }
             RowOperands opA, opB;
-            if (args.splits == 1) fetch_operands(e, ri, nbase, Nout, opA);
-            named_bar_sync(2, 128);
+            if (args.splits == 1) fetch_operands(e, ri, nbase + 16 * wg, Nout, opA);
+            named_bar_sync(2, EPI_THREADS);
             const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
 
             mbar_wait(&acc_full[buf], (u >> 1) & 1);
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 float* part = reinterpret_cast<float*>(smem);
                 fence_async_smem();
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = 32 * wg; c < BN; c += 64) {
                     uint32_t v[32];
                     tmem_ld32(trow + c, v);
                     tmem_ld_wait();
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                 for (int zz = 0; zz < 8; ++zz) peer[zz] = zz < S ? dsmem_map(part_addr, zz) : 0u;
 #pragma unroll 1
-                for (int g = g0; g < g1; ++g) {
+                for (int g = g0 + wg; g < g1; g += 2) {
                     const int c = g * 8;
                     const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
                     RowOperands o;
@@ -410,31 +413,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0);
                 }
             } else {
-                // one 32-column chunk: accumulators -> fused epilogue -> global
+                // one 16-column chunk: accumulators -> fused epilogue -> global
                 auto process = [&](int c, const RowOperands& o) {
-                    float va[32], ga[32];
                     // column of the value / gate accumulator inside the tile for output column c + i
                     const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
-                    uint32_t v[32];
-                    tmem_ld32(trow + vcol, v);
-                    if (geglu) {
-                        uint32_t g[32];
-                        tmem_ld32(trow + vcol + 64, g);
-                        tmem_ld_wait();
+                    uint32_t v[16], g[16];
+                    tmem_ld16(trow + vcol, v);
+                    if (geglu) tmem_ld16(trow + vcol + 64, g);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) ga[i] = __uint_as_float(g[i]);
-                    } else {
-                        tmem_ld_wait();
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) va[i] = __uint_as_float(v[i]);
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
+                    for (int h = 0; h < 2; ++h) {
                         float v8[8], g8[8], bv[8], bg[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            v8[i] = va[h * 8 + i];
-                            g8[i] = geglu ? ga[h * 8 + i] : 0.f;
+                            v8[i] = __uint_as_float(v[h * 8 + i]);
+                            g8[i] = geglu ? __uint_as_float(g[h * 8 + i]) : 0.f;
                             bv[i] = bias_s[c + h * 8 + i];
                             bg[i] = geglu ? bias_s[ncols + c + h * 8 + i] : 0.f;
                         }
@@ -442,7 +435,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     }
                 };
 #pragma unroll 1
-                for (int c = 0; c < ncols; c += 64) {
+                for (int c = 16 * wg; c < ncols; c += 64) {
                     if (c + 32 < ncols) fetch_operands(e, ri, nbase + c + 32, Nout, opB);
                     process(c, opA);
                     if (c + 32 < ncols) {

@@ -10,6 +10,7 @@
 // stream switches to fp32 after the relation fusion exactly where CUDA autocast does in the reference; weights are
 // repacked once (ltt_finalize) to K-major fp16 [N, K] matrices in the K order the TMA gather walks.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -127,6 +128,12 @@ struct ltt_model {
     float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
     GemmWorkspace ws;
     int64_t launches = 0;
+    // CUDA graphs of the UNet evaluation, keyed by (gate scale, first-conv variant, grounded rows)
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    std::map<uint64_t, GraphEntry> graphs;
+    std::map<uint64_t, int> graph_seen;
+    cudaStream_t capture_stream = nullptr;
+    bool use_graphs = true;
     // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
     struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
     bool prof_on = false;
@@ -773,8 +780,62 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------ graph replay
+static void drop_graphs(ltt_model* m) {
+    for (auto& kv : m->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    m->graphs.clear();
+    m->graph_seen.clear();
+}
+
+// One UNet evaluation from the static buffers x_in / t_in into eps_buf.  The ~600-750 launches of an evaluation are
+// captured once per (gate scale, first-conv variant) into a CUDA graph -- all operand addresses are library-owned and
+// stable between ltt_set_conditioning geometry changes -- and replayed on the caller's stream.  The first call of a key
+// runs eagerly (sets function attributes / occupancy caches that must not happen during capture).
+static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st) {
+    if (!m->use_graphs || m->tap_buf || m->prof_on) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+    uint32_t abits;
+    memcpy(&abits, &alpha_scale, 4);
+    const uint64_t key = (uint64_t)abits | ((uint64_t)(m->sd_conv_w ? 1 : 0) << 32) | ((uint64_t)m->n_grounded << 33);
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+        if (m->graph_seen[key]++ == 0) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+        if (!m->capture_stream) LTT_CUDA_OK(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
+        const int64_t l0 = m->launches;
+        LTT_CUDA_OK(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, m->capture_stream);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &g);
+        const int64_t nl = m->launches - l0;
+        m->launches = l0;
+        if (rc || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (rc) return rc;
+            // capture not possible: stay on the eager path
+            m->use_graphs = false;
+            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+        }
+        ltt_model::GraphEntry ge;
+        const cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            m->use_graphs = false;
+            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+        }
+        ge.launches = nl;
+        if (m->graphs.size() >= 16) drop_graphs(m);
+        it = m->graphs.emplace(key, ge).first;
+    }
+    LTT_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    m->launches += it->second.launches;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------ conditioning
 static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n_rel) {
+    drop_graphs(m);
     m->carena.release();
     m->qbuf.clear(); m->kbuf.clear(); m->rects.clear(); m->skips.clear();
     const ltt_unet_config& c = m->cfg;
@@ -909,6 +970,7 @@ int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
     m->cfg = *cfg;
     m->device = device;
     LTT_CUDA_OK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device));
+    m->use_graphs = getenv("LTT_NO_GRAPH") == nullptr;     // debugging / per-launch profiling: eager launches
     *out = m;
     return 0;
 }
@@ -917,6 +979,8 @@ void ltt_destroy(ltt_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
+    drop_graphs(m);
+    if (m->capture_stream) cudaStreamDestroy(m->capture_stream);
     m->warena.release();
     m->carena.release();
     for (auto& kv : m->params) cudaFree(kv.second.dev);
@@ -948,22 +1012,31 @@ int ltt_load_param(ltt_model* m, const char* key, const float* data, const int64
 int ltt_finalize(ltt_model* m) {
     if (!m) return -1;
     LTT_CUDA_OK(cudaSetDevice(m->device));
+    drop_graphs(m);
     RC(build_plan(m));
     m->finalized = true;
     m->B = 0;   // conditioning caches depend on the packed weights
     return 0;
 }
 
-int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int is_host) {
-    if (!m) return -1;
+static int set_first_conv_on(ltt_model* m, const float* weight, const float* bias, int is_host, cudaStream_t st) {
     const size_t nw = (size_t)m->cfg.model_channels * m->cfg.in_channels * 9, nb = m->cfg.model_channels;
     if (!m->sd_conv_w) {
         LTT_CUDA_OK(cudaMalloc(&m->sd_conv_w, nw * 4));
         LTT_CUDA_OK(cudaMalloc(&m->sd_conv_b, nb * 4));
     }
     const cudaMemcpyKind k = is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    LTT_CUDA_OK(cudaMemcpy(m->sd_conv_w, weight, nw * 4, k));
-    LTT_CUDA_OK(cudaMemcpy(m->sd_conv_b, bias, nb * 4, k));
+    LTT_CUDA_OK(cudaMemcpyAsync(m->sd_conv_w, weight, nw * 4, k, st));
+    LTT_CUDA_OK(cudaMemcpyAsync(m->sd_conv_b, bias, nb * 4, k, st));
+    return 0;
+}
+
+int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int is_host) {
+    if (!m) return -1;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    LTT_CUDA_OK(cudaDeviceSynchronize());     // in-flight evaluations may still read the previous tensors
+    RC(set_first_conv_on(m, weight, bias, is_host, 0));
+    LTT_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -1045,7 +1118,18 @@ int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, float
                      void* stream) {
     if (!m) return -1;
     LTT_CUDA_OK(cudaSetDevice(m->device));
-    return forward_impl(m, x, timesteps, alpha_scale, eps_out, (cudaStream_t)stream);
+    if (!m->finalized || m->B == 0) {
+        set_error("ltt_unet_forward: call ltt_finalize and ltt_set_conditioning first");
+        return -8;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const ltt_unet_config& c = m->cfg;
+    const size_t nin = (size_t)m->B * c.in_channels * m->H * m->W, nout = (size_t)m->B * c.out_channels * m->H * m->W;
+    LTT_CUDA_OK(cudaMemcpyAsync(m->x_in, x, nin * 4, cudaMemcpyDeviceToDevice, st));
+    LTT_CUDA_OK(cudaMemcpyAsync(m->t_in, timesteps, (size_t)m->B * 4, cudaMemcpyDeviceToDevice, st));
+    RC(forward_cached(m, alpha_scale, st));
+    LTT_CUDA_OK(cudaMemcpyAsync(eps_out, m->eps_buf, nout * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* timesteps_host,
@@ -1065,15 +1149,10 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
     LTT_CUDA_OK(cudaSetDevice(m->device));
     const ltt_unet_config& c = m->cfg;
     const size_t n = (size_t)Bimg * c.in_channels * m->H * m->W;
-    std::vector<float> tvals(m->B);
     auto eval = [&](const float* x, int tval) -> int {
-        // [cond ; uncond] batch of the same latent
-        LTT_CUDA_OK(cudaMemcpyAsync(m->x_in, x, n * 4, cudaMemcpyDeviceToDevice, st));
-        if (cfg) LTT_CUDA_OK(cudaMemcpyAsync(m->x_in + n, x, n * 4, cudaMemcpyDeviceToDevice, st));
-        for (auto& v : tvals) v = (float)tval;
-        LTT_CUDA_OK(cudaMemcpyAsync(m->t_in, tvals.data(), m->B * 4, cudaMemcpyHostToDevice, st));
-        LTT_CUDA_OK(cudaStreamSynchronize(st));   // tvals is pageable host memory reused next step
-        return 0;
+        // [cond ; uncond] batch of the same latent + timestep vector, written on the device (no host sync in the loop)
+        m->launches++;
+        return plms_prep_launch(x, m->x_in, n, cfg ? 2 : 1, m->t_in, m->B, (float)tval, st);
     };
     LTT_CUDA_OK(cudaMemcpyAsync(m->pl_x, x_inout, n * 4, cudaMemcpyDeviceToDevice, st));
     int nold = 0;
@@ -1083,19 +1162,19 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
         const int index = S - 1 - i;
         const float scale = alpha_sched_host ? alpha_sched_host[i] : 1.0f;
         if (alpha_sched_host && scale == 0.0f && sd_conv_weight && !m->sd_conv_w)
-            RC(ltt_set_first_conv(m, sd_conv_weight, sd_conv_bias, 0));
+            RC(set_first_conv_on(m, sd_conv_weight, sd_conv_bias, 0, st));
         const int tv = timesteps_host[index];
         const int tnext = timesteps_host[std::max(index - 1, 0)];
         const float a_t = alphas_host[index], a_prev = alphas_prev_host[index], s1m = sqrt_1m_alphas_host[index];
         RC(eval(m->pl_x, tv));
-        RC(forward_impl(m, m->x_in, m->t_in, scale, m->eps_buf, st));
+        RC(forward_cached(m, scale, st));
         float* e_cur = m->pl_e[ring];
         if (nold == 0) {
             // Euler predictor, second evaluation at t_next, e' = (e_t + e_next) / 2, step from the ORIGINAL x
             RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 0, m->pl_x, e_cur, nullptr, nullptr, nullptr,
                                   nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
             RC(eval(m->pl_xsave, tnext));
-            RC(forward_impl(m, m->x_in, m->t_in, scale, m->eps_buf, st));
+            RC(forward_cached(m, scale, st));
             RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 1, m->pl_x, nullptr, e_cur, nullptr, nullptr,
                                   nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
         } else {

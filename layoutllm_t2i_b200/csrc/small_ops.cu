@@ -42,36 +42,53 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int c0, int ld0, 
     for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&stats[(size_t)b * 64 + i], sh[i]);
 }
 
-// out[b, p, c] = act(r16((x - mean) * rstd * gamma + beta)), optionally reading x at (y/2, x/2) (nearest 2x
-// upsample of the *output* grid is NOT done here; see upsample2x).  fp16 NHWC out with pitch C.
+// out[b, p, c] = act(r16((x - mean) * rstd * gamma + beta)); fp16 NHWC out with pitch C.  Each thread handles 8
+// consecutive channels (one 16-byte vector); mean / rstd of every (batch, group) are decoded once per block.
 __global__ void gn_apply_kernel(const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int c1,
-                                int ld1, int HW, int cpg, const double* __restrict__ stats,
+                                int ld1, int B, int HW, int cpg, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                __half* __restrict__ out, size_t total_pairs) {
-    const int C = c0 + c1, P = C >> 1;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pairs; i += (size_t)gridDim.x * blockDim.x) {
-        const int cp = (int)(i % P);
-        const size_t row = i / P;            // b*HW + p
+                                __half* __restrict__ out, size_t total_vecs) {
+    extern __shared__ float2 mr[];    // [B*32] (mean, rstd)
+    for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+        const double n = (double)cpg * HW;
+        const double mean = stats[2 * i] / n;
+        double var = stats[2 * i + 1] / n - mean * mean;
+        if (var < 0) var = 0;
+        mr[i] = make_float2((float)mean, rsqrtf((float)var + eps));
+    }
+    __syncthreads();
+    const int C = c0 + c1, V = C >> 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % V);
+        const size_t row = i / V;            // b*HW + p
         const int b = (int)(row / HW);
-        const int c = cp * 2;
+        const int c = cv * 8;
         const __half* src;
         int ld, cc;
         if (c < c0) { src = x0; ld = ld0; cc = c; } else { src = x1; ld = ld1; cc = c - c0; }
-        const int g = c / cpg;
-        const double n = (double)cpg * HW;
-        const double mean = stats[(size_t)b * 64 + 2 * g] / n;
-        double var = stats[(size_t)b * 64 + 2 * g + 1] / n - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = rsqrtf((float)var + eps);
-        const float mu = (float)mean;
-        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(src + row * ld + cc));
-        float a = r16f((v.x - mu) * rstd * gamma[c] + beta[c]);
-        float d = r16f((v.y - mu) * rstd * gamma[c + 1] + beta[c + 1]);
-        if (silu) {
-            a = siluf(a);
-            d = siluf(d);
+        const uint4 u = *reinterpret_cast<const uint4*>(src + row * ld + cc);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        float g[8], bt[8];
+        {
+            const float4 ga = *reinterpret_cast<const float4*>(gamma + c), gb = *reinterpret_cast<const float4*>(gamma + c + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(beta + c), bb = *reinterpret_cast<const float4*>(beta + c + 4);
+            g[0] = ga.x; g[1] = ga.y; g[2] = ga.z; g[3] = ga.w; g[4] = gb.x; g[5] = gb.y; g[6] = gb.z; g[7] = gb.w;
+            bt[0] = ba.x; bt[1] = ba.y; bt[2] = ba.z; bt[3] = ba.w; bt[4] = bb.x; bt[5] = bb.y; bt[6] = bb.z; bt[7] = bb.w;
         }
-        *reinterpret_cast<__half2*>(out + row * C + c) = __floats2half2_rn(a, d);
+        __half2 o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 m = mr[b * 32 + (c + 2 * k) / cpg];     // cpg is even: a channel pair never straddles groups
+            const float2 v = __half22float2(h[k]);
+            float a = r16f((v.x - m.x) * m.y * g[2 * k] + bt[2 * k]);
+            float d = r16f((v.y - m.x) * m.y * g[2 * k + 1] + bt[2 * k + 1]);
+            if (silu) {
+                a = siluf(a);
+                d = siluf(d);
+            }
+            o[k] = __floats2half2_rn(a, d);
+        }
+        *reinterpret_cast<uint4*>(out + row * C + c) = *reinterpret_cast<uint4*>(o);
     }
 }
 
@@ -94,15 +111,40 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
                     const double* stats, const float* gamma, const float* beta, float eps, int silu, __half* out,
                     cudaStream_t st) {
     const int C = c0 + c1, cpg = C / groups;
-    const size_t total = (size_t)B * HW * (C / 2);
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    gn_apply_kernel<<<blocks, 256, 0, st>>>(x0, c0, ld0, x1, c1, ld1, HW, cpg, stats, gamma, beta, eps, silu, out, total);
+    if (C % 8 || c0 % 8 || ld0 % 8 || (c1 && ld1 % 8) || B > 64) {
+        set_error("groupnorm: unsupported geometry C=%d c0=%d B=%d", C, c0, B);
+        return -1;
+    }
+    const size_t total = (size_t)B * HW * (C / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    gn_apply_kernel<<<blocks, 256, (size_t)B * 32 * sizeof(float2), st>>>(x0, c0, ld0, x1, c1, ld1, B, HW, cpg, stats, gamma, beta,
+                                                                         eps, silu, out, total);
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row; fp32 statistics (two pass in registers); writes fp16 and/or fp32.
+// One warp per row, 16-byte vector loads / stores (8 halves or 2 x 4 floats per lane per step); fp32 statistics
+// (two pass in registers); writes fp16 and/or fp32.
+template <typename T>
+__device__ __forceinline__ void ln_load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ln_load8<__half>(const __half* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+template <>
+__device__ __forceinline__ void ln_load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, __half* __restrict__ out16,
@@ -111,41 +153,64 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const fl
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
     const T* xr = x + (size_t)row * C;
-    float v[40];   // C <= 1280
-    const int per = C / 32;   // host checks C % 32 == 0, per <= 40
+    const int nvec = C >> 3;           // host checks C % 8 == 0, C <= 1280 (<= 5 vectors per lane)
+    float v[5][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 40; ++i)
-        if (i < per) {
-            v[i] = (float)xr[i * 32 + lane];
-            s += v[i];
+    for (int i = 0; i < 5; ++i) {
+        const int j = i * 32 + lane;
+        if (j < nvec) {
+            ln_load8<T>(xr + j * 8, v[i]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[i][k];
         }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / C;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 40; ++i)
-        if (i < per) {
-            const float d = v[i] - mean;
-            ss += d * d;
+    for (int i = 0; i < 5; ++i) {
+        const int j = i * 32 + lane;
+        if (j < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float d = v[i][k] - mean;
+                ss += d * d;
+            }
         }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / C + eps);
 #pragma unroll
-    for (int i = 0; i < 40; ++i)
-        if (i < per) {
-            const int c = i * 32 + lane;
-            const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            if (out16) out16[(size_t)row * C + c] = __float2half_rn(y);
-            if (out32) out32[(size_t)row * C + c] = y;
+    for (int i = 0; i < 5; ++i) {
+        const int j = i * 32 + lane;
+        if (j < nvec) {
+            const int c = j * 8;
+            float g[8], bt[8], y[8];
+            ln_load8<float>(gamma + c, g);
+            ln_load8<float>(beta + c, bt);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = (v[i][k] - mean) * rstd * g[k] + bt[k];
+            if (out16) {
+                __half2 h[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(y[2 * k], y[2 * k + 1]);
+                *reinterpret_cast<uint4*>(out16 + (size_t)row * C + c) = *reinterpret_cast<uint4*>(h);
+            }
+            if (out32) {
+                float4* o = reinterpret_cast<float4*>(out32 + (size_t)row * C + c);
+                o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                o[1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
         }
+    }
 }
 
 int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
                      __half* out16, float* out32, cudaStream_t st) {
-    if (C % 32 || C / 32 > 40) {
+    if (C % 8 || C > 1280) {
         set_error("layernorm: unsupported C=%d", C);
         return -1;
     }
@@ -162,28 +227,54 @@ int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamm
 // ------------------------------------------------------------------------------------------------ first / last conv
 // input_blocks.0.0: Conv2d(4 -> Cout, 3x3, pad 1) on NCHW fp32 x; inputs and weights rounded to fp16 (autocast),
 // fp32 accumulate, NHWC fp16 out.  w: [Cout, Cin, 3, 3] fp32.
+constexpr int CIN_PIX = 16;   // pixels per block
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                int B, int Cin, int H, int W, int Cout, __half* __restrict__ out) {
-    extern __shared__ float patch[];   // [Cin*9]
-    const int pix = blockIdx.x;        // b*H*W + y*W + x
-    const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
-    for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
-        const int ci = i / 9, t = i % 9, yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+    extern __shared__ float smem_ci[];
+    const int K = Cin * 9;
+    float* patch = smem_ci;                                   // [CIN_PIX][K]
+    __half* wt = reinterpret_cast<__half*>(patch + CIN_PIX * K);   // [K][Cout], fp16-rounded weights
+    const int pix0 = blockIdx.x * CIN_PIX, total = B * H * W;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        const int co = i / K, k = i % K;                      // coalesced global read, transposed smem write
+        wt[k * Cout + co] = __float2half_rn(w[i]);
+    }
+    for (int i = threadIdx.x; i < CIN_PIX * K; i += blockDim.x) {
+        const int p = i / K, k = i % K, pix = pix0 + p;
         float v = 0.f;
-        if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = r16f(x[((size_t)(b * Cin + ci) * H + yy) * W + xs]);
+        if (pix < total) {
+            const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
+            const int ci = k / 9, t = k % 9, yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+            if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = r16f(x[((size_t)(b * Cin + ci) * H + yy) * W + xs]);
+        }
         patch[i] = v;
     }
     __syncthreads();
     for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-        float acc = 0.f;
-        for (int i = 0; i < Cin * 9; ++i) acc += patch[i] * r16f(w[(size_t)co * Cin * 9 + i]);
-        out[(size_t)pix * Cout + co] = __float2half_rn(acc + bias[co]);
+        float acc[CIN_PIX];
+#pragma unroll
+        for (int p = 0; p < CIN_PIX; ++p) acc[p] = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float ww = __half2float(wt[k * Cout + co]);
+#pragma unroll
+            for (int p = 0; p < CIN_PIX; ++p) acc[p] += patch[p * K + k] * ww;
+        }
+        const float bb = bias[co];
+#pragma unroll
+        for (int p = 0; p < CIN_PIX; ++p)
+            if (pix0 + p < total) out[(size_t)(pix0 + p) * Cout + co] = __float2half_rn(acc[p] + bb);
     }
 }
 
 int conv_in_launch(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
                    __half* out, cudaStream_t st) {
-    conv_in_kernel<<<B * H * W, 128, Cin * 9 * sizeof(float), st>>>(x, w, bias, B, Cin, H, W, Cout, out);
+    const int K = Cin * 9, total = B * H * W;
+    const size_t smem = (size_t)CIN_PIX * K * sizeof(float) + (size_t)K * Cout * sizeof(__half);
+    if (smem > 48 * 1024) {
+        set_error("conv_in: Cin=%d Cout=%d needs %zu B of shared memory", Cin, Cout, smem);
+        return -1;
+    }
+    conv_in_kernel<<<(total + CIN_PIX - 1) / CIN_PIX, 128, smem, st>>>(x, w, bias, B, Cin, H, W, Cout, out);
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -591,6 +682,24 @@ int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, i
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 4);
     plms_update_kernel<<<blocks, 256, 0, st>>>(eps_c, eps_u, guidance, use_cfg, mode, x, e_t_out, e_first, old1, old2,
                                                 old3, a_t, a_prev, sqrt_1m_at, x_out, n);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// UNet inputs of one sampler evaluation: x_in = [x ; x] (cond and uncond rows see the same latent, plms.py:116-122) and
+// the timestep vector, written on the device so the sampler loop never synchronises with the host.
+__global__ void plms_prep_kernel(const float* __restrict__ x, float* __restrict__ x_in, size_t n, int copies,
+                                 float* __restrict__ t_in, int B, float tval) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < (size_t)B) t_in[gid] = tval;
+    for (size_t i = gid; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        for (int c = 0; c < copies; ++c) x_in[(size_t)c * n + i] = v;
+    }
+}
+int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((std::max<size_t>(n, (size_t)B) + 255) / 256, 148 * 4);
+    plms_prep_kernel<<<blocks, 256, 0, st>>>(x, x_in, n, copies, t_in, B, tval);
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
