@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();     // programmatic dependent launch: see ltt_ptx.cuh
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -261,7 +263,7 @@ static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t 
         LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
     }
-    attn_tc_kernel<DPAD, DV, BKV><<<grid, ATT_THREADS, C::TOTAL, stream>>>(a);
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

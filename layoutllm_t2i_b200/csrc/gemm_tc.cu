@@ -15,6 +15,7 @@
 // diffusionmodules/openaimodel.py:155-194 (ResBlock convs, emb_layers, skip), :57-114 (Up/Downsample convs).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ltt_kernels.h"
 #include "ltt_ptx.cuh"
@@ -36,6 +37,7 @@ struct GemmDeviceArgs {
     int iters_total;
     int B, H, W, N;
     int tw, th, tiles_x, tiles_y;
+    int kind;                     // epilogue_kind(epi)
     int mtiles, ntiles, splits;   // splits > 1: one cluster of `splits` CTAs per tile, K range split by cluster rank
     GemmEpilogue epi;
 };
@@ -169,6 +171,107 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
     }
 }
 
+// ---- specialised epilogues: the model's GEMMs fall into a handful of epilogue shapes; each gets a branch-free inner
+// loop (the generic routine above costs ~12 issue slots per element, which made small-K GEMMs epilogue bound).
+// All produce bit-identical results to epilogue_group8 for their flag combination.
+enum : int { EK_GENERIC = 0, EK_F16 = 1, EK_GATE16 = 2, EK_GEGLU = 3, EK_QKV = 4, EK_RES32 = 5 };
+
+__host__ __device__ inline int epilogue_kind(const GemmEpilogue& e) {
+    if (e.out_mode == OUT_QKV) return (!e.bias && !e.act && !e.has_gate && !e.rowvec) ? EK_QKV : EK_GENERIC;
+    if (e.act == ACT_GEGLU) return (!e.res && !e.has_gate && !e.rowvec && e.out_dtype == DT_F16) ? EK_GEGLU : EK_GENERIC;
+    if (e.act != ACT_NONE || e.rowvec) return EK_GENERIC;
+    if (e.res && e.res_dtype == DT_F32) return e.has_gate ? EK_GENERIC : EK_RES32;
+    if (e.out_dtype != DT_F16) return EK_GENERIC;
+    if (e.has_gate) return e.res ? EK_GATE16 : EK_GENERIC;
+    return EK_F16;      // bias -> fp16, optional fp16 residual
+}
+
+template <int K>
+struct KindTag {
+    static constexpr int value = K;
+};
+
+template <int KIND>
+__device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
+                                           const float (&g)[8], const float* __restrict__ bs, const float* __restrict__ bsg,
+                                           const RowOperands& o, int j) {
+    if constexpr (KIND == EK_GENERIC) {
+        float bv[8], bg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bv[i] = bs[i];
+            bg[i] = e.act == ACT_GEGLU ? bsg[i] : 0.f;
+        }
+        epilogue_group8(e, ri, n, Nout, v, g, bv, bg, o, j);
+        return;
+    } else {
+        if (!ri.valid || n >= Nout) return;
+        __half2 h[4];
+        if constexpr (KIND == EK_F16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i] + bs[2 * i], v[2 * i + 1] + bs[2 * i + 1]);
+            if (e.res) {
+                const __half2* rh = reinterpret_cast<const __half2*>(&o.res[j]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __hadd2(h[i], rh[i]);     // one rounding of the exact sum
+            }
+        } else if constexpr (KIND == EK_GATE16) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&o.res[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 y = __half22float2(__floats2half2_rn(v[2 * i] + bs[2 * i], v[2 * i + 1] + bs[2 * i + 1]));
+                h[i] = __hadd2(__floats2half2_rn(e.gate * y.x, e.gate * y.y), rh[i]);
+            }
+        } else if constexpr (KIND == EK_GEGLU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2 val = __floats2half2_rn(v[2 * i] + bs[2 * i], v[2 * i + 1] + bs[2 * i + 1]);
+                const float2 gt = __half22float2(__floats2half2_rn(g[2 * i] + bsg[2 * i], g[2 * i + 1] + bsg[2 * i + 1]));
+                h[i] = __hmul2(val, __floats2half2_rn(gelu_erf_f(gt.x), gelu_erf_f(gt.y)));
+            }
+        } else if constexpr (KIND == EK_QKV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const int which = n / e.C + e.qkv_base, c = n % e.C;
+            const int t = ri.m - ri.b * e.tokens;
+            if (which == 2) {
+                __half* dst = e.vt + ((size_t)ri.b * e.C + c) * e.pitch_v + t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dst[(size_t)(2 * i) * e.pitch_v] = __low2half(h[i]);
+                    dst[(size_t)(2 * i + 1) * e.pitch_v] = __high2half(h[i]);
+                }
+            } else {
+                const int head = c / e.dhead, jj = c % e.dhead;
+                __half* base = which == 0 ? e.q + ((size_t)ri.b * e.rows_q + t) * (size_t)(e.dpad * (e.C / e.dhead))
+                                          : e.k + ((size_t)ri.b * e.rows_k + t) * (size_t)(e.dpad * (e.C / e.dhead));
+                *reinterpret_cast<uint4*>(base + head * e.dpad + jj) = *reinterpret_cast<uint4*>(h);
+            }
+            return;
+        } else if constexpr (KIND == EK_RES32) {
+            const float4 a = *reinterpret_cast<const float4*>(&o.res[2 * j]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&o.res[2 * j + 1]);
+            const float rr[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(__floats2half2_rn(v[2 * i] + bs[2 * i], v[2 * i + 1] + bs[2 * i + 1]));
+                y[2 * i] = f.x + rr[2 * i];
+                y[2 * i + 1] = f.y + rr[2 * i + 1];
+            }
+            if (e.out_dtype == DT_F32) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
+                op[0] = make_float4(y[0], y[1], y[2], y[3]);
+                op[1] = make_float4(y[4], y[5], y[6], y[7]);
+                return;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
 // Persistent, warp-specialised kernel.  Work unit = (output tile 128 x BN, K split).  Each CTA walks units
 // blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA issuer run ahead of the epilogue warps by up
 // to one unit because the fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of unit u
@@ -212,6 +315,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the predecessor's tail (programmatic dependent launch); from here on global memory
+    // written by it is read
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -413,35 +520,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0);
                 }
             } else {
-                // one 16-column chunk: accumulators -> fused epilogue -> global
-                auto process = [&](int c, const RowOperands& o) {
-                    // column of the value / gate accumulator inside the tile for output column c + i
-                    const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
-                    uint32_t v[16], g[16];
-                    tmem_ld16(trow + vcol, v);
-                    if (geglu) tmem_ld16(trow + vcol + 64, g);
-                    tmem_ld_wait();
+                // 16-column chunks: accumulators -> fused epilogue (specialised per epilogue kind) -> global
+                auto run_tile = [&](auto kind_tag) {
+                    constexpr int KIND = decltype(kind_tag)::value;
+                    auto process = [&](int c, const RowOperands& o) {
+                        // column of the value / gate accumulator inside the tile for output column c + i
+                        const int vcol = KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu) ? (c / 64) * 128 + (c % 64) : c;
+                        uint32_t v[16], g[16];
+                        tmem_ld16(trow + vcol, v);
+                        if (KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu)) tmem_ld16(trow + vcol + 64, g);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float v8[8], g8[8], bv[8], bg[8];
+                        for (int h = 0; h < 2; ++h) {
+                            float v8[8], g8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            v8[i] = __uint_as_float(v[h * 8 + i]);
-                            g8[i] = geglu ? __uint_as_float(g[h * 8 + i]) : 0.f;
-                            bv[i] = bias_s[c + h * 8 + i];
-                            bg[i] = geglu ? bias_s[ncols + c + h * 8 + i] : 0.f;
+                            for (int i = 0; i < 8; ++i) {
+                                v8[i] = __uint_as_float(v[h * 8 + i]);
+                                g8[i] = (KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu)) ? __uint_as_float(g[h * 8 + i]) : 0.f;
+                            }
+                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, o, h);
                         }
-                        epilogue_group8(e, ri, nbase + c + h * 8, Nout, v8, g8, bv, bg, o, h);
+                    };
+                    constexpr bool kFetch = KIND == EK_GENERIC || KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32;
+#pragma unroll 1
+                    for (int c = 16 * wg; c < ncols; c += 64) {
+                        if (kFetch && c + 32 < ncols) fetch_operands(e, ri, nbase + c + 32, Nout, opB);
+                        process(c, opA);
+                        if (c + 32 < ncols) {
+                            if (kFetch && c + 64 < ncols) fetch_operands(e, ri, nbase + c + 64, Nout, opA);
+                            process(c + 32, opB);
+                        }
                     }
                 };
-#pragma unroll 1
-                for (int c = 16 * wg; c < ncols; c += 64) {
-                    if (c + 32 < ncols) fetch_operands(e, ri, nbase + c + 32, Nout, opB);
-                    process(c, opA);
-                    if (c + 32 < ncols) {
-                        if (c + 64 < ncols) fetch_operands(e, ri, nbase + c + 64, Nout, opA);
-                        process(c + 32, opB);
-                    }
+                switch (args.kind) {
+                    case EK_F16: run_tile(KindTag<EK_F16>{}); break;
+                    case EK_GATE16: run_tile(KindTag<EK_GATE16>{}); break;
+                    case EK_GEGLU: run_tile(KindTag<EK_GEGLU>{}); break;
+                    case EK_QKV: run_tile(KindTag<EK_QKV>{}); break;
+                    case EK_RES32: run_tile(KindTag<EK_RES32>{}); break;
+                    default: run_tile(KindTag<EK_GENERIC>{}); break;
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[buf]);
@@ -471,6 +588,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("LTT_NO_PDL") ? 0 : 1;
+    return on != 0;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -589,7 +712,7 @@ struct Variant {
         a.splits = S;
         if (S == 1) {
             const int grid = ctas < num_sms ? ctas : num_sms;
-            gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, stream>>>(a);
+            LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
@@ -597,13 +720,15 @@ struct Variant {
             cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
             cfg.dynamicSmemBytes = SM::TOTAL;
             cfg.stream = stream;
-            cudaLaunchAttribute at[1];
+            cudaLaunchAttribute at[2];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = S;
             at[0].val.clusterDim.y = 1;
             at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = pdl_enabled() ? 2 : 1;
             LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, a));
         }
         LTT_CUDA_OK(cudaGetLastError());
@@ -645,6 +770,7 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     }
     a.iters_total = iters;
     a.epi = p.epi;
+    a.kind = epilogue_kind(p.epi);
 
     // tile width: widest UMMA N that divides N (fewer operand bytes per flop); single-m-tile problems stream weights
     // from DRAM, so they get narrow tiles (more CTAs pulling bandwidth).  GEGLU tiles are groups of 128 packed rows.

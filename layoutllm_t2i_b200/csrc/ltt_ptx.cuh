@@ -182,6 +182,13 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t addr) {
     return v;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the UNet sequence is launched with programmatic stream serialisation: it may start (prologue:
+// barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains, and blocks here until the
+// predecessor grid has completed and its writes are visible.  No global memory is touched before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

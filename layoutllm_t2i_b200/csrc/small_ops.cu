@@ -8,6 +8,7 @@
 // FourierEmbedder util.py:12-26, PositionNet text_grounding_net.py:26-43, RelationCrossAttention
 // attention.py:315-359, p_sample_plms models/diffusion/plms.py:110-163.
 #include "ltt_ops.h"
+#include "ltt_ptx.cuh"
 
 namespace ltt {
 
@@ -18,6 +19,8 @@ __device__ __forceinline__ float siluf(float x) { return x / (1.0f + __expf(-x))
 // stats[b][g] = {sum, sumsq} in double (zeroed by the caller).  Input = channel concat of up to two NHWC tensors.
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int c1,
                                 int ld1, int HW, int cpg, int strip, double* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double sh[64];
     const int b = blockIdx.y, C = c0 + c1, P = C >> 1;
     for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0.0;
@@ -48,6 +51,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int c0, int ld0, 
                                 int ld1, int B, int HW, int cpg, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                 __half* __restrict__ out, size_t total_vecs) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float2 mr[];    // [B*32] (mean, rstd)
     for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
         const double n = (double)cpg * HW;
@@ -102,7 +107,7 @@ int gn_stats_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
     LTT_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)B * 64 * sizeof(double), st));
     const int strip = HW >= 4096 ? 32 : (HW >= 1024 ? 16 : 8);
     dim3 grid((HW + strip - 1) / strip, B);
-    gn_stats_kernel<<<grid, 256, 0, st>>>(x0, c0, ld0, x1, c1, ld1, HW, cpg, strip, stats);
+    LTT_CUDA_OK(launch_k(gn_stats_kernel, dim3(grid), dim3(256), 0, st, x0, c0, ld0, x1, c1, ld1, HW, cpg, strip, stats));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -117,8 +122,8 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
     }
     const size_t total = (size_t)B * HW * (C / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-    gn_apply_kernel<<<blocks, 256, (size_t)B * 32 * sizeof(float2), st>>>(x0, c0, ld0, x1, c1, ld1, B, HW, cpg, stats, gamma, beta,
-                                                                         eps, silu, out, total);
+    LTT_CUDA_OK(launch_k(gn_apply_kernel, dim3(blocks), dim3(256), (size_t)B * 32 * sizeof(float2), st, x0, c0, ld0, x1, c1, ld1, B, HW, cpg, stats, gamma, beta,
+                                                                         eps, silu, out, total));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -149,6 +154,8 @@ template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, __half* __restrict__ out16,
                                  float* __restrict__ out32) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -217,9 +224,9 @@ int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamm
     const int wpb = 8;
     const int blocks = (M + wpb - 1) / wpb;
     if (x_dtype == DT_F16)
-        layernorm_kernel<__half><<<blocks, wpb * 32, 0, st>>>((const __half*)x, M, C, gamma, beta, eps, out16, out32);
+        LTT_CUDA_OK(launch_k(layernorm_kernel<__half>, dim3(blocks), dim3(wpb * 32), 0, st, (const __half*)x, M, C, gamma, beta, eps, out16, out32));
     else
-        layernorm_kernel<float><<<blocks, wpb * 32, 0, st>>>((const float*)x, M, C, gamma, beta, eps, out16, out32);
+        LTT_CUDA_OK(launch_k(layernorm_kernel<float>, dim3(blocks), dim3(wpb * 32), 0, st, (const float*)x, M, C, gamma, beta, eps, out16, out32));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -230,6 +237,8 @@ int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamm
 constexpr int CIN_PIX = 16;   // pixels per block
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                int B, int Cin, int H, int W, int Cout, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float smem_ci[];
     const int K = Cin * 9;
     float* patch = smem_ci;                                   // [CIN_PIX][K]
@@ -274,7 +283,7 @@ int conv_in_launch(const float* x, const float* w, const float* bias, int B, int
         set_error("conv_in: Cin=%d Cout=%d needs %zu B of shared memory", Cin, Cout, smem);
         return -1;
     }
-    conv_in_kernel<<<(total + CIN_PIX - 1) / CIN_PIX, 128, smem, st>>>(x, w, bias, B, Cin, H, W, Cout, out);
+    LTT_CUDA_OK(launch_k(conv_in_kernel, dim3((total + CIN_PIX - 1) / CIN_PIX), dim3(128), smem, st, x, w, bias, B, Cin, H, W, Cout, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -283,6 +292,8 @@ int conv_in_launch(const float* x, const float* w, const float* bias, int B, int
 // NCHW fp32 out (values rounded to fp16 as the autocast reference returns half).  One warp per pixel.
 __global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                                 int B, int H, int W, int C, int Cout, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pix >= B * H * W) return;
@@ -320,7 +331,7 @@ int conv_out_launch(const __half* x, const __half* w, const float* bias, int B, 
         return -1;
     }
     const int wpb = 8, total = B * H * W;
-    conv_out_kernel<<<(total + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, w, bias, B, H, W, C, Cout, out);
+    LTT_CUDA_OK(launch_k(conv_out_kernel, dim3((total + wpb - 1) / wpb), dim3(wpb * 32), 0, st, x, w, bias, B, H, W, C, Cout, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -328,6 +339,8 @@ int conv_out_launch(const __half* x, const __half* w, const float* bias, int B, 
 // ------------------------------------------------------------------------------------------------ resampling helpers
 // nearest 2x upsample, NHWC fp16, 16-byte vectors
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)B * 4 * H * W * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8);
@@ -342,13 +355,15 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 int upsample2x_launch(const __half* in, __half* out, int B, int H, int W, int C, cudaStream_t st) {
     const size_t total = (size_t)B * 4 * H * W * (C / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    upsample2x_kernel<<<blocks, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LTT_CUDA_OK(launch_k(upsample2x_kernel, dim3(blocks), dim3(256), 0, st, (const uint4*)in, (uint4*)out, B, H, W, C / 8));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 // stride-2 pad-1 3x3 patch gather: out[(b, oy, ox)][tap*C + c] = in[b, 2oy-1+ky, 2ox-1+kx, c] (0 outside)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)B * Ho * Wo * 9 * C8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -369,7 +384,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict
 int im2col_s2_launch(const __half* in, __half* out, int B, int H, int W, int C, cudaStream_t st) {
     const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    im2col_s2_kernel<<<blocks, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    LTT_CUDA_OK(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), 0, st, (const uint4*)in, (uint4*)out, B, H, W, C / 8));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -377,6 +392,8 @@ int im2col_s2_launch(const __half* in, __half* out, int B, int H, int W, int C, 
 // ------------------------------------------------------------------------------------------------ embeddings
 // timestep_embedding: [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half), fp32 math, fp16 out [B, dim]
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half = dim / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
         const int b = i / half, k = i % half;
@@ -387,7 +404,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int B, int di
     }
 }
 int timestep_embed_launch(const float* t, int B, int dim, __half* out, cudaStream_t st) {
-    timestep_embed_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, st>>>(t, B, dim, out);
+    LTT_CUDA_OK(launch_k(timestep_embed_kernel, dim3((B * dim / 2 + 127) / 128), dim3(128), 0, st, t, B, dim, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -398,6 +415,8 @@ __global__ void posnet_input_kernel(const float* __restrict__ boxes, const float
                                     const float* __restrict__ emb, const float* __restrict__ null_txt,
                                     const float* __restrict__ null_pos, int rows, int in_dim, int nfreq,
                                     __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -422,7 +441,7 @@ int posnet_input_launch(const float* boxes, const float* masks, const float* emb
         set_error("posnet: too many frequencies");
         return -1;
     }
-    posnet_input_kernel<<<(rows + 3) / 4, 128, 0, st>>>(boxes, masks, emb, null_txt, null_pos, rows, in_dim, nfreq, out);
+    LTT_CUDA_OK(launch_k(posnet_input_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, boxes, masks, emb, null_txt, null_pos, rows, in_dim, nfreq, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -431,6 +450,8 @@ int posnet_input_launch(const float* boxes, const float* masks, const float* emb
 // rects[b][i] = {top, bottom, left, right, valid}: reference truncation and first-break rules (attention.py:321-346)
 __global__ void rela_rects_kernel(const float* __restrict__ boxes, const float* __restrict__ masks, int B, int mo, int h,
                                   int w, int* __restrict__ rects) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float nv = 0.f;
@@ -448,7 +469,7 @@ __global__ void rela_rects_kernel(const float* __restrict__ boxes, const float* 
     }
 }
 int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, cudaStream_t st) {
-    rela_rects_kernel<<<(B + 31) / 32, 32, 0, st>>>(boxes, masks, B, mo, h, w, rects);
+    LTT_CUDA_OK(launch_k(rela_rects_kernel, dim3((B + 31) / 32), dim3(32), 0, st, boxes, masks, B, mo, h, w, rects));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -457,6 +478,8 @@ int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int
 // 16 pixel lanes x 16 channel quads, shuffle-free smem reduction over the pixel lanes.
 __global__ void rela_pool_kernel(const float* __restrict__ hid, const int* __restrict__ rects, int mo, int w, int HW,
                                  int C, __half* __restrict__ feats) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.y, b = blockIdx.z, cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c = blockIdx.x * 64 + cq * 4;
     const int* rc = rects + ((size_t)b * mo + i) * 5;
@@ -495,7 +518,7 @@ int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, i
         set_error("rela_pool: C %% 64 != 0 (C=%d)", C);
         return -1;
     }
-    rela_pool_kernel<<<dim3(C / 64, mo, B), 256, 0, st>>>(hid, rects, mo, w, h * w, C, feats);
+    LTT_CUDA_OK(launch_k(rela_pool_kernel, dim3(dim3(C / 64, mo, B)), dim3(256), 0, st, hid, rects, mo, w, h * w, C, feats));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -505,6 +528,8 @@ int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, i
 __global__ void rela_scatter_kernel(const float* __restrict__ hid, const __half* __restrict__ x,
                                     const __half* __restrict__ feats, const int* __restrict__ rects, int nb_feats,
                                     int mo, int w, int HW, int C, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x, b = row / HW, p = row % HW, y = p / w, xx = p % w;
     __shared__ int hit[32];
     __shared__ int nhit;
@@ -540,7 +565,7 @@ int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, 
         set_error("rela_scatter: more than 32 object slots");
         return -1;
     }
-    rela_scatter_kernel<<<B * h * w, 128, 0, st>>>(hid, x, feats, rects, nb_feats, mo, w, h * w, C, out);
+    LTT_CUDA_OK(launch_k(rela_scatter_kernel, dim3(B * h * w), dim3(128), 0, st, hid, x, feats, rects, nb_feats, mo, w, h * w, C, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -551,6 +576,8 @@ int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, 
 __global__ void small_attn_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
                                   const __half* __restrict__ v, int ldkv, int nq, int nk, int heads, int d, float scale,
                                   __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int qi = wid % nq, hh = (wid / nq) % heads, b = wid / (nq * heads);
@@ -593,9 +620,9 @@ int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v
     const int warps = B * heads * nq;   // multiple of 1
     const int wpb = 4;
     if (warps % wpb) {
-        small_attn_kernel<<<warps, 32, 0, st>>>(q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out);
+        LTT_CUDA_OK(launch_k(small_attn_kernel, dim3(warps), dim3(32), 0, st, q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out));
     } else {
-        small_attn_kernel<<<warps / wpb, wpb * 32, 0, st>>>(q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out);
+        LTT_CUDA_OK(launch_k(small_attn_kernel, dim3(warps / wpb), dim3(wpb * 32), 0, st, q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out));
     }
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
@@ -603,23 +630,27 @@ int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v
 
 // ------------------------------------------------------------------------------------------------ misc
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = __float2half_rn(in[i]);
 }
 int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-    cast_f32_f16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+    LTT_CUDA_OK(launch_k(cast_f32_f16_kernel, dim3(blocks), dim3(256), 0, st, in, out, n));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 __global__ void cast_f16_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = __half2float(in[i]);
 }
 int cast_f16_f32_launch(const __half* in, float* out, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-    cast_f16_f32_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+    LTT_CUDA_OK(launch_k(cast_f16_f32_kernel, dim3(blocks), dim3(256), 0, st, in, out, n));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -627,6 +658,8 @@ int cast_f16_f32_launch(const __half* in, float* out, size_t n, cudaStream_t st)
 // generic strided 2-D fp16 copy: dst[b][r][c] = src[b][r][c], rows x cols per batch element
 __global__ void copy2d_kernel(const __half* __restrict__ src, size_t sb, int sld, __half* __restrict__ dst, size_t db,
                               int dld, int B, int rows, int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)B * rows * cols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cols);
@@ -639,7 +672,7 @@ int copy2d_launch(const __half* src, size_t sb, int sld, __half* dst, size_t db,
                   cudaStream_t st) {
     const size_t total = (size_t)B * rows * cols;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-    copy2d_kernel<<<blocks, 256, 0, st>>>(src, sb, sld, dst, db, dld, B, rows, cols);
+    LTT_CUDA_OK(launch_k(copy2d_kernel, dim3(blocks), dim3(256), 0, st, src, sb, sld, dst, db, dld, B, rows, cols));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -653,6 +686,8 @@ __global__ void plms_update_kernel(const float* __restrict__ eps_c, const float*
                                    const float* __restrict__ e_first, const float* __restrict__ old1,
                                    const float* __restrict__ old2, const float* __restrict__ old3, float a_t,
                                    float a_prev, float sqrt_1m_at, float* __restrict__ x_out, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float e = eps_c[i];
         if (use_cfg) {
@@ -680,8 +715,8 @@ int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, i
                        float* e_t_out, const float* e_first, const float* old1, const float* old2, const float* old3,
                        float a_t, float a_prev, float sqrt_1m_at, float* x_out, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 4);
-    plms_update_kernel<<<blocks, 256, 0, st>>>(eps_c, eps_u, guidance, use_cfg, mode, x, e_t_out, e_first, old1, old2,
-                                                old3, a_t, a_prev, sqrt_1m_at, x_out, n);
+    LTT_CUDA_OK(launch_k(plms_update_kernel, dim3(blocks), dim3(256), 0, st, eps_c, eps_u, guidance, use_cfg, mode, x, e_t_out, e_first, old1, old2,
+                                                old3, a_t, a_prev, sqrt_1m_at, x_out, n));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -690,6 +725,8 @@ int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, i
 // the timestep vector, written on the device so the sampler loop never synchronises with the host.
 __global__ void plms_prep_kernel(const float* __restrict__ x, float* __restrict__ x_in, size_t n, int copies,
                                  float* __restrict__ t_in, int B, float tval) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < (size_t)B) t_in[gid] = tval;
     for (size_t i = gid; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -699,7 +736,7 @@ __global__ void plms_prep_kernel(const float* __restrict__ x, float* __restrict_
 }
 int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((std::max<size_t>(n, (size_t)B) + 255) / 256, 148 * 4);
-    plms_prep_kernel<<<blocks, 256, 0, st>>>(x, x_in, n, copies, t_in, B, tval);
+    LTT_CUDA_OK(launch_k(plms_prep_kernel, dim3(blocks), dim3(256), 0, st, x, x_in, n, copies, t_in, B, tval));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -708,6 +745,8 @@ int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t
 // conv weight [O, Cin, taps] fp32 (OIHW flattened) -> fp16 dst[o*Kdst + koff + tap*Cs + c] = w[o][cstart + c][tap]
 __global__ void pack_conv_kernel(const float* __restrict__ w, int O, int Cin, int taps, int cstart, int Cs,
                                  __half* __restrict__ dst, int Kdst, int koff) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)O * taps * Cs;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cs);
@@ -720,7 +759,7 @@ int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int C
                      cudaStream_t st) {
     const size_t total = (size_t)O * taps * Cs;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    pack_conv_kernel<<<blocks, 256, 0, st>>>(w, O, Cin, taps, cstart, Cs, dst, Kdst, koff);
+    LTT_CUDA_OK(launch_k(pack_conv_kernel, dim3(blocks), dim3(256), 0, st, w, O, Cin, taps, cstart, Cs, dst, Kdst, koff));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -729,6 +768,8 @@ int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int C
 // packed row p = tile*128 + h*64 + i  <-  source row h*(rows/2) + tile*64 + i   (h = 0 value, 1 gate)
 __global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int K, __half* __restrict__ dst, int row_off,
                                  int geglu) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)rows * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
@@ -748,7 +789,7 @@ int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, 
     }
     const size_t total = (size_t)rows * K;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    pack_rows_kernel<<<blocks, 256, 0, st>>>(w, rows, K, dst, row_off, geglu);
+    LTT_CUDA_OK(launch_k(pack_rows_kernel, dim3(blocks), dim3(256), 0, st, w, rows, K, dst, row_off, geglu));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
