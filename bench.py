@@ -280,7 +280,7 @@ def main():
                           set_alpha_scale=set_alpha_scale)
     host = synthetic_host_inputs(B, lat, lat, args.boxes, rank, pin=True)
     devin = {k: v.to(dev) for k, v in host.items()}
-    gathered = [torch.empty(B, 4, lat, lat, device=dev) for _ in range(world)] if world > 1 else None
+    from layoutllm_t2i_b200 import shard
     out_host = torch.empty(B, 4, lat, lat).pin_memory()
 
     def one_image_batch(src, from_host):
@@ -290,7 +290,7 @@ def main():
                    inpainting_extra_input=None, grounding_extra_input=None)
         z = sampler.sample(S=S, shape=(B, 4, lat, lat), input=inp, uc=t["uc"], guidance_scale=GUIDANCE)
         if world > 1:
-            dist.all_gather(gathered, z.contiguous())     # the path's single collective: final latents over NVLink
+            z_all = shard.gather_latents(z, B * world)    # the path's single collective: final latents over NVLink
         if from_host:
             out_host.copy_(z, non_blocking=True)
             torch.cuda.current_stream().synchronize()     # the caller holds the result on the host

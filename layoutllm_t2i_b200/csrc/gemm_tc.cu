@@ -13,6 +13,7 @@
 // Replaces (reference, /root/reference/GLIGEN/ldm/modules): every nn.Linear / nn.Conv2d on the UNet path --
 // attention.py:108-112,153-157 (q/k/v/out projections), :38-65 (GEGLU feed-forward), :425-433 (proj_in/out),
 // diffusionmodules/openaimodel.py:155-194 (ResBlock convs, emb_layers, skip), :57-114 (Up/Downsample convs).
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -673,6 +674,7 @@ struct Variant {
     static int max_clusters(int S) {
         static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (cache[S]) return cache[S];
+        if (configure()) return -1;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(S * 64, 1, 1);
@@ -693,22 +695,8 @@ struct Variant {
         cache[S] = n > 0 ? n : -1;
         return cache[S];
     }
-    static int launch(GemmDeviceArgs& a, int ctas, int iters, int num_sms, cudaStream_t stream) {
+    static int launch(GemmDeviceArgs& a, int ctas, int S, int num_sms, cudaStream_t stream) {
         if (int rc = configure()) return rc;
-        // split-K over a thread-block cluster when the tile grid leaves most SMs idle (small-M, weight-streaming
-        // layers): the largest cluster size whose clusters are all co-resident, with >= 2 k-iterations per rank
-        int S = 1;
-        if (ctas * 2 <= num_sms && iters >= 4) {
-            for (int c = 8; c >= 2; --c) {
-                if (c * 2 > iters) continue;
-                const int per = (iters + c - 1) / c;
-                if ((iters + per - 1) / per != c) continue;       // every rank must own at least one iteration
-                if (max_clusters(c) >= ctas) {
-                    S = c;
-                    break;
-                }
-            }
-        }
         a.splits = S;
         if (S == 1) {
             const int grid = ctas < num_sms ? ctas : num_sms;
@@ -772,23 +760,56 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     a.epi = p.epi;
     a.kind = epilogue_kind(p.epi);
 
-    // tile width: widest UMMA N that divides N (fewer operand bytes per flop); single-m-tile problems stream weights
-    // from DRAM, so they get narrow tiles (more CTAs pulling bandwidth).  GEGLU tiles are groups of 128 packed rows.
-    int BN;
+    // Tile width BN and split-K cluster size S from a small cycle model (constants fitted to the measurements in
+    // profiles/): per k-iteration a CTA is bound by the slower of the tensor pipe (2*BN cycles for 128 x BN x 64) and
+    // its share of L2->SM bandwidth (~75 B/cycle/SM); the epilogue costs ~600 + 6*BN cycles per tile; a cluster
+    // reduction moves 128*BN*4 B per CTA through DSMEM (~20 B/cycle) plus the dump; launch + prologue ~3000 cycles.
     const bool geglu = p.epi.act == ACT_GEGLU;
-    if (geglu) BN = (p.N % 256 == 0 && mtiles > 1) ? 256 : 128;
-    else if (mtiles == 1 && p.N % 64 == 0) BN = 64;
-    else if (p.N % 256 == 0) BN = 256;
-    else if (p.N % 160 == 0) BN = 160;
-    else if (p.N % 128 == 0) BN = 128;
-    else if (p.N <= 64 || p.N % 64 == 0) BN = 64;
-    else BN = 128;
     if (geglu && p.N % 128 != 0) {
         set_error("gemm: GEGLU needs N %% 128 == 0 (N=%d)", p.N);
         return -1;
     }
+    static const int kBN[4] = {64, 128, 160, 256};
+    int BN = 128, S = 1;
+    double best = 1e30;
+    for (int bi = 0; bi < 4; ++bi) {
+        const int bn = kBN[bi];
+        if (geglu && bn % 128) continue;
+        const int nt = (p.N + bn - 1) / bn;
+        const int ctas_c = mtiles * nt;
+        const double it_cycles = std::max(2.0 * bn, (16384.0 + 128.0 * bn) / 75.0);
+        const double epi_cycles = 600.0 + 6.0 * bn;
+        for (int sp = 1; sp <= 8; ++sp) {
+            int resident = num_sms;
+            if (sp > 1) {
+                if (sp * 2 > iters) break;
+                const int per = (iters + sp - 1) / sp;
+                if ((iters + per - 1) / per != sp) continue;      // every rank must own at least one iteration
+                int mc = 0;
+                switch (bn) {
+                    case 64: mc = Variant<64, 6>::max_clusters(sp); break;
+                    case 128: mc = Variant<128, 6>::max_clusters(sp); break;
+                    case 160: mc = Variant<160, 5>::max_clusters(sp); break;
+                    default: mc = Variant<256, 4>::max_clusters(sp); break;
+                }
+                if (mc < ctas_c) continue;                         // all clusters of the launch must be co-resident
+                resident = mc * sp;
+            }
+            const int units = ctas_c * sp;
+            const int waves = (units + resident - 1) / resident;
+            // several units per CTA overlap epilogue and main loop (double-buffered accumulator)
+            const double per_unit = (double)((iters + sp - 1) / sp) * it_cycles;
+            double t = 3000.0 + (waves > 1 ? waves * std::max(per_unit, epi_cycles) + std::min(per_unit, epi_cycles)
+                                           : per_unit + epi_cycles);
+            if (sp > 1) t += 30.0 * bn + 800.0;
+            if (t < best) {
+                best = t;
+                BN = bn;
+                S = sp;
+            }
+        }
+    }
     const int ntiles = (p.N + BN - 1) / BN;
-
     const int ctas = mtiles * ntiles;
     a.mtiles = mtiles;
     a.ntiles = ntiles;
@@ -801,10 +822,10 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     }
     (void)ws;
     switch (BN) {
-        case 64: return Variant<64, 6>::launch(a, ctas, iters, num_sms, stream);
-        case 128: return Variant<128, 6>::launch(a, ctas, iters, num_sms, stream);
-        case 160: return Variant<160, 5>::launch(a, ctas, iters, num_sms, stream);
-        case 256: return Variant<256, 4>::launch(a, ctas, iters, num_sms, stream);
+        case 64: return Variant<64, 6>::launch(a, ctas, S, num_sms, stream);
+        case 128: return Variant<128, 6>::launch(a, ctas, S, num_sms, stream);
+        case 160: return Variant<160, 5>::launch(a, ctas, S, num_sms, stream);
+        case 256: return Variant<256, 4>::launch(a, ctas, S, num_sms, stream);
     }
     set_error("gemm: no kernel variant for BN=%d", BN);
     return -1;
