@@ -11,6 +11,9 @@
 // Replaces the einsum / softmax / einsum triple of the reference's attention modules
 // (/root/reference/GLIGEN/ldm/modules/attention.py:127-141 CrossAttention, :164-176 SelfAttention), which
 // materialise the [B*8, N, N] score matrix.
+#include <cstdio>
+#include <cstdlib>
+
 #include "ltt_kernels.h"
 #include "ltt_ptx.cuh"
 
@@ -26,7 +29,7 @@ struct AttnDeviceArgs {
     float scale_log2;
 };
 
-template <int DPAD, int DV, int BKV>
+template <int DPAD, int DV, int BKV, int SBUF>
 struct AttnCfg {
     static constexpr int NKC = DPAD / 64;           // 64-column chunks of Q / K rows
     static constexpr int KSTEPS = DV / 16;          // k16 steps of QK^T (d rounded up to 16)
@@ -40,12 +43,28 @@ struct AttnCfg {
     static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + P_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
-    static constexpr int TM_S = 0, TM_O = 2 * BKV;
+    static constexpr int TM_S = 0, TM_O = SBUF * BKV;
+    static constexpr int TM_USED = SBUF * BKV + DV;
+    static constexpr int TM_COLS = TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
 };
 
-template <int DPAD, int DV, int BKV>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
-    using C = AttnCfg<DPAD, DV, BKV>;
+template <bool V>
+struct BoolTag {
+    static constexpr bool value = V;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// SBUF = number of S accumulators in TMEM: 2 lets QK^T of tile j+1 overlap the softmax of tile j inside one CTA;
+// 1 (with MINB = 2 CTAs per SM, 256 TMEM columns each) gets the same overlap from the co-resident CTA and doubles
+// the number of softmax warps per SM -- the d=40 level is bound by the softmax warps' issue rate, not by the tensor pipe.
+template <int DPAD, int DV, int BKV, int SBUF, int MINB>
+__global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
+    using C = AttnCfg<DPAD, DV, BKV, SBUF>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -81,7 +100,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == 1) tmem_alloc<C::TM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -117,26 +136,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         const uint32_t sv = smem_u32(smem + C::OFF_V);
         const uint32_t sp = smem_u32(smem + C::OFF_P);
         auto issue_qk = [&](int j) {
-            const int st = j & 1;
+            const int st = j & 1, sb = j % SBUF;
             mbar_wait(&k_full[st], (j >> 1) & 1);
-            if (j >= 2) mbar_wait(&s_empty[st], ((j >> 1) - 1) & 1);
+            if (j >= SBUF) mbar_wait(&s_empty[sb], ((j / SBUF) - 1) & 1);
             tc_fence_after();
             if (lane == 0) {
 #pragma unroll
                 for (int kk = 0; kk < C::KSTEPS; ++kk) {
                     const uint64_t ad = umma_desc_sw128(sq + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
                     const uint64_t bd = umma_desc_sw128(sk + st * C::K_BYTES + (kk >> 2) * (BKV * 128)) + 2 * (kk & 3);
-                    umma_f16(tmem_base + C::TM_S + st * BKV, ad, bd, idesc_qk, kk != 0);
+                    umma_f16(tmem_base + C::TM_S + sb * BKV, ad, bd, idesc_qk, kk != 0);
                 }
                 umma_commit(&k_empty[st]);
-                umma_commit(&s_full[st]);
+                umma_commit(&s_full[sb]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_qk(0);
         for (int j = 0; j < nt; ++j) {
-            if (j + 1 < nt) issue_qk(j + 1);
+            if (SBUF == 2 && j + 1 < nt) issue_qk(j + 1);
             const int st = j & 1;
             mbar_wait(&v_full[st], (j >> 1) & 1);
             mbar_wait(p_full, j & 1);
@@ -152,8 +171,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                 umma_commit(pv_done);
             }
             __syncwarp();
+            if (SBUF == 1 && j + 1 < nt) issue_qk(j + 1);
         }
     } else {
+        // ---- softmax warps: one thread per query row.  Scores are consumed in 32-column chunks straight from TMEM.
+        // Steady state is ONE pass: exponentiate against the running reference maximum m_used (exp2 domain) and only
+        // when a row's tile maximum exceeds it by more than 2^8 (or on the first tile) take the slow path: fix the
+        // reference, rescale O and l, and redo the tile.  P <= 256 fits fp16; l and O are fp32.
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
@@ -161,34 +185,75 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         float m_used = -INFINITY, l = 0.f;
         const float sc = args.scale_log2;
         for (int j = 0; j < nt; ++j) {
-            const int st = j & 1;
-            mbar_wait(&s_full[st], (j >> 1) & 1);
-            tc_fence_after();
-            float s[BKV];
-#pragma unroll
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(trow + C::TM_S + st * BKV + c, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(v[i]);
-            }
-            tc_fence_before();
-            mbar_arrive(&s_empty[st]);
+            const int sb = j % SBUF;
             const int kvalid = args.nk - j * BKV;   // >= 1
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < BKV; ++i) {
-                s[i] = (i < kvalid) ? s[i] * sc : -INFINITY;
-                mx = fmaxf(mx, s[i]);
-            }
-            const bool need = mx > m_used + 8.0f;
-            const float m_new = need ? mx : m_used;
+            const bool tail = kvalid < BKV;
+            const uint32_t ts = trow + C::TM_S + sb * BKV;
+            mbar_wait(&s_full[sb], (j / SBUF) & 1);
+            tc_fence_after();
             if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);
+                mbar_wait(pv_done, (j - 1) & 1);      // P buffer and O are free again
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, need)) {
-                    const float f = need ? exp2f(m_used - m_new) : 1.0f;
+            }
+            // exponentiate the tile against reference `mref`, write P, return the row sum; track the raw tile maximum
+            auto pass = [&](auto tail_tag, auto store_tag, float mref, float& tmax) -> float {
+                constexpr bool TAIL = decltype(tail_tag)::value;
+                constexpr bool store = decltype(store_tag)::value;     // false: raw tile maximum only
+                float rs = 0.f;
+                const float nm = -mref;
+#pragma unroll
+                for (int c = 0; c < BKV; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(ts + c, v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        f[i] = __uint_as_float(v[i]);
+                        if (TAIL && c + i >= kvalid) f[i] = -INFINITY;
+                        if (!store) tmax = fmaxf(tmax, f[i]);
+                    }
+                    if (store) {
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            __half2 h[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float p0 = ex2_approx(fmaf(f[c8 * 8 + 2 * i], sc, nm));
+                                const float p1 = ex2_approx(fmaf(f[c8 * 8 + 2 * i + 1], sc, nm));
+                                rs += p0 + p1;
+                                h[i] = __floats2half2_rn(p0, p1);
+                            }
+                            const int g8 = (c >> 3) + c8;              // 8-column group inside the tile
+                            const int kc = g8 >> 3, u = g8 & 7;
+                            *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
+                                *reinterpret_cast<uint4*>(h);
+                        }
+                    }
+                }
+                return rs;
+            };
+            auto exp_pass = [&](float mref) -> float {
+                float unused = 0.f;
+                return tail ? pass(BoolTag<true>{}, BoolTag<true>{}, mref, unused) : pass(BoolTag<false>{}, BoolTag<true>{}, mref, unused);
+            };
+            // optimistic pass against the current reference; every p >= 0, so a row sum below the fp16 range proves
+            // that no single p overflowed -- otherwise (or on the first tile) fix the reference and redo the tile
+            float rs = 0.f;
+            bool ok = false;
+            if (j > 0) {
+                rs = exp_pass(m_used);
+                ok = rs <= 32768.0f;
+            }
+            if (!__all_sync(0xffffffffu, ok)) {
+                float tmax = -INFINITY;
+                if (tail) pass(BoolTag<true>{}, BoolTag<false>{}, 0.f, tmax);
+                else pass(BoolTag<false>{}, BoolTag<false>{}, 0.f, tmax);
+                const float mx = tmax * sc;
+                const bool need = mx > m_used + 8.0f;
+                const float m_new = need ? mx : m_used;
+                if (j > 0 && __any_sync(0xffffffffu, need)) {
+                    const float f = need ? ex2_approx(m_used - m_new) : 1.0f;
                     l *= f;
 #pragma unroll
                     for (int c = 0; c < DV; c += 16) {
@@ -201,26 +266,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     }
                     tmem_st_wait();
                 }
-            }
-            m_used = m_new;
-            float rs = 0.f;
-#pragma unroll
-            for (int c8 = 0; c8 < BKV / 8; ++c8) {
-                __half2 h[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float p0 = exp2f(s[c8 * 8 + 2 * i] - m_used);
-                    const float p1 = exp2f(s[c8 * 8 + 2 * i + 1] - m_used);
-                    rs += p0 + p1;
-                    h[i] = __floats2half2_rn(p0, p1);
-                }
-                const int kc = c8 >> 3, u = c8 & 7;
-                *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
-                    *reinterpret_cast<uint4*>(h);
+                m_used = m_new;
+                rs = exp_pass(m_used);
             }
             l += rs;
-            fence_async_smem();
             tc_fence_before();
+            mbar_arrive(&s_empty[sb]);
+            fence_async_smem();
             mbar_arrive(p_full);
         }
         mbar_wait(pv_done, (nt - 1) & 1);
@@ -251,19 +303,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<C::TM_COLS>(tmem_base);
     }
 }
 
-template <int DPAD, int DV, int BKV>
+template <int DPAD, int DV, int BKV, int SBUF, int MINB>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
-    using C = AttnCfg<DPAD, DV, BKV>;
+    using C = AttnCfg<DPAD, DV, BKV, SBUF>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
+        if (getenv("LTT_VERBOSE")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, ATT_THREADS, C::TOTAL);
+            fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, MINB, C::TOTAL, nb);
+        }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -273,7 +330,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     memset(&a, 0, sizeof(a));
     const int rowlen = p.heads * p.dpad;
     int bkv, dv;
-    if (p.dhead == 40 && p.dpad == 64) { bkv = 128; dv = 48; }
+    if (p.dhead == 40 && p.dpad == 64) { bkv = (getenv("LTT_ATTN40") && atoi(getenv("LTT_ATTN40")) == 1) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
@@ -312,10 +369,15 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     a.out = p.out; a.ldo = p.ldo;
     a.scale_log2 = p.scale * 1.4426950408889634f;
     dim3 grid((p.nq + 127) / 128, p.heads, p.B);
-    if (dv == 48) return attn_launch_variant<64, 48, 128>(a, grid, stream);
-    if (dv == 80) return attn_launch_variant<128, 80, 128>(a, grid, stream);
-    if (dv == 160) return attn_launch_variant<192, 160, 64>(a, grid, stream);
-    return attn_launch_variant<64, 16, 128>(a, grid, stream);
+    if (dv == 48) {
+        static int v = -1;
+        if (v < 0) v = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;
+        if (v == 1) return attn_launch_variant<64, 48, 64, 1, 3>(a, grid, stream);
+        return attn_launch_variant<64, 48, 128, 1, 2>(a, grid, stream);
+    }
+    if (dv == 80) return attn_launch_variant<128, 80, 128, 2, 1>(a, grid, stream);
+    if (dv == 160) return attn_launch_variant<192, 160, 64, 2, 1>(a, grid, stream);
+    return attn_launch_variant<64, 16, 128, 2, 1>(a, grid, stream);
 }
 
 }  // namespace ltt
