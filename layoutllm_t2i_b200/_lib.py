@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libltt_b200.so")
+# LTT_LIB: development aid for A/B-ing two builds of the library on the GPU box (default: the in-tree build)
+LIB_PATH = os.environ.get("LTT_LIB") or os.path.join(_HERE, "libltt_b200.so")
 
 
 class LttError(RuntimeError):

@@ -1,5 +1,7 @@
 // Operator-level C-ABI entry points (include/ltt_b200.h): thin argument marshalling onto the kernel launchers.
 #include "../../include/ltt_b200.h"
+#include <cstdlib>
+
 #include "ltt_ops.h"
 
 using namespace ltt;
@@ -24,6 +26,14 @@ const GemmWorkspace& global_ws() { return g_ws; }
 int global_sms() { return g_sms; }
 }  // namespace ltt
 
+// Operator-level calls take caller-owned weights that an earlier kernel on the stream may still be writing (e.g. a
+// pack kernel), so the early weight prefetch is off unless LTT_OP_WSTATIC=1 (micro-benchmarks on quiescent weights).
+static int op_w_static() {
+    static int v = -1;
+    if (v < 0) v = getenv("LTT_OP_WSTATIC") ? 1 : 0;
+    return v;
+}
+
 extern "C" {
 
 const char* ltt_last_error(void) { return last_error(); }
@@ -39,6 +49,7 @@ int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, co
     p.w = (const __half*)w; p.Ktot = K;
     p.epi.bias = bias; p.epi.act = act; p.epi.res = res; p.epi.res_dtype = res_dtype; p.epi.ldr = ldr;
     p.epi.gate = gate; p.epi.has_gate = has_gate; p.epi.out = out; p.epi.out_dtype = out_dtype; p.epi.ldo = ldo;
+    p.w_static = op_w_static();
     return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
 }
 
@@ -59,6 +70,7 @@ int ltt_op_conv3x3(const void* x, int B, int H, int W, int C, const void* w_pack
     p.w = (const __half*)w_packed; p.Ktot = 9 * C;
     p.epi.bias = bias; p.epi.rowvec = (const __half*)rowvec; p.epi.ld_rowvec = N;
     p.epi.out = out; p.epi.out_dtype = DT_F16; p.epi.ldo = N;
+    p.w_static = op_w_static();
     return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
 }
 
@@ -72,6 +84,7 @@ int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int h
     p.epi.out_mode = OUT_QKV; p.epi.q = (__half*)q; p.epi.k = (__half*)k; p.epi.vt = (__half*)vt;
     p.epi.C = C; p.epi.dhead = C / heads; p.epi.dpad = dpad; p.epi.rows_q = rows_q; p.epi.rows_k = rows_k;
     p.epi.pitch_v = pitch_v; p.epi.tokens = tokens;
+    p.w_static = op_w_static();
     return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
 }
 

@@ -201,11 +201,14 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                 constexpr bool store = decltype(store_tag)::value;     // false: raw tile maximum only
                 float rs = 0.f;
                 const float nm = -mref;
+                // software pipelined: the TMEM load of chunk c + 32 is in flight while chunk c is exponentiated
+                uint32_t vb[2][32];
+                tmem_ld32(ts, vb[0]);
 #pragma unroll
                 for (int c = 0; c < BKV; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(ts + c, v);
+                    uint32_t(&v)[32] = vb[(c >> 5) & 1];
                     tmem_ld_wait();
+                    if (c + 32 < BKV) tmem_ld32(ts + c + 32, vb[((c >> 5) + 1) & 1]);
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {

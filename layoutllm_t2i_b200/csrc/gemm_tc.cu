@@ -26,8 +26,12 @@ namespace ltt {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 2 epilogue warpgroups
-constexpr int EPI_THREADS = 256;
+#ifndef LTT_EPI_WGS
+#define LTT_EPI_WGS 3
+#endif
+constexpr int EPI_WGS = LTT_EPI_WGS;                          // epilogue warpgroups (the epilogue is latency bound: more warps)
+constexpr int EPI_THREADS = 128 * EPI_WGS;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;      // TMA warp, MMA warp, epilogue warpgroups
 
 struct GemmDeviceArgs {
     CUtensorMap amap[3];
@@ -40,6 +44,7 @@ struct GemmDeviceArgs {
     int tw, th, tiles_x, tiles_y;
     int kind;                     // epilogue_kind(epi)
     int mtiles, ntiles, splits;   // splits > 1: one cluster of `splits` CTAs per tile, K range split by cluster rank
+    int w_static;                 // weights may be fetched before the predecessor grid completes
     GemmEpilogue epi;
 };
 
@@ -53,7 +58,22 @@ struct GemmSmem {
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU (erf form) through the Abramowitz-Stegun 7.1.26 erfc approximation (|abs err| < 5e-7 on x * Phi(x)): after the
+// fp16 rounding the reference applies to the GELU output it differs from the exact value on fewer fp16 inputs (254 of
+// 63488) than the erff() formulation does (333), at about half the instructions.
+__device__ __forceinline__ float gelu_erf_f(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float tail = 0.5f * p * e;                 // Phi(-|x|)
+    return x * (x >= 0.f ? 1.0f - tail : tail);
+}
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
 struct RowInfo {
@@ -319,6 +339,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // everything above overlapped the predecessor's tail (programmatic dependent launch); from here on global memory
     // written by it is read
     pdl_launch_dependents();
+    // Weights are not produced by the predecessor (w_static): the producer starts streaming the B tiles of its first
+    // unit's first STAGES iterations BEFORE waiting on the predecessor grid, so the HBM latency of the weight stream
+    // hides behind the predecessor's tail.  Only the activation (A) loads wait.
+    int npre = 0;
+    if (warp == 0 && lane == 0 && args.w_static && (int)blockIdx.x < total_units) {
+        const int unit = blockIdx.x;
+        const int z = unit % args.splits, tile = unit / args.splits;
+        const int n0 = (tile % args.ntiles) * BN;
+        const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
+        npre = min(STAGES, it1 - it0);
+        for (int i = 0; i < npre; ++i) {
+            mbar_expect_tx(&full_bar[i], SM::STAGE_BYTES);
+            tma_load_2d(smem + i * SM::STAGE_BYTES + A_TILE_BYTES, &args.bmap, &full_bar[i], (it0 + i) * BK, n0);
+        }
+    }
     pdl_wait();
 
     if (warp == 0) {
@@ -343,8 +378,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     chunk = rem % args.kchunks[s];
                 }
                 for (int it = it0; it < it1; ++it) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+                    const bool pre = npre > 0;     // B tile of this iteration is already in flight (see above)
+                    if (!pre) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+                    } else {
+                        --npre;
+                    }
                     uint8_t* sa = smem + stage * SM::STAGE_BYTES;
                     int dx = 0, dy = 0;
                     if (args.taps[s] == 9) {
@@ -352,7 +392,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         dx = tap % 3 - 1;
                     }
                     tma_load_4d(sa, &args.amap[s], &full_bar[stage], chunk * BK, x0 + dx, y0 + dy, b0);
-                    tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
+                    if (!pre) tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
                     if (++chunk == args.kchunks[s]) {
                         chunk = 0;
                         if (++tap == args.taps[s]) {
@@ -405,7 +445,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // thread owns one tile row (TMEM lane) and its warpgroup's share of the 32-column chunks
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;            // tile row
-        const int wg = (warp - 2) >> 2;         // 0 / 1
+        const int wg = (warp - 2) >> 2;         // 0 .. EPI_WGS-1
         const int et = threadIdx.x - 64;        // 0..255
         const GemmEpilogue& e = args.epi;
         const bool geglu = e.act == ACT_GEGLU;
@@ -445,7 +485,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
                 bias_s[c] = bvv;
             }
-            RowOperands opA, opB;
+            RowOperands opA;
             if (args.splits == 1) fetch_operands(e, ri, nbase + 16 * wg, Nout, opA);
             named_bar_sync(2, EPI_THREADS);
             const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -460,7 +500,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 float* part = reinterpret_cast<float*>(smem);
                 fence_async_smem();
 #pragma unroll 1
-                for (int c = 32 * wg; c < BN; c += 64) {
+                for (int c = 32 * wg; c < BN; c += 32 * EPI_WGS) {
                     uint32_t v[32];
                     tmem_ld32(trow + c, v);
                     tmem_ld_wait();
@@ -477,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                 for (int zz = 0; zz < 8; ++zz) peer[zz] = zz < S ? dsmem_map(part_addr, zz) : 0u;
 #pragma unroll 1
-                for (int g = g0 + wg; g < g1; g += 2) {
+                for (int g = g0 + wg; g < g1; g += EPI_WGS) {
                     const int c = g * 8;
                     const int vcol = geglu ? (c / 64) * 128 + (c % 64) : c;
                     RowOperands o;
@@ -524,12 +564,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 // 16-column chunks: accumulators -> fused epilogue (specialised per epilogue kind) -> global
                 auto run_tile = [&](auto kind_tag) {
                     constexpr int KIND = decltype(kind_tag)::value;
-                    auto process = [&](int c, const RowOperands& o) {
+                    constexpr bool kGeglu = KIND == EK_GEGLU;
+                    constexpr bool kFetch = KIND == EK_GENERIC || KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32;
+                    bool fetched = true;        // operands of the first chunk were fetched before the accumulator wait
+#pragma unroll 1
+                    for (int c = 16 * wg; c < ncols; c += 16 * EPI_WGS) {
                         // column of the value / gate accumulator inside the tile for output column c + i
-                        const int vcol = KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu) ? (c / 64) * 128 + (c % 64) : c;
+                        const bool gg = kGeglu || (KIND == EK_GENERIC && geglu);
+                        const int vcol = gg ? (c / 64) * 128 + (c % 64) : c;
                         uint32_t v[16], g[16];
                         tmem_ld16(trow + vcol, v);
-                        if (KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu)) tmem_ld16(trow + vcol + 64, g);
+                        if (gg) tmem_ld16(trow + vcol + 64, g);
+                        if (kFetch && !fetched) fetch_operands(e, ri, nbase + c, Nout, opA);   // overlaps the TMEM load
+                        fetched = false;
                         tmem_ld_wait();
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -537,19 +584,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 v8[i] = __uint_as_float(v[h * 8 + i]);
-                                g8[i] = (KIND == EK_GEGLU || (KIND == EK_GENERIC && geglu)) ? __uint_as_float(g[h * 8 + i]) : 0.f;
+                                g8[i] = gg ? __uint_as_float(g[h * 8 + i]) : 0.f;
                             }
-                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, o, h);
-                        }
-                    };
-                    constexpr bool kFetch = KIND == EK_GENERIC || KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32;
-#pragma unroll 1
-                    for (int c = 16 * wg; c < ncols; c += 64) {
-                        if (kFetch && c + 32 < ncols) fetch_operands(e, ri, nbase + c + 32, Nout, opB);
-                        process(c, opA);
-                        if (c + 32 < ncols) {
-                            if (kFetch && c + 64 < ncols) fetch_operands(e, ri, nbase + c + 64, Nout, opA);
-                            process(c + 32, opB);
+                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, opA, h);
                         }
                     }
                 };
@@ -759,6 +796,8 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     a.iters_total = iters;
     a.epi = p.epi;
     a.kind = epilogue_kind(p.epi);
+    static const bool no_prefetch = getenv("LTT_NO_WPREFETCH") != nullptr;
+    a.w_static = p.w_static && !no_prefetch;
 
     // Tile width BN and split-K cluster size S from a small cycle model (constants fitted to the measurements in
     // profiles/): per k-iteration a CTA is bound by the slower of the tensor pipe (2*BN cycles for 128 x BN x 64) and

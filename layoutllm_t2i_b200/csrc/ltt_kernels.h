@@ -92,6 +92,7 @@ struct GemmProblem {
     GemmSrc src[3];
     const __half* w;      // packed weights [N, Ktot]
     int Ktot;             // = sum taps*channels
+    int w_static;         // 1: `w` is never written by a kernel still in flight on the stream (model weights)
     GemmEpilogue epi;
 };
 

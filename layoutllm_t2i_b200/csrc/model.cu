@@ -486,6 +486,7 @@ struct Run {
             return -7;
         }
         p.w = w.w;
+        p.w_static = 1;      // packed model weights: written once at ltt_finalize
         p.epi = epi;
         if (!p.epi.bias) p.epi.bias = w.bias;
         m->launches++;

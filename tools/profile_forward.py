@@ -45,6 +45,12 @@ for alpha in ((1.0, 0.0) if which == "both" else (float(which),)):
     ms = e0.elapsed_time(e1) / iters
     print(f"alpha={alpha}: {n:.0f} launches/eval, host enqueue {1e3 * t_host / iters:.2f} ms, device {ms:.2f} ms "
           f"-> {gf / ms:.1f} TFLOP/s algorithmic ({gf:.0f} GF)", flush=True)
+    if os.environ.get("LTT_CUPROF"):      # ncu --profile-from-start off: capture exactly one evaluation
+        torch.cuda.profiler.start()
+        eng.forward(x, t, alpha)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        continue
     eng.profile(True)
     eng.forward(x, t, alpha)
     rep = eng.profile_report()
