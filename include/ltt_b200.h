@@ -136,6 +136,10 @@ int ltt_op_rela_rects(const float* boxes, const float* masks, int B, int mo, int
 int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, int w, int C, void* feats16, void* stream);
 int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                         int mo, int h, int w, int C, float* out, void* stream);
+/* the same with the block's norm2 (attention.py:437, nn.LayerNorm eps 1e-5 on the fp32 stream) fused: ln16 = fp16 LN(out) */
+int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
+                           int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
+                           void* ln16, void* stream);
 /* 30 x 10 relation cross-attention core (warp shuffles) */
 int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
                            float scale, void* out, void* stream);

@@ -107,6 +107,11 @@ int ltt_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int 
         cap = B;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    {   // same dispatch as the model path: fused cluster kernel, stats + apply outside its envelope
+        const int rc = groupnorm_fused_launch((const __half*)x0, c0, c0, (const __half*)x1, c1, c1, B, HW, 32, gamma, beta, eps,
+                                              silu, (__half*)out, st);
+        if (rc <= 0) return rc;
+    }
     if (int rc = gn_stats_launch((const __half*)x0, c0, c0, (const __half*)x1, c1, c1, B, HW, 32, stats, st)) return rc;
     return gn_apply_launch((const __half*)x0, c0, c0, (const __half*)x1, c1, c1, B, HW, 32, stats, gamma, beta, eps, silu,
                            (__half*)out, st);
@@ -126,7 +131,13 @@ int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, i
 int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                         int mo, int h, int w, int C, float* out, void* stream) {
     return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
-                               (cudaStream_t)stream);
+                               nullptr, nullptr, 0.f, nullptr, (cudaStream_t)stream);
+}
+int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
+                           int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
+                           void* ln16, void* stream) {
+    return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+                               gamma, beta, eps, (__half*)ln16, (cudaStream_t)stream);
 }
 int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
                            float scale, void* out, void* stream) {

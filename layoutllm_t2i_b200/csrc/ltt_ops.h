@@ -11,6 +11,8 @@ int gn_stats_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
                     const double* stats, const float* gamma, const float* beta, float eps, int silu, __half* out,
                     cudaStream_t st);
+int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
+                           const float* gamma, const float* beta, float eps, int silu, __half* out, cudaStream_t st);
 int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
                      __half* out16, float* out32, cudaStream_t st);
 int conv_in_launch(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
@@ -26,7 +28,10 @@ int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int
 int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, int w, int C, __half* feats,
                      cudaStream_t st);
 int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, const int* rects, int nb_feats, int B,
-                        int mo, int h, int w, int C, float* out, cudaStream_t st);
+                        int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
+                        __half* ln16, cudaStream_t st);
+int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
+                          int pitch_v, int B, int mo, int C, cudaStream_t st);
 int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int nq, int nk,
                       int heads, int d, float scale, __half* out, cudaStream_t st);
 int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st);

@@ -182,6 +182,14 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ double dsmem_ld_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the UNet sequence is launched with programmatic stream serialisation: it may start (prologue:
 // barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains, and blocks here until the

@@ -508,6 +508,12 @@ static GemmEpilogue epi_out(void* out, int ldo, int dtype = DT_F16) {
 static int groupnorm(ltt_model* m, cudaStream_t st, const __half* x0, int c0, const __half* x1, int c1, int B, int HW,
                      const Norm& n, float eps, int silu, __half* out) {
     ProfScope ps(m, st, PC_GN, 0.0, (double)B * HW * (c0 + c1) * 2.0 * 3.0);
+    const int rc = groupnorm_fused_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, n.g, n.b, eps, silu, out, st);
+    if (rc <= 0) {
+        m->launches += 1;
+        return rc;
+    }
+    // geometry outside the fused kernel's envelope: statistics + apply
     RC(gn_stats_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, st));
     RC(gn_apply_launch(x0, c0, c0, x1, c1, c1, B, HW, 32, m->gn_stats, n.g, n.b, eps, silu, out, st));
     m->launches += 3;
@@ -595,9 +601,9 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
         RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_qkv, epi_qkv(s, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, 0)));
         const int rowlen = s.heads * s.dpad;
-        RC(copy2d_launch(s.fg_k, (size_t)mo * rowlen, rowlen, kb + (size_t)N * rowlen, (size_t)rows_k * rowlen, rowlen, B, mo, rowlen, st));
-        RC(copy2d_launch(s.fg_vt, (size_t)C * 32, 32, m->vtbuf + N, (size_t)C * pitch_v, pitch_v, B, C, mo, st));
-        m->launches += 2;
+        RC(ground_kv_copy_launch(s.fg_k, kb + (size_t)N * rowlen, (size_t)rows_k * rowlen, rowlen, s.fg_vt, m->vtbuf + N,
+                                 (size_t)C * pitch_v, pitch_v, B, mo, C, st));
+        m->launches += 1;
         RC(attention(m, st, s, B, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, N + mo, m->ao));
         {
             GemmEpilogue e = epi_out(m->xa, C);
@@ -649,11 +655,12 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         }
         feats_final = m->feats3;
     }
-    RC(rela_scatter_launch(m->hid32, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, st));
+    // scatter + the block's norm2 in one kernel
+    RC(rela_scatter_launch(m->hid32, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
+                           m->ln16, st));
     m->launches++;
     RC(tap(m, st, s.p + ":rela", m->xe32, DT_F32, M, C));
     // attn2 over the cached text K/V
-    RC(ln(m, st, m->xe32, DT_F32, M, C, s.ln2, m->ln16, nullptr));
     RC(r.gemm(H, W, C, {GemmSrc{m->ln16, C, C, 1}}, s.a2_q, epi_qkv(s, qb, N, nullptr, 0, nullptr, 0, N, 0)));
     RC(attention(m, st, s, B, qb, N, s.c2_k, m->ctx_len, s.c2_vt, 128, N, m->ctx_len, m->ao));
     {

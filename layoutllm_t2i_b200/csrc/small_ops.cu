@@ -128,6 +128,170 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
     return 0;
 }
 
+// ---- single-kernel GroupNorm.  One thread-block cluster per (batch element, set of G consecutive groups); the
+// GN_S CTAs of a cluster split the pixels.  Pass 1 streams the CTA's slab (pixels x G*cpg channels) from global memory
+// once -- staging it in shared memory when it fits -- and reduces (sum, sum of squares): fp32 per thread over its
+// pixel column, then double across threads, then double across the cluster through distributed shared memory in fixed
+// rank order (deterministic).  Pass 2 normalises from the staged copy.  One read + one write of the tensor, no
+// statistics buffer, no memset node between the producer GEMM and the consumer (the PDL chain stays intact).
+constexpr int GN_S = 8;          // CTAs per cluster (pixel split)
+constexpr int GN_MAXG = 4;       // groups per cluster
+constexpr int GN_THREADS = 256;
+
+__global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
+    const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int ld1, int C, int HW, int cpg, int G,
+    int V, int R, int px_per_cta, int stage, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    int silu, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    extern __shared__ uint4 gn_slab[];                 // [px_per_cta][V] when stage
+    __shared__ float part[GN_THREADS * 8];             // per-thread (sum, sumsq) of its 4 channel pairs
+    __shared__ double colsum[GN_THREADS * 2];          // [V*4 pair columns][2]  (V <= GN_THREADS/4 by host check)
+    __shared__ double cta_stats[2 * GN_MAXG];          // this CTA's (sum, sumsq) per group -- read by the whole cluster
+    __shared__ float2 mr[GN_MAXG];
+    const int tid = threadIdx.x;
+    const int rank = blockIdx.x;                       // cluster dims (GN_S,1,1), gridDim.x == GN_S
+    const int b = blockIdx.z;
+    const int cbase = blockIdx.y * G * cpg;
+    const bool active = tid < V * R;
+    const int v = tid % V, r = tid / V;
+    const int c = cbase + v * 8;
+    const __half* src = c < c0 ? x0 + c : x1 + (c - c0);
+    const int ld = c < c0 ? ld0 : ld1;
+    const int p0 = rank * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+    // step-invariant operands first (they do not depend on the predecessor grid)
+    float g[8], bt[8];
+    if (active) {
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), gb = *reinterpret_cast<const float4*>(gamma + c + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(beta + c), bb = *reinterpret_cast<const float4*>(beta + c + 4);
+        g[0] = ga.x; g[1] = ga.y; g[2] = ga.z; g[3] = ga.w; g[4] = gb.x; g[5] = gb.y; g[6] = gb.z; g[7] = gb.w;
+        bt[0] = ba.x; bt[1] = ba.y; bt[2] = ba.z; bt[3] = ba.w; bt[4] = bb.x; bt[5] = bb.y; bt[6] = bb.z; bt[7] = bb.w;
+    }
+    pdl_wait();
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        for (int p = p0 + r; p < p1; p += R) {
+            const uint4 u = *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
+            if (stage) gn_slab[(p - p0) * V + v] = u;
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                s[k] += f.x + f.y;
+                ss[k] += f.x * f.x + f.y * f.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            part[tid * 8 + 2 * k] = s[k];
+            part[tid * 8 + 2 * k + 1] = ss[k];
+        }
+    }
+    __syncthreads();
+    const int PC = V * 4;                              // channel-pair columns of the slab
+    if (tid < PC) {
+        double a = 0.0, q = 0.0;
+        const int vv = tid >> 2, k = tid & 3;
+        for (int rr = 0; rr < R; ++rr) {
+            a += (double)part[(rr * V + vv) * 8 + 2 * k];
+            q += (double)part[(rr * V + vv) * 8 + 2 * k + 1];
+        }
+        colsum[2 * tid] = a;
+        colsum[2 * tid + 1] = q;
+    }
+    __syncthreads();
+    if (tid < 2 * G) {
+        const int gi = tid >> 1, which = tid & 1, npc = cpg >> 1;
+        double a = 0.0;
+        for (int j = 0; j < npc; ++j) a += colsum[2 * (gi * npc + j) + which];
+        cta_stats[tid] = a;
+    }
+    cluster_sync_all();                                // every CTA's cta_stats is complete and visible
+    if (tid < G) {
+        double sm = 0.0, sq = 0.0;
+        const uint32_t base = smem_u32(&cta_stats[2 * tid]);
+        for (int rk = 0; rk < GN_S; ++rk) {
+            const uint32_t a = dsmem_map(base, rk);
+            sm += dsmem_ld_f64(a);
+            sq += dsmem_ld_f64(a + 8);
+        }
+        const double n = (double)cpg * HW;
+        const double mean = sm / n;
+        double var = sq / n - mean * mean;
+        if (var < 0) var = 0;
+        mr[tid] = make_float2((float)mean, rsqrtf((float)var + eps));
+    }
+    cluster_arrive();                                  // done reading peers; matching wait at the end
+    __syncthreads();
+    if (active) {
+        float2 m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = mr[(v * 8 + 2 * k) / cpg];   // cpg is even: a pair never straddles groups
+        for (int p = p0 + r; p < p1; p += R) {
+            const uint4 u = stage ? gn_slab[(p - p0) * V + v] : *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+            __half2 o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                float a = r16f((f.x - m4[k].x) * m4[k].y * g[2 * k] + bt[2 * k]);
+                float d = r16f((f.y - m4[k].x) * m4[k].y * g[2 * k + 1] + bt[2 * k + 1]);
+                if (silu) {
+                    a = siluf(a);
+                    d = siluf(d);
+                }
+                o[k] = __floats2half2_rn(a, d);
+            }
+            *reinterpret_cast<uint4*>(out + ((size_t)b * HW + p) * C + c) = *reinterpret_cast<uint4*>(o);
+        }
+    }
+    cluster_wait();                                    // no CTA exits while a peer may still read its cta_stats
+}
+
+// GroupNorm(32 groups) (+SiLU) of the channel concat of up to two NHWC fp16 tensors -> NHWC fp16 [B, HW, C].
+// Returns 1 when the geometry is not supported by the fused kernel (caller falls back to stats + apply).
+int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
+                           const float* gamma, const float* beta, float eps, int silu, __half* out, cudaStream_t st) {
+    const int C = c0 + c1;
+    if (groups != 32 || C % groups) return 1;
+    const int cpg = C / groups;
+    if ((cpg & 1) || c0 % 8 || ld0 % 8 || (c1 && ld1 % 8)) return 1;
+    // groups per cluster: the slab must be whole 16-byte vectors; fewer groups per cluster = more CTAs for small batches
+    int G = 0;
+    for (int g = 1; g <= GN_MAXG; g *= 2)
+        if ((g * cpg) % 8 == 0 && (G == 0 || GN_S * B * (32 / g) >= 128)) G = g;
+    if (G == 0) return 1;
+    const int V = G * cpg / 8;
+    if (V > GN_THREADS / 4) return 1;
+    const int R = GN_THREADS / V;
+    const int px = (HW + GN_S - 1) / GN_S;
+    const size_t slab = (size_t)px * V * 16;
+    const int stage = slab <= 160 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(GN_S, 32 / G, B);
+    cfg.blockDim = dim3(GN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = stage ? slab : 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = GN_S;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, x0, c0, ld0, x1, ld1, C, HW, cpg, G, V, R, px, stage, gamma, beta, eps,
+                                   silu, out));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row, 16-byte vector loads / stores (8 halves or 2 x 4 floats per lane per step); fp32 statistics
 // (two pass in registers); writes fp16 and/or fp32.
@@ -524,48 +688,115 @@ int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, i
 }
 
 // out[b,p,:] = (hid + (1/mo) sum_{i: p in rect_i} feats[b,i,:] + x) / 2   (fp32).  feats == nullptr or b >= nb_feats
-// -> no boxes (uncond half): out = (hid + x) / 2.
-__global__ void rela_scatter_kernel(const float* __restrict__ hid, const __half* __restrict__ x,
-                                    const __half* __restrict__ feats, const int* __restrict__ rects, int nb_feats,
-                                    int mo, int w, int HW, int C, float* __restrict__ out) {
+// -> no boxes (uncond half): out = (hid + x) / 2.  One CTA per pixel row; the row stays in registers and the
+// LayerNorm that follows in the block (norm2, attention.py:437) is applied in the same kernel: ln16 = LN(out) in fp16
+// (fp32 two-pass statistics, as layernorm_kernel).  C <= 8 * blockDim.x.
+constexpr int RS_THREADS = 160;
+__global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
+    const float* __restrict__ hid, const __half* __restrict__ x, const __half* __restrict__ feats,
+    const int* __restrict__ rects, int nb_feats, int mo, int w, int HW, int C, float* __restrict__ out,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ ln16) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x, b = row / HW, p = row % HW, y = p / w, xx = p % w;
     __shared__ int hit[32];
     __shared__ int nhit;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        if (feats && b < nb_feats)
-            for (int i = 0; i < mo && i < 32; ++i) {
-                const int* rc = rects + ((size_t)b * mo + i) * 5;
-                if (rc[4] && y >= rc[0] && y < rc[1] && xx >= rc[2] && xx < rc[3]) hit[n++] = i;
-            }
-        nhit = n;
+    __shared__ float red[2][RS_THREADS / 32];
+    if (threadIdx.x < 32) {
+        const int i = threadIdx.x;
+        bool in = false;
+        if (feats && b < nb_feats && i < mo) {
+            const int* rc = rects + ((size_t)b * mo + i) * 5;
+            in = rc[4] && y >= rc[0] && y < rc[1] && xx >= rc[2] && xx < rc[3];
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        if (in) hit[__popc(mask & ((1u << i) - 1))] = i;        // ascending slot order, as the sequential scan
+        if (i == 0) nhit = __popc(mask);
     }
     __syncthreads();
     const float inv = 1.0f / (float)mo;
-    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-        float2 acc = make_float2(0.f, 0.f);
+    const int c = threadIdx.x * 8;
+    const bool act = c < C;
+    float o[8];
+    float s = 0.f;
+    if (act) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < nhit; ++k) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(feats + ((size_t)b * mo + hit[k]) * C + c));
-            acc.x += f.x;
-            acc.y += f.y;
+            const uint4 u = *reinterpret_cast<const uint4*>(feats + ((size_t)b * mo + hit[k]) * C + c);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+            }
         }
-        const float2 hv = *reinterpret_cast<const float2*>(hid + (size_t)row * C + c);
-        const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)row * C + c));
-        float2 o;
-        o.x = ((hv.x + acc.x * inv) + xv.x) * 0.5f;
-        o.y = ((hv.y + acc.y * inv) + xv.y) * 0.5f;
-        *reinterpret_cast<float2*>(out + (size_t)row * C + c) = o;
+        const float4 h0 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c);
+        const float4 h1 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint4 xu = *reinterpret_cast<const uint4*>(x + (size_t)row * C + c);
+        const __half2* xh = reinterpret_cast<const __half2*>(&xu);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 xv = __half22float2(xh[j]);
+            o[2 * j] = ((hv[2 * j] + acc[2 * j] * inv) + xv.x) * 0.5f;
+            o[2 * j + 1] = ((hv[2 * j + 1] + acc[2 * j + 1] * inv) + xv.y) * 0.5f;
+        }
+        float4* op = reinterpret_cast<float4*>(out + (size_t)row * C + c);
+        op[0] = make_float4(o[0], o[1], o[2], o[3]);
+        op[1] = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += o[j];
+    }
+    if (!ln16) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < RS_THREADS / 32; ++k) tot += red[0][k];
+    const float mean = tot / C;
+    float ss = 0.f;
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = o[j] - mean;
+            ss += d * d;
+        }
+    }
+#pragma unroll
+    for (int k = 16; k; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+    if (lane == 0) red[1][warp] = ss;
+    __syncthreads();
+    float tss = 0.f;
+#pragma unroll
+    for (int k = 0; k < RS_THREADS / 32; ++k) tss += red[1][k];
+    const float rstd = rsqrtf(tss / C + eps);
+    if (act) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            h[j] = __floats2half2_rn((o[2 * j] - mean) * rstd * g[2 * j] + bt[2 * j],
+                                     (o[2 * j + 1] - mean) * rstd * g[2 * j + 1] + bt[2 * j + 1]);
+        *reinterpret_cast<uint4*>(ln16 + (size_t)row * C + c) = *reinterpret_cast<uint4*>(h);
     }
 }
+// gamma == nullptr: scatter only (ln16 ignored).
 int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, const int* rects, int nb_feats, int B,
-                        int mo, int h, int w, int C, float* out, cudaStream_t st) {
-    if (mo > 32) {
-        set_error("rela_scatter: more than 32 object slots");
+                        int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
+                        __half* ln16, cudaStream_t st) {
+    if (mo > 32 || C % 8 || C > 8 * RS_THREADS) {
+        set_error("rela_scatter: unsupported mo=%d C=%d", mo, C);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(rela_scatter_kernel, dim3(B * h * w), dim3(128), 0, st, hid, x, feats, rects, nb_feats, mo, w, h * w, C, out));
+    LTT_CUDA_OK(launch_k(rela_scatter_ln_kernel, dim3(B * h * w), dim3(RS_THREADS), 0, st, hid, x, feats, rects, nb_feats, mo, w,
+                         h * w, C, out, gamma, beta, eps, gamma ? ln16 : (__half*)nullptr));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -668,6 +899,49 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, size_t sb, int sld
         dst[b * db + (size_t)r * dld + c] = src[b * sb + (size_t)r * sld + c];
     }
 }
+// Both strided copies of one gated self-attention layer in ONE launch: the cached grounding-token K rows
+// [B][mo][rowlen] go behind the visual keys of the K buffer and the cached V^T columns [B][C][32] behind the visual
+// columns of the V^T buffer.  blockIdx.y selects the copy.
+__global__ void ground_kv_copy_kernel(const __half* __restrict__ ksrc, __half* __restrict__ kdst, size_t kdb, int rowlen,
+                                      const __half* __restrict__ vsrc, __half* __restrict__ vdst, size_t vdb, int pitch_v,
+                                      int B, int mo, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (blockIdx.y == 0) {
+        const int vec = rowlen >> 3;                       // 16-byte vectors per K row
+        const size_t total = (size_t)B * mo * vec;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const int cv = (int)(i % vec);
+            const size_t r = i / vec;
+            const int rr = (int)(r % mo);
+            const size_t b = r / mo;
+            reinterpret_cast<uint4*>(kdst + b * kdb + (size_t)rr * rowlen)[cv] =
+                reinterpret_cast<const uint4*>(ksrc + (b * mo + rr) * (size_t)rowlen)[cv];
+        }
+    } else {
+        const size_t total = (size_t)B * C * mo;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const int c = (int)(i % mo);
+            const size_t r = i / mo;
+            const int rr = (int)(r % C);
+            const size_t b = r / C;
+            vdst[b * vdb + (size_t)rr * pitch_v + c] = vsrc[(b * C + rr) * 32 + c];
+        }
+    }
+}
+int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
+                          int pitch_v, int B, int mo, int C, cudaStream_t st) {
+    if (rowlen % 8 || mo > 32) {
+        set_error("ground_kv_copy: unsupported rowlen=%d mo=%d", rowlen, mo);
+        return -1;
+    }
+    const size_t total = (size_t)B * C * mo;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 4);
+    LTT_CUDA_OK(launch_k(ground_kv_copy_kernel, dim3(blocks, 2), dim3(256), 0, st, ksrc, kdst, kdb, rowlen, vsrc, vdst, vdb, pitch_v, B, mo, C));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int copy2d_launch(const __half* src, size_t sb, int sld, __half* dst, size_t db, int dld, int B, int rows, int cols,
                   cudaStream_t st) {
     const size_t total = (size_t)B * rows * cols;

@@ -169,6 +169,43 @@ def check_layernorm(M, C, dtype, seed=0):
     return max(rel(o32, ref), rel(o16.float(), ref) / 4)
 
 
+def check_rela_scatter_ln(B, nb, h, w, C, seed=0):
+    """scatter of pooled box features + (out + x) / 2 + the fused LayerNorm, against plain torch on the same inputs."""
+    mo = 30
+    g0 = torch.Generator().manual_seed(seed)
+    boxes = torch.zeros(B, mo, 4)
+    masks = torch.zeros(B, mo)
+    for b in range(nb):
+        n = 5 + b
+        xy = torch.rand(n, 2, generator=g0) * 0.6
+        wh = torch.rand(n, 2, generator=g0) * 0.35 + 0.05
+        boxes[b, :n] = torch.cat([xy, xy + wh], dim=-1)
+        masks[b, :n] = 1
+    boxes, masks = boxes.to(DEV), masks.to(DEV)
+    rects = torch.zeros(B, mo, 5, device=DEV, dtype=torch.int32)
+    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes), L.ptr(masks), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
+    hid = rn(B, h * w, C, seed=seed + 1) * 2
+    x = rn(B, h * w, C, seed=seed + 2, dtype=torch.float16)
+    feats = rn(nb, mo, C, seed=seed + 3, dtype=torch.float16)
+    g = 1 + 0.1 * rn(C, seed=seed + 4)
+    bt = 0.1 * rn(C, seed=seed + 5)
+    out = torch.empty(B, h * w, C, device=DEV)
+    ln16 = torch.empty(B, h * w, C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_rela_scatter_ln(L.ptr(hid), L.ptr(x), L.ptr(feats), L.ptr(rects), nb, B, mo, h, w, C, L.ptr(out),
+                                           L.ptr(g), L.ptr(bt), 1e-5, L.ptr(ln16), L.stream_ptr()), "rela_scatter_ln")
+    torch.cuda.synchronize()
+    rc = rects.cpu()
+    add = torch.zeros(B, h, w, C, device=DEV)
+    for b in range(nb):
+        for i in range(mo):
+            t, bo, le, ri, ok = [int(v) for v in rc[b, i]]
+            if ok:
+                add[b, t:bo, le:ri] += feats[b, i].float() / mo
+    ref = ((hid + add.view(B, h * w, C)) + x.float()) * 0.5
+    ref_ln = F.layer_norm(ref, (C,), g, bt, 1e-5)
+    return max(rel(out, ref), rel(ln16.float(), ref_ln) / 4)
+
+
 ALL = [
     # name, fn, args, tolerance (rel-L2 vs fp32 math on the same fp16 inputs)
     ("linear 256x128x64 (1 tile, 1 k-iter)", check_linear, dict(M=256, N=128, K=64, bias=False), 2e-3),
@@ -205,6 +242,15 @@ ALL = [
     ("groupnorm+silu 2x4096 320", check_groupnorm, dict(B=2, HW=4096, c0=320, c1=0, silu=True, eps=1e-5), 2e-3),
     ("groupnorm concat 1x1024 1280+640", check_groupnorm, dict(B=1, HW=1024, c0=1280, c1=640, silu=True, eps=1e-5), 2e-3),
     ("groupnorm eps1e-6 nosilu 2x64 1280", check_groupnorm, dict(B=2, HW=64, c0=1280, c1=0, silu=False, eps=1e-6), 2e-3),
+    ("groupnorm concat 2x4096 320+640 (cpg 30)", check_groupnorm, dict(B=2, HW=4096, c0=320, c1=640, silu=True, eps=1e-5), 2e-3),
+    ("groupnorm concat 2x256 1280+1280", check_groupnorm, dict(B=2, HW=256, c0=1280, c1=1280, silu=True, eps=1e-5), 2e-3),
+    ("groupnorm 3x4 64 (cpg 2, fewer pixels than CTAs)", check_groupnorm, dict(B=3, HW=4, c0=64, c1=0, silu=True, eps=1e-5), 2e-3),
+    ("groupnorm concat 2x384 64+128 (cpg 6, ragged pixels)", check_groupnorm, dict(B=2, HW=381, c0=64, c1=128, silu=False, eps=1e-5), 2e-3),
+    ("groupnorm 1x9216 960 (slab not staged)", check_groupnorm, dict(B=1, HW=9216, c0=640, c1=320, silu=True, eps=1e-5), 2e-3),
+    ("rela scatter + LN 2x32x32 C=640 (uncond half without boxes)", check_rela_scatter_ln, dict(B=2, nb=1, h=32, w=32, C=640), 1e-4),
+    ("rela scatter + LN 3x24x16 C=320", check_rela_scatter_ln, dict(B=3, nb=3, h=24, w=16, C=320), 1e-4),
+    ("rela scatter + LN 2x8x8 C=1280", check_rela_scatter_ln, dict(B=2, nb=2, h=8, w=8, C=1280), 1e-4),
+    ("rela scatter + LN 2x16x16 C=64", check_rela_scatter_ln, dict(B=2, nb=1, h=16, w=16, C=64), 1e-4),
     ("layernorm f16 4096x320", check_layernorm, dict(M=4096, C=320, dtype=torch.float16), 1e-4),
     ("layernorm f32 1000x1280", check_layernorm, dict(M=1000, C=1280, dtype=torch.float32), 1e-4),
     ("layernorm f16 90x64", check_layernorm, dict(M=90, C=64, dtype=torch.float16), 1e-4),
