@@ -45,6 +45,8 @@ struct GemmDeviceArgs {
     int kind;                     // epilogue_kind(epi)
     int mtiles, ntiles, splits;   // splits > 1: one cluster of `splits` CTAs per tile, K range split by cluster rank
     int w_static;                 // weights may be fetched before the predecessor grid completes
+    int pair;                     // 1: CTA-pair mode (cta_group::2): cluster of 2 CTAs computes a 256 x BN tile, each CTA
+                                  // loads its own 128 A rows and half of the B tile, the leader issues 256-row MMAs
     GemmEpilogue epi;
 };
 
@@ -52,6 +54,7 @@ template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES / 2;     // per CTA of a pair
     static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;           // BN floats
     static constexpr int BAR_OFFSET = BIAS_OFFSET + BN * 4;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;              // + barriers/tmem slot + alignment slack
@@ -297,7 +300,7 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
 // blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA issuer run ahead of the epilogue warps by up
 // to one unit because the fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of unit u
 // overlaps the main loop of unit u + 1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
     using SM = GemmSmem<BN, STAGES>;
     constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -310,10 +313,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint64_t* acc_empty = acc_full + 2;          // 2 (count EPI_THREADS)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so ptxas treats it (and every branch on it) as warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    // CTA-pair mode: work unit = (pair of M tiles, N tile); CTA rank r of the cluster owns M tile 2 * mpair + r.
+    constexpr bool pair = PAIR;     // a kernel containing cta_group::2 instructions can only be launched as a cluster
+    const uint32_t crank = pair ? cluster_ctarank() : 0u;
+    const int cta_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;     // units advance by clusters in pair mode
+    const int cta_first = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     // Split-K mode (splits > 1): the grid is exactly one cluster per tile, every CTA runs ONE unit (tile = cluster id,
     // K range = cluster rank) and the partial accumulators are reduced through distributed shared memory.
-    const int total_units = args.mtiles * args.ntiles * args.splits;
+    const int total_units = pair ? ((args.mtiles + 1) >> 1) * args.ntiles : args.mtiles * args.ntiles * args.splits;
     const int per = (args.iters_total + args.splits - 1) / args.splits;   // host guarantees every z gets >= 1 iteration
     const int tiles_img = args.tiles_x * args.tiles_y;
     const int tb = BM / (args.tw * args.th);
@@ -327,116 +336,148 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], EPI_THREADS);
+            mbar_init(&acc_empty[i], pair ? 2 * EPI_THREADS : EPI_THREADS);   // pair: both CTAs' epilogues report to the leader
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) {
+        if constexpr (pair) tmem_alloc2<TMEM_COLS>(tmem_slot);
+        else tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();      // the peer's barriers are initialised before anything is signalled remotely
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     // everything above overlapped the predecessor's tail (programmatic dependent launch); from here on global memory
     // written by it is read
     pdl_launch_dependents();
+    // The producer and MMA-issuer warps run their loops CONVERGED with warp-uniform operands; a single elected lane
+    // performs each TMA / tcgen05 operation inside the "_elect" wrappers (see ltt_ptx.cuh).
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_addr = smem_u32(full_bar), empty_addr = smem_u32(empty_bar), accfull_addr = smem_u32(acc_full);
     // Weights are not produced by the predecessor (w_static): the producer starts streaming the B tiles of its first
     // unit's first STAGES iterations BEFORE waiting on the predecessor grid, so the HBM latency of the weight stream
     // hides behind the predecessor's tail.  Only the activation (A) loads wait.
     int npre = 0;
-    if (warp == 0 && lane == 0 && args.w_static && (int)blockIdx.x < total_units) {
+    if (warp == 0 && args.w_static && !pair && (int)blockIdx.x < total_units) {
         const int unit = blockIdx.x;
         const int z = unit % args.splits, tile = unit / args.splits;
         const int n0 = (tile % args.ntiles) * BN;
         const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
         npre = min(STAGES, it1 - it0);
         for (int i = 0; i < npre; ++i) {
-            mbar_expect_tx(&full_bar[i], SM::STAGE_BYTES);
-            tma_load_2d(smem + i * SM::STAGE_BYTES + A_TILE_BYTES, &args.bmap, &full_bar[i], (it0 + i) * BK, n0);
+            mbar_expect_tx_elect(full_addr + 8u * i, SM::STAGE_BYTES);
+            tma_load_2d_elect(smem_base + i * SM::STAGE_BYTES + A_TILE_BYTES, &args.bmap, full_addr + 8u * i, (it0 + i) * BK, n0);
         }
     }
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                const int z = unit % args.splits, tile = unit / args.splits;
-                const int n0 = (tile % args.ntiles) * BN, mt = tile / args.ntiles;
-                const int tile_b = mt / tiles_img, trem = mt % tiles_img;
-                const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
-                const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
-                // decode (source, tap, chunk) of the first iteration
-                int s = 0, tap = 0, chunk = 0;
-                {
-                    int rem = it0;
-                    while (s < args.nsrc - 1 && rem >= args.taps[s] * args.kchunks[s]) {
-                        rem -= args.taps[s] * args.kchunks[s];
-                        ++s;
-                    }
-                    tap = rem / args.kchunks[s];
-                    chunk = rem % args.kchunks[s];
+        // ------------------------------------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t full_leader = pair ? dsmem_map(full_addr, 0) : 0u;   // leader's full_bar[0] (cluster window)
+        for (int unit = cta_first; unit < total_units; unit += cta_step) {
+            const int z = pair ? 0 : unit % args.splits, tile = pair ? unit : unit / args.splits;
+            const int n0 = (tile % args.ntiles) * BN;
+            const int mt = pair ? (tile / args.ntiles) * 2 + (int)crank : tile / args.ntiles;
+            const int tile_b = mt / tiles_img, trem = mt % tiles_img;
+            const int b0 = tile_b * tb, y0 = (trem / args.tiles_x) * args.th, x0 = (trem % args.tiles_x) * args.tw;
+            const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
+            // decode (source, tap, chunk) of the first iteration
+            int s = 0, tap = 0, chunk = 0;
+            {
+                int rem = it0;
+                while (s < args.nsrc - 1 && rem >= args.taps[s] * args.kchunks[s]) {
+                    rem -= args.taps[s] * args.kchunks[s];
+                    ++s;
                 }
-                for (int it = it0; it < it1; ++it) {
+                tap = rem / args.kchunks[s];
+                chunk = rem % args.kchunks[s];
+            }
+            for (int it = it0; it < it1; ++it) {
+                const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
+                int dx = 0, dy = 0;
+                if (args.taps[s] == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap % 3 - 1;
+                }
+                const CUtensorMap* am = s == 0 ? &args.amap[0] : (s == 1 ? &args.amap[1] : &args.amap[2]);
+                if constexpr (pair) {
+                    // the stage is free in THIS CTA once the leader's multicast commit arrived here; both CTAs'
+                    // bytes are credited to the leader's full barrier
+                    mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+                    if (crank == 0) mbar_expect_tx_elect(full_addr + 8u * stage, 2 * SM::PAIR_STAGE_BYTES);
+                    const uint32_t fb = full_leader + 8u * stage;
+                    tma_load_4d_2sm_elect(sa, am, fb, chunk * BK, x0 + dx, y0 + dy, b0);
+                    tma_load_2d_2sm_elect(sa + A_TILE_BYTES, &args.bmap, fb, it * BK, n0 + (int)crank * (BN / 2));
+                } else {
                     const bool pre = npre > 0;     // B tile of this iteration is already in flight (see above)
                     if (!pre) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+                        mbar_expect_tx_elect(full_addr + 8u * stage, SM::STAGE_BYTES);
                     } else {
                         --npre;
                     }
-                    uint8_t* sa = smem + stage * SM::STAGE_BYTES;
-                    int dx = 0, dy = 0;
-                    if (args.taps[s] == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
+                    tma_load_4d_elect(sa, am, full_addr + 8u * stage, chunk * BK, x0 + dx, y0 + dy, b0);
+                    if (!pre) tma_load_2d_elect(sa + A_TILE_BYTES, &args.bmap, full_addr + 8u * stage, it * BK, n0);
+                }
+                if (++chunk == args.kchunks[s]) {
+                    chunk = 0;
+                    if (++tap == args.taps[s]) {
+                        tap = 0;
+                        ++s;
                     }
-                    tma_load_4d(sa, &args.amap[s], &full_bar[stage], chunk * BK, x0 + dx, y0 + dy, b0);
-                    if (!pre) tma_load_2d(sa + A_TILE_BYTES, &args.bmap, &full_bar[stage], it * BK, n0);
-                    if (++chunk == args.kchunks[s]) {
-                        chunk = 0;
-                        if (++tap == args.taps[s]) {
-                            tap = 0;
-                            ++s;
-                        }
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        // pair mode: the leader CTA issues 256 x BN x 16 MMAs for both CTAs; its commits are multicast so the producer
+        // (empty) and epilogue (acc_full) barriers of BOTH CTAs are released.
+        if (!pair || crank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(BN, pair ? 256 : 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            int u = 0;
+            for (int unit = cta_first; unit < total_units; unit += cta_step, ++u) {
+                const int z = pair ? 0 : unit % args.splits;
+                const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
+                const int niter = it1 - it0;
+                const int buf = u & 1;
+                // epilogue(s) have drained this accumulator
+                if constexpr (pair) mbar_wait_cluster(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
+                else mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int i = 0; i < niter; ++i) {
+                    if constexpr (pair) mbar_wait_cluster(&full_bar[stage], phase);
+                    else mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if constexpr (pair) umma_f16_2sm_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                        else umma_f16_elect(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                    }
+                    if constexpr (pair) {
+                        umma_commit_2sm_elect(empty_addr + 8u * stage, 3);
+                        if (i == niter - 1) umma_commit_2sm_elect(accfull_addr + 8u * buf, 3);
+                    } else {
+                        umma_commit_elect(empty_addr + 8u * stage);
+                        if (i == niter - 1) umma_commit_elect(accfull_addr + 8u * buf);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_f16(BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        int u = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
-            const int z = unit % args.splits;
-            const int it0 = z * per, it1 = min(args.iters_total, it0 + per);
-            const int niter = it1 - it0;
-            const int buf = u & 1;
-            mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t tacc = tmem_base + buf * BN;
-            for (int i = 0; i < niter; ++i) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-                    umma_commit(&empty_bar[stage]);
-                    if (i == niter - 1) umma_commit(&acc_full[buf]);
-                }
-                __syncwarp();
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
                 }
             }
         }
@@ -451,9 +492,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const bool geglu = e.act == ACT_GEGLU;
         const int Nout = geglu ? args.N / 2 : args.N;
         int u = 0;
-        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++u) {
-            const int z = unit % args.splits, tile = unit / args.splits;
-            const int n0 = (tile % args.ntiles) * BN, mt = tile / args.ntiles;
+        const uint32_t acc_empty_leader = pair ? dsmem_map(smem_u32(acc_empty), 0) : 0u;
+        for (int unit = cta_first; unit < total_units; unit += cta_step, ++u) {
+            const int z = pair ? 0 : unit % args.splits, tile = pair ? unit : unit / args.splits;
+            const int n0 = (tile % args.ntiles) * BN;
+            const int mt = pair ? (tile / args.ntiles) * 2 + (int)crank : tile / args.ntiles;
             const int buf = u & 1;
             RowInfo ri;
             {
@@ -490,7 +533,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             named_bar_sync(2, EPI_THREADS);
             const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-            mbar_wait(&acc_full[buf], (u >> 1) & 1);
+            if (pair) mbar_wait_cluster(&acc_full[buf], (u >> 1) & 1);
+            else mbar_wait(&acc_full[buf], (u >> 1) & 1);
             tc_fence_after();
 
             if (args.splits > 1) {
@@ -599,7 +643,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     default: run_tile(KindTag<EK_GENERIC>{}); break;
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
+                if (pair) mbar_arrive_remote(acc_empty_leader + (uint32_t)buf * 8u);
+                else mbar_arrive(&acc_empty[buf]);
             }
         }
     }
@@ -610,9 +655,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives are in flight
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        if constexpr (pair) tmem_dealloc2<TMEM_COLS>(tmem_base);
+        else tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -702,7 +749,8 @@ struct Variant {
     static int configure() {
         static bool configured = false;
         if (!configured) {
-            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
             configured = true;
         }
         return 0;
@@ -725,19 +773,48 @@ struct Variant {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES>, &cfg) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES, false>, &cfg) != cudaSuccess) {
             cudaGetLastError();
             n = -1;
         }
         cache[S] = n > 0 ? n : -1;
         return cache[S];
     }
+    // CTA-pair launch: clusters of 2, persistent over (M-tile pair, N tile) units
+    static int launch_pair(GemmDeviceArgs& a, int cluster_units, cudaStream_t stream) {
+        if (int rc = configure()) return rc;
+        a.splits = 1;
+        a.pair = 1;
+        const int mc = max_clusters(2);
+        if (mc <= 0) {
+            set_error("gemm: no resident 2-CTA clusters for BN=%d", BN);
+            return -1;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * std::min(cluster_units, mc), 1, 1);
+        cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = SM::TOTAL;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, a));
+        LTT_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     static int launch(GemmDeviceArgs& a, int ctas, int S, int num_sms, cudaStream_t stream) {
         if (int rc = configure()) return rc;
         a.splits = S;
         if (S == 1) {
             const int grid = ctas < num_sms ? ctas : num_sms;
-            LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
+            LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
@@ -754,7 +831,7 @@ struct Variant {
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at;
             cfg.numAttrs = pdl_enabled() ? 2 : 1;
-            LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, a));
+            LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false>, a));
         }
         LTT_CUDA_OK(cudaGetLastError());
         return 0;
@@ -808,16 +885,45 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
         set_error("gemm: GEGLU needs N %% 128 == 0 (N=%d)", p.N);
         return -1;
     }
+    // CTA-pair mode (cta_group::2): per k-iteration a lone CTA moves (16 KB A + 128*bn B) through shared memory twice
+    // (TMA write + tensor-core read) against 128 B/cycle, which is what bounds the K-deep GEMMs; in a pair each CTA
+    // stages only half of the B tile.  Used for main-loop-bound shapes (>= 10 k-iterations, >= 2 M tiles).
+    static const int pair_mode = getenv("LTT_GEMM_PAIR") ? atoi(getenv("LTT_GEMM_PAIR")) : 1;
     static const int kBN[4] = {64, 128, 160, 256};
     int BN = 128, S = 1;
+    bool use_pair = false;
     double best = 1e30;
+    static const int force_bn = getenv("LTT_GEMM_BN") ? atoi(getenv("LTT_GEMM_BN")) : 0;     // experiments only
     for (int bi = 0; bi < 4; ++bi) {
         const int bn = kBN[bi];
         if (geglu && bn % 128) continue;
+        if (force_bn && bn != force_bn && !(geglu && force_bn % 128)) continue;
         const int nt = (p.N + bn - 1) / bn;
         const int ctas_c = mtiles * nt;
         const double it_cycles = std::max(2.0 * bn, (16384.0 + 128.0 * bn) / 75.0);
         const double epi_cycles = 600.0 + 6.0 * bn;
+        if (pair_mode && mtiles >= 2 && (iters >= 10 || pair_mode == 2) && bn >= 128) {
+            int mc = 0;
+            switch (bn) {
+                case 128: mc = Variant<128, 6>::max_clusters(2); break;
+                case 160: mc = Variant<160, 5>::max_clusters(2); break;
+                default: mc = Variant<256, 4>::max_clusters(2); break;
+            }
+            if (mc > 0) {
+                const int cu = ((mtiles + 1) / 2) * nt;
+                const int waves = (cu + mc - 1) / mc;
+                const double it_pair = 1.1 * std::max(2.0 * bn, 256.0 + bn);
+                const double per_unit = iters * it_pair;
+                const double t = 3500.0 + (waves > 1 ? waves * std::max(per_unit, epi_cycles) + std::min(per_unit, epi_cycles)
+                                                     : per_unit + epi_cycles);
+                if (t < best || (pair_mode == 2 && !use_pair)) {
+                    best = pair_mode == 2 ? 0.0 : t;      // 2: force pair mode wherever it is legal (experiments)
+                    BN = bn;
+                    S = 1;
+                    use_pair = true;
+                }
+            }
+        }
         for (int sp = 1; sp <= 8; ++sp) {
             int resident = num_sms;
             if (sp > 1) {
@@ -845,6 +951,7 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
                 best = t;
                 BN = bn;
                 S = sp;
+                use_pair = false;
             }
         }
     }
@@ -855,11 +962,19 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
     {
         uint64_t dims[2] = {(uint64_t)p.Ktot, (uint64_t)p.N};
         uint64_t str[1] = {(uint64_t)p.Ktot};
-        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};
         int rc = make_tmap_f16(&a.bmap, p.w, 2, dims, str, box);
         if (rc) return rc;
     }
     (void)ws;
+    if (use_pair) {
+        const int cu = ((mtiles + 1) / 2) * ntiles;
+        switch (BN) {
+            case 128: return Variant<128, 6>::launch_pair(a, cu, stream);
+            case 160: return Variant<160, 5>::launch_pair(a, cu, stream);
+            default: return Variant<256, 4>::launch_pair(a, cu, stream);
+        }
+    }
     switch (BN) {
         case 64: return Variant<64, 6>::launch(a, ctas, S, num_sms, stream);
         case 128: return Variant<128, 6>::launch(a, ctas, S, num_sms, stream);

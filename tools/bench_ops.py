@@ -83,6 +83,11 @@ if not only or only == "linear":
     bench_linear(60, 1280, 1280)
     bench_linear(60, 10240, 1280, act=2)
     bench_linear(154, 2560, 768)
+if only == "peak":      # large square-ish GEMMs: the kernel's own main-loop ceiling per tile width / pair mode
+    bench_linear(16384, 4096, 4096)
+    bench_linear(16384, 5120, 2560)
+    bench_conv(16, 64, 64, 320, 320)
+    bench_conv(16, 32, 32, 640, 640)
 if not only or only == "conv":
     bench_conv(2, 64, 64, 320, 320)
     bench_conv(2, 64, 64, 640, 320)
