@@ -29,7 +29,7 @@ struct AttnDeviceArgs {
     float scale_log2;
 };
 
-template <int DPAD, int DV, int BKV, int SBUF>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF>
 struct AttnCfg {
     static constexpr int NKC = DPAD / 64;           // 64-column chunks of Q / K rows
     static constexpr int KSTEPS = DV / 16;          // k16 steps of QK^T (d rounded up to 16)
@@ -41,7 +41,7 @@ struct AttnCfg {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
     static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
-    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int OFF_BAR = OFF_P + PBUF * P_BYTES;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
     static constexpr int TM_S = 0, TM_O = SBUF * BKV;
     static constexpr int TM_USED = SBUF * BKV + DV;
@@ -62,9 +62,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // SBUF = number of S accumulators in TMEM: 2 lets QK^T of tile j+1 overlap the softmax of tile j inside one CTA;
 // 1 (with MINB = 2 CTAs per SM, 256 TMEM columns each) gets the same overlap from the co-resident CTA and doubles
 // the number of softmax warps per SM -- the d=40 level is bound by the softmax warps' issue rate, not by the tensor pipe.
-template <int DPAD, int DV, int BKV, int SBUF, int MINB>
+// PBUF = number of P tiles in shared memory: with 2 (and SBUF = 2) the softmax of tile j+1 never waits for the tensor
+// core -- S(j+1) was produced while tile j was exponentiated and P(j+1) goes to the other buffer while PV(j) runs.
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB>
 __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
-    using C = AttnCfg<DPAD, DV, BKV, SBUF>;
+    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -75,11 +77,13 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
     uint64_t* v_empty = bars + 7;       // 2
     uint64_t* s_full = bars + 9;        // 2
     uint64_t* s_empty = bars + 11;      // 2  (count 128)
-    uint64_t* p_full = bars + 13;       // 1  (count 128)
-    uint64_t* pv_done = bars + 14;      // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* p_full = bars + 13;       // 2  (count 128)
+    uint64_t* pv_done = bars + 15;      // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: warp-uniform for ptxas, so the producer / MMA-issuer loops below stay on the uniform
+    // datapath (their TMA / tcgen05 operations are issued by one elected lane inside the "_elect" wrappers)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
     const int nt = (args.nk + BKV - 1) / BKV;
 
@@ -95,82 +99,76 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 128);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&pv_done[i], 1);
         }
-        mbar_init(p_full, 128);
-        mbar_init(pv_done, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<C::TM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_launch_dependents();     // programmatic dependent launch: see ltt_ptx.cuh
     pdl_wait();
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);     // barrier i lives at bar_base + 8 * i (same order as the pointers above)
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(q_full, C::Q_BYTES);
+        mbar_expect_tx_elect(bar_base + 0, C::Q_BYTES);
+        for (int c = 0; c < C::NKC; ++c)
+            tma_load_3d_elect(smem_base + c * (128 * 128), &args.qmap, bar_base + 0, head * DPAD + c * 64, q0, b);
+        for (int j = 0; j < nt; ++j) {
+            const int st = j & 1;
+            const uint32_t par = ((j >> 1) & 1) ^ 1;
+            mbar_wait(&k_empty[st], par);
+            mbar_expect_tx_elect(bar_base + 8 * (1 + st), C::K_BYTES);
             for (int c = 0; c < C::NKC; ++c)
-                tma_load_3d(smem + c * (128 * 128), &args.qmap, q_full, head * DPAD + c * 64, q0, b);
-            for (int j = 0; j < nt; ++j) {
-                const int st = j & 1;
-                const uint32_t par = ((j >> 1) & 1) ^ 1;
-                mbar_wait(&k_empty[st], par);
-                mbar_expect_tx(&k_full[st], C::K_BYTES);
-                for (int c = 0; c < C::NKC; ++c)
-                    tma_load_3d(smem + C::OFF_K + st * C::K_BYTES + c * (BKV * 128), &args.kmap, &k_full[st],
-                                head * DPAD + c * 64, j * BKV, b);
-                mbar_wait(&v_empty[st], par);
-                mbar_expect_tx(&v_full[st], C::V_BYTES);
-                for (int c = 0; c < C::NVC; ++c)
-                    tma_load_3d(smem + C::OFF_V + st * C::V_BYTES + c * (DV * 128), &args.vmap, &v_full[st],
-                                j * BKV + c * 64, head * args.dhead, b);
-            }
+                tma_load_3d_elect(smem_base + C::OFF_K + st * C::K_BYTES + c * (BKV * 128), &args.kmap, bar_base + 8 * (1 + st),
+                                  head * DPAD + c * 64, j * BKV, b);
+            mbar_wait(&v_empty[st], par);
+            mbar_expect_tx_elect(bar_base + 8 * (5 + st), C::V_BYTES);
+            for (int c = 0; c < C::NVC; ++c)
+                tma_load_3d_elect(smem_base + C::OFF_V + st * C::V_BYTES + c * (DV * 128), &args.vmap, bar_base + 8 * (5 + st),
+                                  j * BKV + c * 64, head * args.dhead, b);
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc_qk = umma_idesc_f16(BKV);
         constexpr uint32_t idesc_pv = umma_idesc_f16(DV);
-        const uint32_t sq = smem_u32(smem);
-        const uint32_t sk = smem_u32(smem + C::OFF_K);
-        const uint32_t sv = smem_u32(smem + C::OFF_V);
-        const uint32_t sp = smem_u32(smem + C::OFF_P);
+        const uint32_t sq = smem_base;
+        const uint32_t sk = smem_base + C::OFF_K;
+        const uint32_t sv = smem_base + C::OFF_V;
+        const uint32_t sp = smem_base + C::OFF_P;
         auto issue_qk = [&](int j) {
             const int st = j & 1, sb = j % SBUF;
             mbar_wait(&k_full[st], (j >> 1) & 1);
             if (j >= SBUF) mbar_wait(&s_empty[sb], ((j / SBUF) - 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
 #pragma unroll
-                for (int kk = 0; kk < C::KSTEPS; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(sq + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
-                    const uint64_t bd = umma_desc_sw128(sk + st * C::K_BYTES + (kk >> 2) * (BKV * 128)) + 2 * (kk & 3);
-                    umma_f16(tmem_base + C::TM_S + sb * BKV, ad, bd, idesc_qk, kk != 0);
-                }
-                umma_commit(&k_empty[st]);
-                umma_commit(&s_full[sb]);
+            for (int kk = 0; kk < C::KSTEPS; ++kk) {
+                const uint64_t ad = umma_desc_sw128(sq + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+                const uint64_t bd = umma_desc_sw128(sk + st * C::K_BYTES + (kk >> 2) * (BKV * 128)) + 2 * (kk & 3);
+                umma_f16_elect(tmem_base + C::TM_S + sb * BKV, ad, bd, idesc_qk, kk != 0);
             }
-            __syncwarp();
+            umma_commit_elect(bar_base + 8 * (3 + st));      // k_empty[st]
+            umma_commit_elect(bar_base + 8 * (9 + sb));      // s_full[sb]
         };
         mbar_wait(q_full, 0);
         issue_qk(0);
         for (int j = 0; j < nt; ++j) {
             if (SBUF == 2 && j + 1 < nt) issue_qk(j + 1);
-            const int st = j & 1;
+            const int st = j & 1, pb = j % PBUF;
             mbar_wait(&v_full[st], (j >> 1) & 1);
-            mbar_wait(p_full, j & 1);
+            mbar_wait(&p_full[pb], (j / PBUF) & 1);
             tc_fence_after();
-            if (lane == 0) {
 #pragma unroll
-                for (int kk = 0; kk < BKV / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(sp + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
-                    const uint64_t bd = umma_desc_sw128(sv + st * C::V_BYTES + (kk >> 2) * (DV * 128)) + 2 * (kk & 3);
-                    umma_f16(tmem_base + C::TM_O, ad, bd, idesc_pv, (j | kk) != 0);
-                }
-                umma_commit(&v_empty[st]);
-                umma_commit(pv_done);
+            for (int kk = 0; kk < BKV / 16; ++kk) {
+                const uint64_t ad = umma_desc_sw128(sp + pb * C::P_BYTES + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+                const uint64_t bd = umma_desc_sw128(sv + st * C::V_BYTES + (kk >> 2) * (DV * 128)) + 2 * (kk & 3);
+                umma_f16_elect(tmem_base + C::TM_O, ad, bd, idesc_pv, (j | kk) != 0);
             }
-            __syncwarp();
+            umma_commit_elect(bar_base + 8 * (7 + st));      // v_empty[st]
+            umma_commit_elect(bar_base + 8 * (15 + pb));     // pv_done[pb]
             if (SBUF == 1 && j + 1 < nt) issue_qk(j + 1);
         }
     } else {
@@ -181,18 +179,18 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-        uint8_t* sP = smem + C::OFF_P;
         float m_used = -INFINITY, l = 0.f;
         const float sc = args.scale_log2;
         for (int j = 0; j < nt; ++j) {
-            const int sb = j % SBUF;
+            const int sb = j % SBUF, pb = j % PBUF;
+            uint8_t* sP = smem + C::OFF_P + pb * C::P_BYTES;
             const int kvalid = args.nk - j * BKV;   // >= 1
             const bool tail = kvalid < BKV;
             const uint32_t ts = trow + C::TM_S + sb * BKV;
             mbar_wait(&s_full[sb], (j / SBUF) & 1);
             tc_fence_after();
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);      // P buffer and O are free again
+            if (j >= PBUF) {
+                mbar_wait(&pv_done[pb], ((j / PBUF) - 1) & 1);      // P[pb] is free again (PBUF == 1: and O is up to date)
                 tc_fence_after();
             }
             // exponentiate the tile against reference `mref`, write P, return the row sum; track the raw tile maximum
@@ -256,6 +254,10 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                 const bool need = mx > m_used + 8.0f;
                 const float m_new = need ? mx : m_used;
                 if (j > 0 && __any_sync(0xffffffffu, need)) {
+                    if (PBUF == 2) {      // O must hold every PV up to tile j-1 before it is rescaled
+                        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                        tc_fence_after();
+                    }
                     const float f = need ? ex2_approx(m_used - m_new) : 1.0f;
                     l *= f;
 #pragma unroll
@@ -276,9 +278,9 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
             tc_fence_before();
             mbar_arrive(&s_empty[sb]);
             fence_async_smem();
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[pb]);
         }
-        mbar_wait(pv_done, (nt - 1) & 1);
+        mbar_wait(&pv_done[(nt - 1) % PBUF], ((nt - 1) / PBUF) & 1);
         tc_fence_after();
         const float inv = 1.0f / l;
         const bool valid = (q0 + r) < args.nq;
@@ -310,20 +312,20 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
     }
 }
 
-template <int DPAD, int DV, int BKV, int SBUF, int MINB>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
-    using C = AttnCfg<DPAD, DV, BKV, SBUF>;
+    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
         if (getenv("LTT_VERBOSE")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, ATT_THREADS, C::TOTAL);
-            fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, MINB, C::TOTAL, nb);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, ATT_THREADS, C::TOTAL);
+            fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, PBUF, MINB, C::TOTAL, nb);
         }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, MINB>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -333,7 +335,8 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     memset(&a, 0, sizeof(a));
     const int rowlen = p.heads * p.dpad;
     int bkv, dv;
-    if (p.dhead == 40 && p.dpad == 64) { bkv = (getenv("LTT_ATTN40") && atoi(getenv("LTT_ATTN40")) == 1) ? 64 : 128; dv = 48; }
+    static const int v40 = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;      // d = 40 variant (experiments)
+    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
@@ -373,14 +376,14 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     a.scale_log2 = p.scale * 1.4426950408889634f;
     dim3 grid((p.nq + 127) / 128, p.heads, p.B);
     if (dv == 48) {
-        static int v = -1;
-        if (v < 0) v = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;
-        if (v == 1) return attn_launch_variant<64, 48, 64, 1, 3>(a, grid, stream);
-        return attn_launch_variant<64, 48, 128, 1, 2>(a, grid, stream);
+        if (v40 == 1) return attn_launch_variant<64, 48, 64, 1, 1, 3>(a, grid, stream);
+        if (v40 == 2) return attn_launch_variant<64, 48, 64, 2, 2, 2>(a, grid, stream);
+        if (v40 == 3) return attn_launch_variant<64, 48, 128, 2, 2, 1>(a, grid, stream);
+        return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
     }
-    if (dv == 80) return attn_launch_variant<128, 80, 128, 2, 1>(a, grid, stream);
-    if (dv == 160) return attn_launch_variant<192, 160, 64, 2, 1>(a, grid, stream);
-    return attn_launch_variant<64, 16, 128, 2, 1>(a, grid, stream);
+    if (dv == 80) return attn_launch_variant<128, 80, 128, 2, 2, 1>(a, grid, stream);
+    if (dv == 160) return attn_launch_variant<192, 160, 64, 2, 2, 1>(a, grid, stream);
+    return attn_launch_variant<64, 16, 128, 2, 2, 1>(a, grid, stream);
 }
 
 }  // namespace ltt

@@ -909,8 +909,9 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
                 case 160: mc = Variant<160, 5>::max_clusters(2); break;
                 default: mc = Variant<256, 4>::max_clusters(2); break;
             }
-            if (mc > 0) {
-                const int cu = ((mtiles + 1) / 2) * nt;
+            const int cu = ((mtiles + 1) / 2) * nt;
+            // measured: the pair only pays once every CTA walks several tiles (cluster sync + remote barriers cost ~1.5 us)
+            if (mc > 0 && (cu >= 2 * mc || pair_mode == 2)) {
                 const int waves = (cu + mc - 1) / mc;
                 const double it_pair = 1.1 * std::max(2.0 * bn, 256.0 + bn);
                 const double per_unit = iters * it_pair;

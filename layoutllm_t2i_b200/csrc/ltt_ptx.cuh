@@ -139,6 +139,15 @@ __device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_addr, const CUte
         ::"r"(smem_addr), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t smem_addr, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
+                                                  int c2) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n"
+        ::"r"(smem_addr), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_elect(uint32_t smem_addr, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
                                                   int c2, int c3) {
     asm volatile(
