@@ -13,7 +13,14 @@
 namespace ltt {
 
 __device__ __forceinline__ float r16f(float x) { return __half2float(__float2half_rn(x)); }
-__device__ __forceinline__ float siluf(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with ex2.approx / rcp.approx (2 MUFU + 3 FMA-pipe ops; the IEEE division cost ~15 instructions per
+// element and made GroupNorm+SiLU instruction bound).  Relative error ~2e-7, far below the fp16 rounding that follows.
+__device__ __forceinline__ float siluf(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // stats[b][g] = {sum, sumsq} in double (zeroed by the caller).  Input = channel concat of up to two NHWC tensors.
@@ -145,8 +152,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     pdl_launch_dependents();
     extern __shared__ uint4 gn_slab[];                 // [px_per_cta][V] when stage
     __shared__ float part[GN_THREADS * 8];             // per-thread (sum, sumsq) of its 4 channel pairs
+    __shared__ float2 sub2[GN_THREADS];                // second-level partial sums
     __shared__ double colsum[GN_THREADS * 2];          // [V*4 pair columns][2]  (V <= GN_THREADS/4 by host check)
     __shared__ double cta_stats[2 * GN_MAXG];          // this CTA's (sum, sumsq) per group -- read by the whole cluster
+    __shared__ double all_stats[2 * GN_MAXG * GN_S];   // every rank's cta_stats, gathered through DSMEM
     __shared__ float2 mr[GN_MAXG];
     const int tid = threadIdx.x;
     const int rank = blockIdx.x;                       // cluster dims (GN_S,1,1), gridDim.x == GN_S
@@ -168,16 +177,28 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     }
     pdl_wait();
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int UNR = 8;      // independent 16-byte loads in flight per thread (the pass is latency bound otherwise)
     if (active) {
-        for (int p = p0 + r; p < p1; p += R) {
-            const uint4 u = *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
-            if (stage) gn_slab[(p - p0) * V + v] = u;
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+        for (int pb = p0 + r; pb < p1; pb += R * UNR) {
+            uint4 u[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
-                s[k] += f.x + f.y;
-                ss[k] += f.x * f.x + f.y * f.y;
+            for (int i = 0; i < UNR; ++i) {
+                const int p = pb + i * R;
+                if (p < p1) u[i] = *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
+            }
+#pragma unroll
+            for (int i = 0; i < UNR; ++i) {
+                const int p = pb + i * R;
+                if (p < p1) {
+                    if (stage) gn_slab[(p - p0) * V + v] = u[i];
+                    const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = __half22float2(h[k]);
+                        s[k] += f.x + f.y;
+                        ss[k] += f.x * f.x + f.y * f.y;
+                    }
+                }
             }
         }
 #pragma unroll
@@ -188,12 +209,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     }
     __syncthreads();
     const int PC = V * 4;                              // channel-pair columns of the slab
+    // two-level reduction over the R pixel rows of every pair column (fixed order: deterministic)
+    int SUB = 1;
+    while (SUB < 8 && PC * SUB * 2 <= GN_THREADS) SUB *= 2;
+    if (tid < PC * SUB) {
+        const int pc = tid / SUB, sub = tid - pc * SUB;
+        const int vv = pc >> 2, k = pc & 3;
+        float a = 0.f, q = 0.f;
+        for (int rr = sub; rr < R; rr += SUB) {
+            a += part[(rr * V + vv) * 8 + 2 * k];
+            q += part[(rr * V + vv) * 8 + 2 * k + 1];
+        }
+        sub2[tid] = make_float2(a, q);
+    }
+    __syncthreads();
     if (tid < PC) {
         double a = 0.0, q = 0.0;
-        const int vv = tid >> 2, k = tid & 3;
-        for (int rr = 0; rr < R; ++rr) {
-            a += (double)part[(rr * V + vv) * 8 + 2 * k];
-            q += (double)part[(rr * V + vv) * 8 + 2 * k + 1];
+        for (int i = 0; i < SUB; ++i) {
+            const float2 f = sub2[tid * SUB + i];
+            a += (double)f.x;
+            q += (double)f.y;
         }
         colsum[2 * tid] = a;
         colsum[2 * tid + 1] = q;
@@ -206,13 +241,17 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
         cta_stats[tid] = a;
     }
     cluster_sync_all();                                // every CTA's cta_stats is complete and visible
+    if (tid < 2 * GN_MAXG * GN_S) {                    // one remote load per thread, all in flight together
+        const int rk = tid / (2 * GN_MAXG), e = tid % (2 * GN_MAXG);
+        all_stats[tid] = e < 2 * G ? dsmem_ld_f64(dsmem_map(smem_u32(&cta_stats[e]), rk)) : 0.0;
+    }
+    cluster_arrive();                                  // done reading peers; matching wait at the end
+    __syncthreads();
     if (tid < G) {
         double sm = 0.0, sq = 0.0;
-        const uint32_t base = smem_u32(&cta_stats[2 * tid]);
-        for (int rk = 0; rk < GN_S; ++rk) {
-            const uint32_t a = dsmem_map(base, rk);
-            sm += dsmem_ld_f64(a);
-            sq += dsmem_ld_f64(a + 8);
+        for (int rk = 0; rk < GN_S; ++rk) {            // fixed rank order: deterministic
+            sm += all_stats[rk * 2 * GN_MAXG + 2 * tid];
+            sq += all_stats[rk * 2 * GN_MAXG + 2 * tid + 1];
         }
         const double n = (double)cpg * HW;
         const double mean = sm / n;
@@ -220,28 +259,46 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
         if (var < 0) var = 0;
         mr[tid] = make_float2((float)mean, rsqrtf((float)var + eps));
     }
-    cluster_arrive();                                  // done reading peers; matching wait at the end
     __syncthreads();
     if (active) {
-        float2 m4[4];
+        // y = x * a + b with a = rstd * gamma, b = beta - mean * a (the formulation of PyTorch's own GroupNorm kernel)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m4[k] = mr[(v * 8 + 2 * k) / cpg];   // cpg is even: a pair never straddles groups
-        for (int p = p0 + r; p < p1; p += R) {
-            const uint4 u = stage ? gn_slab[(p - p0) * V + v] : *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
-            __half2 o[4];
+        for (int k = 0; k < 4; ++k) {
+            const float2 m = mr[(v * 8 + 2 * k) / cpg];   // cpg is even: a pair never straddles groups
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
-                float a = r16f((f.x - m4[k].x) * m4[k].y * g[2 * k] + bt[2 * k]);
-                float d = r16f((f.y - m4[k].x) * m4[k].y * g[2 * k + 1] + bt[2 * k + 1]);
-                if (silu) {
-                    a = siluf(a);
-                    d = siluf(d);
-                }
-                o[k] = __floats2half2_rn(a, d);
+            for (int e = 0; e < 2; ++e) {
+                const float a = m.y * g[2 * k + e];
+                bt[2 * k + e] = bt[2 * k + e] - m.x * a;
+                g[2 * k + e] = a;
             }
-            *reinterpret_cast<uint4*>(out + ((size_t)b * HW + p) * C + c) = *reinterpret_cast<uint4*>(o);
+        }
+        constexpr int UN2 = 4;
+        for (int pb = p0 + r; pb < p1; pb += R * UN2) {
+            uint4 u[UN2];
+#pragma unroll
+            for (int i = 0; i < UN2; ++i) {
+                const int p = pb + i * R;
+                if (p < p1)
+                    u[i] = stage ? gn_slab[(p - p0) * V + v] : *reinterpret_cast<const uint4*>(src + ((size_t)b * HW + p) * ld);
+            }
+#pragma unroll
+            for (int i = 0; i < UN2; ++i) {
+                const int p = pb + i * R;
+                if (p >= p1) continue;
+                const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+                __half2 o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h[k]);
+                    __half2 y = __floats2half2_rn(fmaf(f.x, g[2 * k], bt[2 * k]), fmaf(f.y, g[2 * k + 1], bt[2 * k + 1]));
+                    if (silu) {
+                        const float2 yf = __half22float2(y);
+                        y = __floats2half2_rn(siluf(yf.x), siluf(yf.y));
+                    }
+                    o[k] = y;
+                }
+                *reinterpret_cast<uint4*>(out + ((size_t)b * HW + p) * C + c) = *reinterpret_cast<uint4*>(o);
+            }
         }
     }
     cluster_wait();                                    // no CTA exits while a peer may still read its cta_stats
@@ -398,26 +455,29 @@ int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamm
 // ------------------------------------------------------------------------------------------------ first / last conv
 // input_blocks.0.0: Conv2d(4 -> Cout, 3x3, pad 1) on NCHW fp32 x; inputs and weights rounded to fp16 (autocast),
 // fp32 accumulate, NHWC fp16 out.  w: [Cout, Cin, 3, 3] fp32.
-constexpr int CIN_PIX = 16;   // pixels per block
+constexpr int CIN_PIX = 32;   // pixels per block
+// One block = CIN_PIX consecutive pixels x all output channels (one thread per channel).  The fp16-rounded weights sit
+// in shared memory as [K][Cout + 2] (the +2 keeps the transposing fill free of bank conflicts), the input patches as
+// [K][CIN_PIX] so a thread reads four pixels per 16-byte shared load.
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                int B, int Cin, int H, int W, int Cout, __half* __restrict__ out) {
     pdl_launch_dependents();
-    pdl_wait();
     extern __shared__ float smem_ci[];
-    const int K = Cin * 9;
-    float* patch = smem_ci;                                   // [CIN_PIX][K]
-    __half* wt = reinterpret_cast<__half*>(patch + CIN_PIX * K);   // [K][Cout], fp16-rounded weights
+    const int K = Cin * 9, WS = Cout + 2;
+    float* patch = smem_ci;                                        // [K][CIN_PIX]
+    __half* wt = reinterpret_cast<__half*>(patch + CIN_PIX * K);   // [K][WS], fp16-rounded weights
     const int pix0 = blockIdx.x * CIN_PIX, total = B * H * W;
-    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-        const int co = i / K, k = i % K;                      // coalesced global read, transposed smem write
-        wt[k * Cout + co] = __float2half_rn(w[i]);
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {     // weights are static: filled before the PDL wait
+        const int co = i / K, k = i - co * K;
+        wt[k * WS + co] = __float2half_rn(w[i]);
     }
+    pdl_wait();
     for (int i = threadIdx.x; i < CIN_PIX * K; i += blockDim.x) {
-        const int p = i / K, k = i % K, pix = pix0 + p;
+        const int k = i / CIN_PIX, p = i - k * CIN_PIX, pix = pix0 + p;
         float v = 0.f;
         if (pix < total) {
-            const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
-            const int ci = k / 9, t = k % 9, yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+            const int b = pix / (H * W), rem = pix - b * (H * W), y = rem / W, xx = rem - y * W;
+            const int ci = k / 9, t = k - ci * 9, yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
             if (yy >= 0 && yy < H && xs >= 0 && xs < W) v = r16f(x[((size_t)(b * Cin + ci) * H + yy) * W + xs]);
         }
         patch[i] = v;
@@ -428,9 +488,16 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
         for (int p = 0; p < CIN_PIX; ++p) acc[p] = 0.f;
         for (int k = 0; k < K; ++k) {
-            const float ww = __half2float(wt[k * Cout + co]);
+            const float ww = __half2float(wt[k * WS + co]);
+            const float4* pr = reinterpret_cast<const float4*>(patch + k * CIN_PIX);
 #pragma unroll
-            for (int p = 0; p < CIN_PIX; ++p) acc[p] += patch[p * K + k] * ww;
+            for (int q = 0; q < CIN_PIX / 4; ++q) {
+                const float4 pv = pr[q];
+                acc[4 * q] += pv.x * ww;
+                acc[4 * q + 1] += pv.y * ww;
+                acc[4 * q + 2] += pv.z * ww;
+                acc[4 * q + 3] += pv.w * ww;
+            }
         }
         const float bb = bias[co];
 #pragma unroll
@@ -442,60 +509,89 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 int conv_in_launch(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
                    __half* out, cudaStream_t st) {
     const int K = Cin * 9, total = B * H * W;
-    const size_t smem = (size_t)CIN_PIX * K * sizeof(float) + (size_t)K * Cout * sizeof(__half);
+    const size_t smem = (size_t)CIN_PIX * K * sizeof(float) + (size_t)K * (Cout + 2) * sizeof(__half);
     if (smem > 48 * 1024) {
         set_error("conv_in: Cin=%d Cout=%d needs %zu B of shared memory", Cin, Cout, smem);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(conv_in_kernel, dim3((total + CIN_PIX - 1) / CIN_PIX), dim3(128), smem, st, x, w, bias, B, Cin, H, W, Cout, out));
+    const int threads = std::min(320, (Cout + 31) / 32 * 32);
+    LTT_CUDA_OK(launch_k(conv_in_kernel, dim3((total + CIN_PIX - 1) / CIN_PIX), dim3(threads), smem, st, x, w, bias, B, Cin, H, W, Cout, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// out.2: Conv2d(C -> Cout(4), 3x3, pad 1) on NHWC fp16 input (already GN+SiLU), w packed [Cout][9][C] fp16,
-// NCHW fp32 out (values rounded to fp16 as the autocast reference returns half).  One warp per pixel.
-__global__ void conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
-                                int B, int H, int W, int C, int Cout, float* __restrict__ out) {
+// out.2: Conv2d(C -> Cout(<= 4), 3x3, pad 1) on NHWC fp16 input (already GN+SiLU), w packed [Cout][9][C] fp16,
+// NCHW fp32 out (values rounded to fp16 as the autocast reference returns half).  One warp per pixel: lanes split the
+// channels in 16-byte vectors, the nine taps' loads are issued back to back; the 23 KB of weights are staged in shared
+// memory once per block (filled before the PDL wait -- they are static).
+constexpr int COUT_WARPS = 8, COUT_PIX_PER_WARP = 4;
+__global__ void __launch_bounds__(COUT_WARPS * 32) conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                                                  const float* __restrict__ bias, int B, int H, int W, int C,
+                                                                  int Cout, float* __restrict__ out) {
     pdl_launch_dependents();
+    extern __shared__ uint4 smem_co[];                    // [Cout*9*C/8] packed weights
+    const int nw = Cout * 9 * C / 8;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) smem_co[i] = reinterpret_cast<const uint4*>(w)[i];
     pdl_wait();
-    const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (pix >= B * H * W) return;
-    const int b = pix / (H * W), rem = pix % (H * W), y = rem / W, xx = rem % W;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
-        if (yy < 0 || yy >= H || xs < 0 || xs >= W) continue;
-        const __half* xr = x + ((size_t)(b * H + yy) * W + xs) * C;
-        for (int c = lane * 2; c < C; c += 64) {
-            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(xr + c));
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int V = C >> 3;                                  // 16-byte vectors per pixel
+    const int total = B * H * W;
+    for (int pp = 0; pp < COUT_PIX_PER_WARP; ++pp) {
+        const int pix = (blockIdx.x * COUT_WARPS + warp) * COUT_PIX_PER_WARP + pp;
+        if (pix >= total) break;
+        const int b = pix / (H * W), rem = pix - b * (H * W), y = rem / W, xx = rem - y * W;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int cv = lane; cv < V; cv += 32) {
+            uint4 xv[9];
 #pragma unroll
-            for (int co = 0; co < 4; ++co)
-                if (co < Cout) {
-                    const float2 ww = __half22float2(*reinterpret_cast<const __half2*>(w + ((size_t)co * 9 + t) * C + c));
-                    acc[co] += v.x * ww.x + v.y * ww.y;
-                }
+            for (int t = 0; t < 9; ++t) {
+                const int yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+                const bool in = yy >= 0 && yy < H && xs >= 0 && xs < W;
+                xv[t] = in ? *reinterpret_cast<const uint4*>(x + ((size_t)(b * H + yy) * W + xs) * C + cv * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const __half2* xh = reinterpret_cast<const __half2*>(&xv[t]);
+#pragma unroll
+                for (int co = 0; co < 4; ++co)
+                    if (co < Cout) {
+                        const uint4 wv = smem_co[(co * 9 + t) * V + cv];
+                        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 a = __half22float2(xh[k]), ww = __half22float2(wh[k]);
+                            acc[co] += a.x * ww.x + a.y * ww.y;
+                        }
+                    }
+            }
         }
-    }
 #pragma unroll
-    for (int co = 0; co < 4; ++co) {
+        for (int co = 0; co < 4; ++co) {
 #pragma unroll
-        for (int o = 16; o; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    }
-    if (lane < Cout && lane < 4) {
-        float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        out[((size_t)(b * Cout + lane) * H + y) * W + xx] = r16f(a + bias[lane]);
+            for (int o = 16; o; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        }
+        if (lane < Cout && lane < 4) {
+            const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+            out[((size_t)(b * Cout + lane) * H + y) * W + xx] = r16f(a + bias[lane]);
+        }
     }
 }
 
 int conv_out_launch(const __half* x, const __half* w, const float* bias, int B, int H, int W, int C, int Cout,
                     float* out, cudaStream_t st) {
-    if (Cout > 4 || (C & 1)) {
+    const size_t smem = (size_t)Cout * 9 * C * 2;
+    if (Cout > 4 || (C & 7) || smem > 96 * 1024) {
         set_error("conv_out: unsupported Cout=%d C=%d", Cout, C);
         return -1;
     }
-    const int wpb = 8, total = B * H * W;
-    LTT_CUDA_OK(launch_k(conv_out_kernel, dim3((total + wpb - 1) / wpb), dim3(wpb * 32), 0, st, x, w, bias, B, H, W, C, Cout, out));
+    static bool configured = false;
+    if (!configured) {
+        LTT_CUDA_OK(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    const int per_block = COUT_WARPS * COUT_PIX_PER_WARP, total = B * H * W;
+    LTT_CUDA_OK(launch_k(conv_out_kernel, dim3((total + per_block - 1) / per_block), dim3(COUT_WARPS * 32), smem, st, x, w, bias, B, H, W, C, Cout, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -801,60 +897,84 @@ int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, 
     return 0;
 }
 
-// 30-query x (<= 32)-key cross attention of the relation path.  One warp per (b, head, query): lane j owns key j;
-// the q.k dot products run over d with the K row read per lane, softmax by warp shuffles, PV with lanes over d.
-// q: [B, nq, C], k/v: [B, nk, C] fp16 row-major, out [B, nq, C] fp16.
-__global__ void small_attn_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
-                                  const __half* __restrict__ v, int ldkv, int nq, int nk, int heads, int d, float scale,
-                                  __half* __restrict__ out) {
+// 30-query x (<= 32)-key cross attention of the relation path.  One block per (batch element, head): q / k / v head
+// slices are staged in shared memory with 16-byte loads (the previous one-warp-per-query version walked them with
+// dependent 4-byte global loads and was pure latency), then one warp per query: lane j owns key j for the logits,
+// softmax by warp shuffles, lanes own channels for P V.  Rounding points follow the fp16 autocast reference
+// (attention.py:127-141): logits and probabilities rounded to fp16.
+// q: [B, nq, ldq], k/v: [B, nk, ldkv] fp16 row-major, out [B, nq, heads*d] fp16.
+constexpr int SA_THREADS = 256;
+__global__ void __launch_bounds__(SA_THREADS) small_attn_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
+                                                               const __half* __restrict__ v, int ldkv, int nq, int nk, int heads,
+                                                               int d, float scale, __half* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait();
-    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const int qi = wid % nq, hh = (wid / nq) % heads, b = wid / (nq * heads);
-    const int C = heads * d;
-    const __half* qr = q + ((size_t)b * nq + qi) * ldq + hh * d;
-    float s = -INFINITY;
-    if (lane < nk) {
-        const __half* kr = k + ((size_t)b * nk + lane) * ldkv + hh * d;
-        float acc = 0.f;
-        for (int c = 0; c < d; c += 2) {
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(qr + c));
-            const float2 bb = __half22float2(*reinterpret_cast<const __half2*>(kr + c));
-            acc += a.x * bb.x + a.y * bb.y;
-        }
-        s = r16f(r16f(acc) * scale);   // reference: fp16 einsum result times scale in fp16
+    extern __shared__ float sa_smem[];
+    const int hh = blockIdx.x, b = blockIdx.y;
+    const int ds = d + 4;                                   // padded row stride (keeps 16-byte alignment, spreads banks)
+    float* qs = sa_smem;                                    // [nq][ds]
+    float* ks = qs + nq * ds;                               // [nk][ds]
+    float* vs = ks + nk * ds;                               // [nk][ds]
+    float* ps = vs + nk * ds;                               // [nq][32] logits, then probabilities
+    const int dv = d >> 3;                                  // 16-byte vectors per head row (host: d % 8 == 0)
+    for (int i = threadIdx.x; i < (nq + 2 * nk) * dv; i += blockDim.x) {
+        const int row = i / dv, cv = i - row * dv;
+        const __half* src;
+        float* dst;
+        if (row < nq) { src = q + ((size_t)b * nq + row) * ldq + hh * d; dst = qs + row * ds; }
+        else if (row < nq + nk) { src = k + ((size_t)b * nk + (row - nq)) * ldkv + hh * d; dst = ks + (row - nq) * ds; }
+        else { src = v + ((size_t)b * nk + (row - nq - nk)) * ldkv + hh * d; dst = vs + (row - nq - nk) * ds; }
+        const uint4 u = *reinterpret_cast<const uint4*>(src + cv * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        float4* d4 = reinterpret_cast<float4*>(dst + cv * 8);
+        d4[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        d4[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
     }
-    float mx = s;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float p = lane < nk ? __expf(s - mx) : 0.f;
-    float sum = p;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    p = r16f(p / sum);
-    for (int c = lane; c < d; c += 32) {
+    __syncthreads();
+    // logits: one (query, key) pair per thread; pairwise accumulation order as the reference-checked first version
+    for (int idx = threadIdx.x; idx < nq * nk; idx += blockDim.x) {
+        const int qi = idx / nk, j = idx - qi * nk;
+        const float4* qr = reinterpret_cast<const float4*>(qs + qi * ds);
+        const float4* kr = reinterpret_cast<const float4*>(ks + j * ds);
         float acc = 0.f;
-        for (int j = 0; j < nk; ++j) {
-            const float pj = __shfl_sync(0xffffffffu, p, j);
-            acc += pj * __half2float(v[((size_t)b * nk + j) * ldkv + hh * d + c]);
+        for (int c = 0; c < (d >> 2); ++c) {
+            const float4 a = qr[c], bb = kr[c];
+            acc += a.x * bb.x + a.y * bb.y;
+            acc += a.z * bb.z + a.w * bb.w;
         }
+        ps[qi * 32 + j] = r16f(r16f(acc) * scale);   // reference: fp16 einsum result times scale in fp16
+    }
+    __syncthreads();
+    if (threadIdx.x < nq) {                                 // softmax of one query row (nk <= 32 keys)
+        float* pr = ps + threadIdx.x * 32;
+        float mx = -INFINITY;
+        for (int j = 0; j < nk; ++j) mx = fmaxf(mx, pr[j]);
+        float sum = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            const float e = __expf(pr[j] - mx);
+            pr[j] = e;
+            sum += e;
+        }
+        for (int j = 0; j < nk; ++j) pr[j] = r16f(pr[j] / sum);
+    }
+    __syncthreads();
+    const int C = heads * d;
+    for (int idx = threadIdx.x; idx < nq * d; idx += blockDim.x) {
+        const int qi = idx / d, c = idx - qi * d;
+        float acc = 0.f;
+        for (int j = 0; j < nk; ++j) acc += ps[qi * 32 + j] * vs[j * ds + c];
         out[((size_t)b * nq + qi) * C + hh * d + c] = __float2half_rn(acc);
     }
 }
 int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int nq, int nk,
                       int heads, int d, float scale, __half* out, cudaStream_t st) {
-    if (nk > 32 || (d & 1)) {
-        set_error("small_attn: nk=%d d=%d unsupported", nk, d);
+    const size_t smem = ((size_t)(nq + 2 * nk) * (d + 4) + (size_t)nq * 32) * sizeof(float);
+    if (nk > 32 || (d & 7) || ldq % 8 || ldkv % 8 || smem > 48 * 1024) {
+        set_error("small_attn: nq=%d nk=%d d=%d unsupported", nq, nk, d);
         return -1;
     }
-    const int warps = B * heads * nq;   // multiple of 1
-    const int wpb = 4;
-    if (warps % wpb) {
-        LTT_CUDA_OK(launch_k(small_attn_kernel, dim3(warps), dim3(32), 0, st, q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out));
-    } else {
-        LTT_CUDA_OK(launch_k(small_attn_kernel, dim3(warps / wpb), dim3(wpb * 32), 0, st, q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out));
-    }
+    LTT_CUDA_OK(launch_k(small_attn_kernel, dim3(heads, B), dim3(SA_THREADS), smem, st, q, ldq, k, v, ldkv, nq, nk, heads, d, scale, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

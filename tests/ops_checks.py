@@ -169,6 +169,18 @@ def check_layernorm(M, C, dtype, seed=0):
     return max(rel(o32, ref), rel(o16.float(), ref) / 4)
 
 
+def check_small_attention(B, nq, nk, heads, d, seed=0):
+    """30 x 10 relation cross-attention core against fp32 torch math on the same fp16 inputs."""
+    C = heads * d
+    q = rn(B, nq, C, seed=seed, dtype=torch.float16)
+    k = rn(B, nk, C, seed=seed + 1, dtype=torch.float16)
+    v = rn(B, nk, C, seed=seed + 2, dtype=torch.float16)
+    out = torch.empty(B, nq, C, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_small_attention(L.ptr(q), L.ptr(k), L.ptr(v), B, nq, nk, heads, d, d ** -0.5, L.ptr(out),
+                                           L.stream_ptr()), "small_attention")
+    return rel(out.float(), attention_ref(q, k, v, heads))
+
+
 def check_rela_scatter_ln(B, nb, h, w, C, seed=0):
     """scatter of pooled box features + (out + x) / 2 + the fused LayerNorm, against plain torch on the same inputs."""
     mo = 30
@@ -247,6 +259,9 @@ ALL = [
     ("groupnorm 3x4 64 (cpg 2, fewer pixels than CTAs)", check_groupnorm, dict(B=3, HW=4, c0=64, c1=0, silu=True, eps=1e-5), 2e-3),
     ("groupnorm concat 2x384 64+128 (cpg 6, ragged pixels)", check_groupnorm, dict(B=2, HW=381, c0=64, c1=128, silu=False, eps=1e-5), 2e-3),
     ("groupnorm 1x9216 960 (slab not staged)", check_groupnorm, dict(B=1, HW=9216, c0=640, c1=320, silu=True, eps=1e-5), 2e-3),
+    ("relation attention 30x10 d=40", check_small_attention, dict(B=2, nq=30, nk=10, heads=8, d=40), 3e-3),
+    ("relation attention 30x10 d=160", check_small_attention, dict(B=1, nq=30, nk=10, heads=8, d=160), 3e-3),
+    ("relation attention 30x3 d=8", check_small_attention, dict(B=3, nq=30, nk=3, heads=8, d=8), 3e-3),
     ("rela scatter + LN 2x32x32 C=640 (uncond half without boxes)", check_rela_scatter_ln, dict(B=2, nb=1, h=32, w=32, C=640), 1e-4),
     ("rela scatter + LN 3x24x16 C=320", check_rela_scatter_ln, dict(B=3, nb=3, h=24, w=16, C=320), 1e-4),
     ("rela scatter + LN 2x8x8 C=1280", check_rela_scatter_ln, dict(B=2, nb=2, h=8, w=8, C=1280), 1e-4),

@@ -72,7 +72,48 @@ def bench_attn(B, heads, d, nq, nk):
     print(f"attention B={B} d={d:3d} nq={nq:5d} nk={nk:5d}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
+def bench_gn(B, HW, c0, c1):
+    x0 = oc.rn(B, HW, c0, dtype=torch.float16)
+    x1 = oc.rn(B, HW, c1, seed=1, dtype=torch.float16) if c1 else None
+    C = c0 + c1
+    g = 1 + 0.1 * oc.rn(C, seed=2)
+    b = 0.1 * oc.rn(C, seed=3)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.float16)
+    fn = lambda: L.check(L.lib().ltt_op_groupnorm(L.ptr(x0), c0, L.ptr(x1), c1, B, HW, L.ptr(g), L.ptr(b), 1e-5, 1, L.ptr(out), L.stream_ptr()), "gn")
+    us = timeit(fn)
+    print(f"groupnorm {B}x{HW} {c0}+{c1}: {us:8.1f} us  {B * HW * C * 4 / us / 1e3:7.1f} GB/s (read+write)", flush=True)
+
+
+def bench_ln(M, C, dtype=torch.float16):
+    x = oc.rn(M, C).to(dtype)
+    g = 1 + 0.1 * oc.rn(C, seed=1)
+    b = 0.1 * oc.rn(C, seed=2)
+    o16 = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    fn = lambda: L.check(L.lib().ltt_op_layernorm(L.ptr(x), 0 if dtype == torch.float16 else 1, M, C, L.ptr(g), L.ptr(b), 1e-5, L.ptr(o16), None, L.stream_ptr()), "ln")
+    us = timeit(fn)
+    print(f"layernorm {M}x{C} {str(dtype)[6:]}: {us:8.1f} us  {M * C * (x.element_size() + 2) / us / 1e3:7.1f} GB/s", flush=True)
+
+
+def bench_small_attn(B, d):
+    C = 8 * d
+    q = oc.rn(B, 30, C, dtype=torch.float16)
+    k = oc.rn(B, 10, C, seed=1, dtype=torch.float16)
+    v = oc.rn(B, 10, C, seed=2, dtype=torch.float16)
+    out = torch.empty(B, 30, C, device=DEV, dtype=torch.float16)
+    fn = lambda: L.check(L.lib().ltt_op_small_attention(L.ptr(q), L.ptr(k), L.ptr(v), B, 30, 10, 8, d, d ** -0.5, L.ptr(out), L.stream_ptr()), "sa")
+    print(f"relation attention B={B} d={d}: {timeit(fn):8.1f} us", flush=True)
+
+
 print(torch.cuda.get_device_name(0))
+if only == "small":
+    for B, HW, c0, c1 in ((2, 4096, 320, 0), (2, 4096, 640, 320), (2, 4096, 320, 320), (2, 1024, 640, 0), (2, 1024, 1280, 640),
+                          (2, 256, 1280, 0), (2, 256, 1280, 1280), (2, 64, 1280, 0), (2, 64, 1280, 1280)):
+        bench_gn(B, HW, c0, c1)
+    for M, C in ((8192, 320), (2048, 640), (512, 1280), (128, 1280), (30, 1280)):
+        bench_ln(M, C)
+    bench_ln(8192, 320, torch.float32)
+    for d in (40, 80, 160):
+        bench_small_attn(1, d)
 if not only or only == "linear":
     for M, C in ((8192, 320), (2048, 640), (512, 1280), (128, 1280)):
         bench_linear(M, C, C)                 # proj / to_out

@@ -43,7 +43,29 @@ def attn_fn(B, heads, d, nq, nk):
                                                     nk, d ** -0.5, L.ptr(out), C, L.stream_ptr()), "attention")
 
 
+def gn_fn(B, HW, c0, c1):
+    x0 = oc.rn(B, HW, c0, dtype=torch.float16)
+    x1 = oc.rn(B, HW, c1, seed=1, dtype=torch.float16) if c1 else None
+    C = c0 + c1
+    g = 1 + 0.1 * oc.rn(C, seed=2)
+    b = 0.1 * oc.rn(C, seed=3)
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.float16)
+    return lambda: L.check(L.lib().ltt_op_groupnorm(L.ptr(x0), c0, L.ptr(x1), c1, B, HW, L.ptr(g), L.ptr(b), 1e-5, 1, L.ptr(out), L.stream_ptr()), "gn")
+
+
+def small_attn_fn(B, d):
+    C = 8 * d
+    q = oc.rn(B, 30, C, dtype=torch.float16)
+    k = oc.rn(B, 10, C, seed=1, dtype=torch.float16)
+    v = oc.rn(B, 10, C, seed=2, dtype=torch.float16)
+    out = torch.empty(B, 30, C, device=DEV, dtype=torch.float16)
+    return lambda: L.check(L.lib().ltt_op_small_attention(L.ptr(q), L.ptr(k), L.ptr(v), B, 30, 10, 8, d, d ** -0.5, L.ptr(out), L.stream_ptr()), "sa")
+
+
 OPS = {
+    "gn0": lambda: gn_fn(2, 4096, 320, 0),
+    "gn960": lambda: gn_fn(2, 4096, 640, 320),
+    "sattn": lambda: small_attn_fn(1, 160),
     "geglu0": lambda: linear_fn(8192, 2560, 320, act=2),
     "geglu1": lambda: linear_fn(2048, 5120, 640, act=2),
     "conv0": lambda: conv_fn(2, 64, 64, 320, 320),
