@@ -143,8 +143,9 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 // statistics buffer, no memset node between the producer GEMM and the consumer (the PDL chain stays intact).
 constexpr int GN_S = 8;          // CTAs per cluster (pixel split)
 constexpr int GN_MAXG = 4;       // groups per cluster
-constexpr int GN_THREADS = 256;
+constexpr int GN_MAXTHREADS = 512;
 
+template <int GN_THREADS>
 __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int ld1, int C, int HW, int cpg, int G,
     int V, int R, int px_per_cta, int stage, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -318,20 +319,23 @@ int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, 
         if ((g * cpg) % 8 == 0 && (G == 0 || GN_S * B * (32 / g) >= 128)) G = g;
     if (G == 0) return 1;
     const int V = G * cpg / 8;
-    if (V > GN_THREADS / 4) return 1;
-    const int R = GN_THREADS / V;
     const int px = (HW + GN_S - 1) / GN_S;
     const size_t slab = (size_t)px * V * 16;
+    // big slabs (level-0 concat inputs) own their SM anyway: 16 warps hide the load / MUFU latency better than 8
+    const int threads = slab > 96 * 1024 ? 512 : 256;
+    if (V > threads / 4) return 1;
+    const int R = threads / V;
     const int stage = slab <= 160 * 1024;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(GN_S, 32 / G, B);
-    cfg.blockDim = dim3(GN_THREADS, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = stage ? slab : 0;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -343,7 +347,11 @@ int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, x0, c0, ld0, x1, ld1, C, HW, cpg, G, V, R, px, stage, gamma, beta, eps,
+    if (threads == 512)
+        LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<512>, x0, c0, ld0, x1, ld1, C, HW, cpg, G, V, R, px, stage, gamma, beta, eps,
+                                       silu, out));
+    else
+    LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<256>, x0, c0, ld0, x1, ld1, C, HW, cpg, G, V, R, px, stage, gamma, beta, eps,
                                    silu, out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
