@@ -140,6 +140,15 @@ int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, 
 int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                            int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
                            void* ln16, void* stream);
+/* Relation cross-attention with to_q / to_out folded into the step-invariant relation K / V (attention.py:315-359):
+ * ltt_op_rela_fold: A[g,h*nrel+j,:] = scale * sum_{c in head h} Wq[c,:] k[g,j,c], Bm[g,h*nrel+j,:] = sum_{c in head h} Wo[:,c] v[g,j,c]
+ *   (wq16 / wo16: [C, C] fp16 row-major nn.Linear weights, kv16: [G, nrel, 2C] fp16 = [k | v]; A16 / Bm16: [G, heads*nrel, C] fp16)
+ * ltt_op_rela_attn_fused: per feature row f: f2 = f + gate * (softmax(LN1(f) . A^T) . Bm + bias), ln2 = LN2(f2)   (fp16 out) */
+int ltt_op_rela_fold(const void* wq16, const void* wo16, const void* kv16, int G, int nrel, int heads, int d, float scale,
+                     void* A16, void* Bm16, void* stream);
+int ltt_op_rela_attn_fused(const void* feats16, int G, int rows_per_g, int C, int heads, int nrel, const void* A16,
+                           const void* Bm16, const float* bias, float gate, const float* g1, const float* b1, const float* g2,
+                           const float* b2, float eps, void* feats2_16, void* ln2_16, void* stream);
 /* 30 x 10 relation cross-attention core (warp shuffles) */
 int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
                            float scale, void* out, void* stream);

@@ -58,6 +58,8 @@ _SIGS = {
     "ltt_op_rela_pool": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ltt_op_rela_scatter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ltt_op_rela_scatter_ln": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp]),
+    "ltt_op_rela_fold": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "ltt_op_rela_attn_fused": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "ltt_op_small_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "ltt_op_posnet_input": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "ltt_op_timestep_embedding": (_i, [_vp, _i, _i, _vp, _vp]),

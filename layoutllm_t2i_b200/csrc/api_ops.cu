@@ -139,6 +139,17 @@ int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats1
     return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
                                gamma, beta, eps, (__half*)ln16, (cudaStream_t)stream);
 }
+int ltt_op_rela_fold(const void* wq16, const void* wo16, const void* kv16, int G, int nrel, int heads, int d, float scale,
+                     void* A16, void* Bm16, void* stream) {
+    return rela_fold_launch((const __half*)wq16, (const __half*)wo16, (const __half*)kv16, G, nrel, heads, d, scale, (__half*)A16,
+                            (__half*)Bm16, (cudaStream_t)stream);
+}
+int ltt_op_rela_attn_fused(const void* feats16, int G, int rows_per_g, int C, int heads, int nrel, const void* A16,
+                           const void* Bm16, const float* bias, float gate, const float* g1, const float* b1, const float* g2,
+                           const float* b2, float eps, void* feats2_16, void* ln2_16, void* stream) {
+    return rela_attn_fused_launch((const __half*)feats16, G, rows_per_g, C, heads, nrel, (const __half*)A16, (const __half*)Bm16,
+                                  bias, gate, g1, b1, g2, b2, eps, (__half*)feats2_16, (__half*)ln2_16, (cudaStream_t)stream);
+}
 int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
                            float scale, void* out, void* stream) {
     return small_attn_launch((const __half*)q, heads * d, (const __half*)k, (const __half*)v, heads * d, B, nq, nk, heads, d, scale,

@@ -55,6 +55,7 @@ struct StW {
     float f_ta = 0, f_td = 0, r_ta = 0, r_td = 0;   // tanh(alpha)
     // per-conditioning caches
     __half *c2_k = nullptr, *c2_vt = nullptr, *fg_k = nullptr, *fg_vt = nullptr, *r_kvbuf = nullptr;
+    __half *r_A = nullptr, *r_Bm = nullptr;          // relation keys / values folded through to_q / to_out (rela_fold_kernel)
 };
 
 struct ConvW { std::string p; int C = 0; Lin conv; };
@@ -134,6 +135,7 @@ struct ltt_model {
     std::map<uint64_t, int> graph_seen;
     cudaStream_t capture_stream = nullptr;
     bool use_graphs = true;
+    bool rela_fused = true;           // LTT_RELA_UNFUSED=1: q-GEMM / attention / out-GEMM as separate launches (A/B checks)
     // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
     struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
     bool prof_on = false;
@@ -632,17 +634,25 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         RC(rela_pool_launch(m->hid32, m->rects[level], ng, mo, H, W, C, m->feats, st));
         m->launches++;
         const int R = ng * mo;
-        RC(ln(m, st, m->feats, DT_F16, R, C, s.r_ln1, m->featln, nullptr));
-        RC(r.gemm(1, R, C, {GemmSrc{m->featln, C, C, 1}}, s.r_q, epi_out(m->featq, C), 1));
-        RC(small_attn_launch(m->featq, C, s.r_kvbuf, s.r_kvbuf + C, 2 * C, ng, mo, m->n_rel, s.heads, s.d,
-                             1.0f / sqrtf((float)s.d), m->featao, st));
-        m->launches++;
-        {
-            GemmEpilogue e = epi_out(m->feats2, C);
-            e.res = m->feats; e.ldr = C; e.has_gate = 1; e.gate = s.r_ta;
-            RC(r.gemm(1, R, C, {GemmSrc{m->featao, C, C, 1}}, s.r_out, e, 1));
+        if (m->rela_fused) {
+            // norm1 -> (to_q, attention over the relation tokens, to_out: folded) -> gated residual -> norm2, one kernel
+            ProfScope ps(m, st, PC_LN, 0.0, (double)R * C * 6.0);
+            RC(rela_attn_fused_launch(m->feats, ng, mo, C, s.heads, m->n_rel, s.r_A, s.r_Bm, s.r_out.bias, s.r_ta, s.r_ln1.g,
+                                      s.r_ln1.b, s.r_ln2.g, s.r_ln2.b, 1e-5f, m->feats2, m->featln, st));
+            m->launches++;
+        } else {
+            RC(ln(m, st, m->feats, DT_F16, R, C, s.r_ln1, m->featln, nullptr));
+            RC(r.gemm(1, R, C, {GemmSrc{m->featln, C, C, 1}}, s.r_q, epi_out(m->featq, C), 1));
+            RC(small_attn_launch(m->featq, C, s.r_kvbuf, s.r_kvbuf + C, 2 * C, ng, mo, m->n_rel, s.heads, s.d,
+                                 1.0f / sqrtf((float)s.d), m->featao, st));
+            m->launches++;
+            {
+                GemmEpilogue e = epi_out(m->feats2, C);
+                e.res = m->feats; e.ldr = C; e.has_gate = 1; e.gate = s.r_ta;
+                RC(r.gemm(1, R, C, {GemmSrc{m->featao, C, C, 1}}, s.r_out, e, 1));
+            }
+            RC(ln(m, st, m->feats2, DT_F16, R, C, s.r_ln2, m->featln, nullptr));
         }
-        RC(ln(m, st, m->feats2, DT_F16, R, C, s.r_ln2, m->featln, nullptr));
         {
             GemmEpilogue e = epi_out(m->featff, 4 * C);
             e.act = ACT_GEGLU;
@@ -953,6 +963,8 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
         RC(A(&s.fg_k, (size_t)B * mo * rowlen * 2, true));
         RC(A(&s.fg_vt, (size_t)B * s.C * 32 * 2, true));
         RC(A(&s.r_kvbuf, (size_t)B * n_rel * 2 * s.C * 2, true));
+        RC(A(&s.r_A, (size_t)B * s.heads * n_rel * s.C * 2, true));
+        RC(A(&s.r_Bm, (size_t)B * s.heads * n_rel * s.C * 2, true));
     }
     return 0;
 }
@@ -978,7 +990,8 @@ int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
     m->cfg = *cfg;
     m->device = device;
     LTT_CUDA_OK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device));
-    m->use_graphs = getenv("LTT_NO_GRAPH") == nullptr;     // debugging / per-launch profiling: eager launches
+    m->use_graphs = getenv("LTT_NO_GRAPH") == nullptr;
+    m->rela_fused = getenv("LTT_RELA_UNFUSED") == nullptr;     // debugging / per-launch profiling: eager launches
     *out = m;
     return 0;
 }
@@ -1118,6 +1131,8 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
         }
         // relation K/V (attention.py:348-349)
         RC(r.gemm(1, B * n_rel, 2 * C, {GemmSrc{m->rel16, cd, cd, 1}}, s.r_kv, epi_out(s.r_kvbuf, 2 * C), 1));
+        // ... folded through to_q / to_out for the fused relation-attention kernel
+        RC(rela_fold_launch(s.r_q.w, s.r_out.w, s.r_kvbuf, B, n_rel, s.heads, s.d, 1.0f / sqrtf((float)s.d), s.r_A, s.r_Bm, st));
     }
     return 0;
 }

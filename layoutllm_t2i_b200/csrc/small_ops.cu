@@ -905,6 +905,225 @@ int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, 
     return 0;
 }
 
+// ---- relation cross-attention with the projections folded into the (step-invariant) relation keys / values.
+// RelationCrossAttention (attention.py:315-359) attends 30 pooled box features to <= 32 relation tokens whose K / V are
+// fixed for a whole sampling run.  With A[h,j,:] = scale * sum_{c in head h} Wq[c,:] k_j[c] and
+// Bm[h,j,:] = sum_{c in head h} Wo[:,c] v_j[c] (rela_fold_kernel, once per conditioning) the chain
+// to_q -> QK^T -> softmax -> PV -> to_out collapses to  logits = LN1(f) . A^T,  out = softmax(logits) . Bm + bias:
+// no C x C weight is streamed per step and the branch's q-GEMM, attention and out-GEMM launches (three ~7 us floors on
+// 30 rows) become part of one row kernel together with both LayerNorms and the gated residual.
+// A, Bm: [G][heads*nrel][C] fp16.
+__global__ void rela_fold_kernel(const __half* __restrict__ wq, const __half* __restrict__ wo, const __half* __restrict__ kv,
+                                 int nrel, int heads, int d, float scale, __half* __restrict__ A, __half* __restrict__ Bm) {
+    const int C = heads * d, HJ = heads * nrel;
+    const int g = blockIdx.z, hj = blockIdx.y, h = hj / nrel, j = hj - h * nrel;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const __half* kr = kv + ((size_t)g * nrel + j) * 2 * C + h * d;      // k_j, head h
+    const __half* vr = kr + C;                                          // v_j, head h
+    float a = 0.f, b = 0.f;
+    for (int cc = 0; cc < d; ++cc) {
+        a += __half2float(wq[(size_t)(h * d + cc) * C + c]) * __half2float(kr[cc]);
+        b += __half2float(wo[(size_t)c * C + h * d + cc]) * __half2float(vr[cc]);
+    }
+    A[((size_t)g * HJ + hj) * C + c] = __float2half_rn(a * scale);
+    Bm[((size_t)g * HJ + hj) * C + c] = __float2half_rn(b);
+}
+int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G, int nrel, int heads, int d, float scale,
+                     __half* A, __half* Bm, cudaStream_t st) {
+    const int C = heads * d;
+    rela_fold_kernel<<<dim3((C + 127) / 128, heads * nrel, G), 128, 0, st>>>(wq, wo, kv, nrel, heads, d, scale, A, Bm);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// One CTA per pooled feature row (g, i):  ln = fp16(LN1(f));  logits[h,j] = fp16(ln . A[g,h,j]);  p = fp16(softmax_j);
+// y = fp16(sum p Bm + bias);  f2 = fp16(f + fp16(gate * y));  ln2 = fp16(LN2(f2)).  Rounding points follow the fp16
+// autocast reference except that q and the per-head attention output are never materialised (fp32 through the fold).
+constexpr int RA_THREADS = 512;
+__global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
+    const __half* __restrict__ feats, int rows_per_g, int C, int heads, int nrel, const __half* __restrict__ A,
+    const __half* __restrict__ Bm, const float* __restrict__ bias, float gate, const float* __restrict__ g1,
+    const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
+    __half* __restrict__ feats2, __half* __restrict__ ln2out) {
+    pdl_launch_dependents();
+    // A / Bm are touched once per UNet evaluation, so they are never L2 resident when this kernel starts: every CTA asks
+    // L2 for its 1/rows_per_g slice of both (they are step invariant -> before the PDL wait, under the predecessor's tail)
+    if (threadIdx.x == 0) {
+        const int i = blockIdx.x % rows_per_g, gq = blockIdx.x / rows_per_g;
+        const size_t total = (size_t)heads * nrel * C * sizeof(__half);
+        const size_t chunk = ((total + rows_per_g - 1) / rows_per_g + 15) & ~(size_t)15;
+        const size_t off = (size_t)i * chunk;
+        if (off < total) {
+            const uint32_t n = (uint32_t)min(chunk, total - off);
+            const char* pa = reinterpret_cast<const char*>(A) + (size_t)gq * total + off;
+            const char* pb = reinterpret_cast<const char*>(Bm) + (size_t)gq * total + off;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(n) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pb), "r"(n) : "memory");
+        }
+    }
+    pdl_wait();
+    extern __shared__ float ra_smem[];
+    float* xs = ra_smem;                 // [C] feature row, later f2
+    float* ls = xs + C;                  // [max(C, 2048)] LN1 output (fp16-rounded), later the partial sums of the out phase
+    float* lg = ls + max(C, 8 * RA_THREADS);   // [heads*nrel] logits, then probabilities
+    __shared__ float red[RA_THREADS / 32];
+    const int row = blockIdx.x, g = row / rows_per_g;
+    const int HJ = heads * nrel;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto block_sum = [&](float v) -> float {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();                 // protects `red` from the previous use
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < RA_THREADS / 32; ++k) t += red[k];
+        return t;
+    };
+    // ---- load + LN1
+    float s = 0.f;
+    for (int c = tid; c < C; c += RA_THREADS) {
+        const float v = __half2float(feats[(size_t)row * C + c]);
+        xs[c] = v;
+        s += v;
+    }
+    const float mean = block_sum(s) / C;
+    float ss = 0.f;
+    for (int c = tid; c < C; c += RA_THREADS) {
+        const float dlt = xs[c] - mean;
+        ss += dlt * dlt;
+    }
+    const float rstd = rsqrtf(block_sum(ss) / C + eps);
+    for (int c = tid; c < C; c += RA_THREADS) ls[c] = r16f((xs[c] - mean) * rstd * g1[c] + b1[c]);
+    __syncthreads();
+    // ---- logits: one warp per (head, relation) column, lanes over C in 16-byte vectors.  The loads of two columns
+    // (up to 2 x 5 vectors per lane, C <= 1280) are issued before any arithmetic: the phase is L2-latency bound.
+    const __half* Ag = A + (size_t)g * HJ * C;
+    const int nvec = C >> 3;
+    for (int hj0 = warp * 2; hj0 < HJ; hj0 += 2 * (RA_THREADS / 32)) {
+        uint4 u[2][5];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int cv = lane + 32 * i;
+                if (hj0 + q < HJ && cv < nvec) u[q][i] = *reinterpret_cast<const uint4*>(Ag + (size_t)(hj0 + q) * C + cv * 8);
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int cv = lane + 32 * i;
+                if (hj0 + q < HJ && cv < nvec) {
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&u[q][i]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = __half22float2(h2[k]);
+                        acc += ls[cv * 8 + 2 * k] * f.x + ls[cv * 8 + 2 * k + 1] * f.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && hj0 + q < HJ) lg[hj0 + q] = r16f(acc);
+        }
+    }
+    __syncthreads();
+    if (tid < heads) {                   // softmax over the relations of one head
+        float* pr = lg + tid * nrel;
+        float mx = -INFINITY;
+        for (int j = 0; j < nrel; ++j) mx = fmaxf(mx, pr[j]);
+        float sum = 0.f;
+        for (int j = 0; j < nrel; ++j) {
+            const float e = __expf(pr[j] - mx);
+            pr[j] = e;
+            sum += e;
+        }
+        for (int j = 0; j < nrel; ++j) pr[j] = r16f(pr[j] / sum);
+    }
+    __syncthreads();
+    // ---- out = p . Bm + bias: the (head, relation) rows are split over P thread groups (all 256 threads stream Bm even
+    // at C = 320), sixteen independent loads in flight per thread; partial sums meet in shared memory in fixed order.
+    const __half* Bg = Bm + (size_t)g * HJ * C;
+    const int P = max(1, RA_THREADS / nvec);
+    {
+        const int cv = tid % nvec, part = tid / nvec;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (part < P) {
+            for (int hb = part; hb < HJ; hb += P * 16) {
+                uint4 u[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int hj = hb + i * P;
+                    if (hj < HJ) u[i] = *reinterpret_cast<const uint4*>(Bg + (size_t)hj * C + cv * 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int hj = hb + i * P;
+                    if (hj < HJ) {
+                        const float p = lg[hj];
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 f = __half22float2(h2[k]);
+                            acc[2 * k] += p * f.x;
+                            acc[2 * k + 1] += p * f.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ls[part * C + cv * 8 + k] = acc[k];      // partials [P][C]; LN1 output is dead now
+        }
+    }
+    __syncthreads();
+    float s2 = 0.f;
+    for (int c = tid; c < C; c += RA_THREADS) {
+        float acc = 0.f;
+        for (int pp = 0; pp < P; ++pp) acc += ls[pp * C + c];
+        const float y = r16f(acc + bias[c]);
+        const float f2 = r16f(xs[c] + r16f(gate * y));
+        xs[c] = f2;
+        s2 += f2;
+    }
+    __syncthreads();
+    // ---- LN2
+    const float mean2 = block_sum(s2) / C;
+    float ss2 = 0.f;
+    for (int c = tid; c < C; c += RA_THREADS) {
+        const float dlt = xs[c] - mean2;
+        ss2 += dlt * dlt;
+    }
+    const float rstd2 = rsqrtf(block_sum(ss2) / C + eps);
+    for (int cv = tid; cv < nvec; cv += RA_THREADS) {
+        __half2 o1[4], o2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = cv * 8 + 2 * k;
+            o1[k] = __floats2half2_rn(xs[c], xs[c + 1]);
+            o2[k] = __floats2half2_rn((xs[c] - mean2) * rstd2 * g2[c] + b2[c], (xs[c + 1] - mean2) * rstd2 * g2[c + 1] + b2[c + 1]);
+        }
+        *reinterpret_cast<uint4*>(feats2 + (size_t)row * C + cv * 8) = *reinterpret_cast<uint4*>(o1);
+        *reinterpret_cast<uint4*>(ln2out + (size_t)row * C + cv * 8) = *reinterpret_cast<uint4*>(o2);
+    }
+}
+int rela_attn_fused_launch(const __half* feats, int G, int rows_per_g, int C, int heads, int nrel, const __half* A,
+                           const __half* Bm, const float* bias, float gate, const float* g1, const float* b1,
+                           const float* g2, const float* b2, float eps, __half* feats2, __half* ln2out, cudaStream_t st) {
+    const size_t smem = ((size_t)C + std::max<size_t>(C, 8 * RA_THREADS) + (size_t)heads * nrel) * sizeof(float);
+    if (C % 8 || C > 1280 || heads > RA_THREADS || smem > 48 * 1024) {
+        set_error("rela_attn_fused: unsupported C=%d heads=%d nrel=%d", C, heads, nrel);
+        return -1;
+    }
+    LTT_CUDA_OK(launch_k(rela_attn_fused_kernel, dim3(G * rows_per_g), dim3(RA_THREADS), smem, st, feats, rows_per_g, C, heads, nrel, A, Bm,
+                         bias, gate, g1, b1, g2, b2, eps, feats2, ln2out));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // 30-query x (<= 32)-key cross attention of the relation path.  One block per (batch element, head): q / k / v head
 // slices are staged in shared memory with 16-byte loads (the previous one-warp-per-query version walked them with
 // dependent 4-byte global loads and was pure latency), then one warp per query: lane j owns key j for the logits,

@@ -181,6 +181,37 @@ def check_small_attention(B, nq, nk, heads, d, seed=0):
     return rel(out.float(), attention_ref(q, k, v, heads))
 
 
+def check_rela_attn_fused(G, C, heads, nrel, seed=0):
+    """norm1 -> to_q -> attention over the relation tokens -> to_out -> gated residual -> norm2 with the projections
+    folded into the relation K / V, against the unfolded fp32 torch math on the same fp16 operands."""
+    d, mo = C // heads, 30
+    feats = (rn(G, mo, C, seed=seed) * 1.5).half()
+    feats[:, 7:] = 0                       # padded box slots pool to zero rows
+    wq = rn(C, C, seed=seed + 1, scale=1 / math.sqrt(C)).half()
+    wo = rn(C, C, seed=seed + 2, scale=1 / math.sqrt(C)).half()
+    bo = 0.1 * rn(C, seed=seed + 3)
+    kv = rn(G, nrel, 2 * C, seed=seed + 4, dtype=torch.float16)
+    g1, b1 = 1 + 0.1 * rn(C, seed=seed + 5), 0.1 * rn(C, seed=seed + 6)
+    g2, b2 = 1 + 0.1 * rn(C, seed=seed + 7), 0.1 * rn(C, seed=seed + 8)
+    gate = 0.46
+    A = torch.empty(G, heads * nrel, C, device=DEV, dtype=torch.float16)
+    Bm = torch.empty_like(A)
+    L.check(L.lib().ltt_op_rela_fold(L.ptr(wq), L.ptr(wo), L.ptr(kv), G, nrel, heads, d, d ** -0.5, L.ptr(A), L.ptr(Bm),
+                                     L.stream_ptr()), "rela_fold")
+    f2 = torch.empty(G, mo, C, device=DEV, dtype=torch.float16)
+    l2 = torch.empty_like(f2)
+    L.check(L.lib().ltt_op_rela_attn_fused(L.ptr(feats), G, mo, C, heads, nrel, L.ptr(A), L.ptr(Bm), L.ptr(bo), gate, L.ptr(g1),
+                                           L.ptr(b1), L.ptr(g2), L.ptr(b2), 1e-5, L.ptr(f2), L.ptr(l2), L.stream_ptr()), "rela_attn_fused")
+    x = feats.float()
+    ln = F.layer_norm(x, (C,), g1, b1, 1e-5)
+    q = F.linear(ln, wq.float())
+    k, v = kv.float().split(C, dim=-1)
+    att = attention_ref(q, k, v, heads)
+    ref2 = x + gate * F.linear(att, wo.float(), bo)
+    ref_l2 = F.layer_norm(ref2, (C,), g2, b2, 1e-5)
+    return max(rel(f2.float(), ref2), rel(l2.float(), ref_l2))
+
+
 def check_rela_scatter_ln(B, nb, h, w, C, seed=0):
     """scatter of pooled box features + (out + x) / 2 + the fused LayerNorm, against plain torch on the same inputs."""
     mo = 30
@@ -259,6 +290,9 @@ ALL = [
     ("groupnorm 3x4 64 (cpg 2, fewer pixels than CTAs)", check_groupnorm, dict(B=3, HW=4, c0=64, c1=0, silu=True, eps=1e-5), 2e-3),
     ("groupnorm concat 2x384 64+128 (cpg 6, ragged pixels)", check_groupnorm, dict(B=2, HW=381, c0=64, c1=128, silu=False, eps=1e-5), 2e-3),
     ("groupnorm 1x9216 960 (slab not staged)", check_groupnorm, dict(B=1, HW=9216, c0=640, c1=320, silu=True, eps=1e-5), 2e-3),
+    ("relation attention folded C=320 10 relations", check_rela_attn_fused, dict(G=2, C=320, heads=8, nrel=10), 2e-3),
+    ("relation attention folded C=1280 10 relations", check_rela_attn_fused, dict(G=1, C=1280, heads=8, nrel=10), 2e-3),
+    ("relation attention folded C=64 3 relations", check_rela_attn_fused, dict(G=3, C=64, heads=8, nrel=3), 2e-3),
     ("relation attention 30x10 d=40", check_small_attention, dict(B=2, nq=30, nk=10, heads=8, d=40), 3e-3),
     ("relation attention 30x10 d=160", check_small_attention, dict(B=1, nq=30, nk=10, heads=8, d=160), 3e-3),
     ("relation attention 30x3 d=8", check_small_attention, dict(B=3, nq=30, nk=3, heads=8, d=8), 3e-3),
