@@ -349,6 +349,11 @@ def main():
         else:
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None)
+        try:      # DRAM bytes per launch of the class, from the committed ncu pass over the same workload (profiles/)
+            roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))["per_launch_bytes"].get(dom)
+            roof["traffic_note"] = "dram__bytes_read+write per launch, class average over one evaluation (profiles/r01_dram_traffic.json)"
+        except Exception:  # noqa: BLE001
+            pass
         roof.update(peak_source=pk["source"], launches=d["launches"], avg_launch_us=1e3 * d["ms"] / max(d["launches"], 1),
                     share_of_unet_time=d["ms"] / max(prof["forward"]["ms"], 1e-9),
                     classes={k: dict(ms=round(v["ms"], 3), launches=v["launches"],
