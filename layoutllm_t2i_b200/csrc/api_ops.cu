@@ -147,8 +147,25 @@ int ltt_op_rela_fold(const void* wq16, const void* wo16, const void* kv16, int G
 int ltt_op_rela_attn_fused(const void* feats16, int G, int rows_per_g, int C, int heads, int nrel, const void* A16,
                            const void* Bm16, const float* bias, float gate, const float* g1, const float* b1, const float* g2,
                            const float* b2, float eps, void* feats2_16, void* ln2_16, void* stream) {
+    // operator-level call: private scratch (per-head partial sums + per-row tickets), grown on demand
+    static float* scratch = nullptr;
+    static int* tickets = nullptr;
+    static size_t cap_s = 0, cap_t = 0;
+    const size_t need_s = (size_t)G * rows_per_g * heads * C, need_t = (size_t)G * rows_per_g;
+    if (need_s > cap_s) {
+        if (scratch) cudaFree(scratch);
+        LTT_CUDA_OK(cudaMalloc(&scratch, need_s * sizeof(float)));
+        cap_s = need_s;
+    }
+    if (need_t > cap_t) {
+        if (tickets) cudaFree(tickets);
+        LTT_CUDA_OK(cudaMalloc(&tickets, need_t * sizeof(int)));
+        LTT_CUDA_OK(cudaMemset(tickets, 0, need_t * sizeof(int)));
+        cap_t = need_t;
+    }
     return rela_attn_fused_launch((const __half*)feats16, G, rows_per_g, C, heads, nrel, (const __half*)A16, (const __half*)Bm16,
-                                  bias, gate, g1, b1, g2, b2, eps, (__half*)feats2_16, (__half*)ln2_16, (cudaStream_t)stream);
+                                  bias, gate, g1, b1, g2, b2, eps, scratch, tickets, (__half*)feats2_16, (__half*)ln2_16,
+                                  (cudaStream_t)stream);
 }
 int ltt_op_small_attention(const void* q, const void* k, const void* v, int B, int nq, int nk, int heads, int d,
                            float scale, void* out, void* stream) {

@@ -36,7 +36,8 @@ int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G
                      __half* A, __half* Bm, cudaStream_t st);
 int rela_attn_fused_launch(const __half* feats, int G, int rows_per_g, int C, int heads, int nrel, const __half* A,
                            const __half* Bm, const float* bias, float gate, const float* g1, const float* b1,
-                           const float* g2, const float* b2, float eps, __half* feats2, __half* ln2out, cudaStream_t st);
+                           const float* g2, const float* b2, float eps, float* scratch, int* tickets, __half* feats2,
+                           __half* ln2out, cudaStream_t st);
 int small_attn_launch(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int B, int nq, int nk,
                       int heads, int d, float scale, __half* out, cudaStream_t st);
 int cast_f32_f16_launch(const float* in, __half* out, size_t n, cudaStream_t st);

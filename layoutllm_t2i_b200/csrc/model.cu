@@ -124,6 +124,8 @@ struct ltt_model {
     __half* vtbuf = nullptr;
     int rows_k_max = 0;
     double* gn_stats = nullptr;
+    float* rela_scratch = nullptr;    // per-head partial sums of the fused relation attention
+    int* rela_tickets = nullptr;
     __half *temb16 = nullptr, *te_h = nullptr, *semb = nullptr, *ev_all = nullptr;
     float *x_in = nullptr, *t_in = nullptr, *eps_buf = nullptr;
     float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -638,7 +640,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
             // norm1 -> (to_q, attention over the relation tokens, to_out: folded) -> gated residual -> norm2, one kernel
             ProfScope ps(m, st, PC_LN, 0.0, (double)R * C * 6.0);
             RC(rela_attn_fused_launch(m->feats, ng, mo, C, s.heads, m->n_rel, s.r_A, s.r_Bm, s.r_out.bias, s.r_ta, s.r_ln1.g,
-                                      s.r_ln1.b, s.r_ln2.g, s.r_ln2.b, 1e-5f, m->feats2, m->featln, st));
+                                      s.r_ln1.b, s.r_ln2.g, s.r_ln2.b, 1e-5f, m->rela_scratch, m->rela_tickets, m->feats2, m->featln, st));
             m->launches++;
         } else {
             RC(ln(m, st, m->feats, DT_F16, R, C, s.r_ln1, m->featln, nullptr));
@@ -918,6 +920,8 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->feats, fe * 2)); RC(A(&m->feats2, fe * 2)); RC(A(&m->feats3, fe * 2));
     RC(A(&m->featln, fe * 2)); RC(A(&m->featq, fe * 2)); RC(A(&m->featao, fe * 2));
     RC(A(&m->featff, max_featff * 2));
+    RC(A(&m->rela_scratch, fe * c.num_heads * 4));
+    RC(A(&m->rela_tickets, (size_t)B * mo * 4, true));
     // attention operand buffers: q/k per head padding (pad columns stay zero for ever), one V^T buffer
     m->rows_k_max = (H * W + mo + 63) / 64 * 64;
     size_t max_vt = 0;

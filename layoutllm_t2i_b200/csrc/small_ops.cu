@@ -937,39 +937,28 @@ int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G
     return 0;
 }
 
-// One CTA per pooled feature row (g, i):  ln = fp16(LN1(f));  logits[h,j] = fp16(ln . A[g,h,j]);  p = fp16(softmax_j);
-// y = fp16(sum p Bm + bias);  f2 = fp16(f + fp16(gate * y));  ln2 = fp16(LN2(f2)).  Rounding points follow the fp16
-// autocast reference except that q and the per-head attention output are never materialised (fp32 through the fold).
-constexpr int RA_THREADS = 512;
+// One CTA per (pooled feature row, head):  ln = fp16(LN1(f)) (recomputed per head: the row is 2.5 KB);
+// logits[j] = fp16(ln . A[g,h,j]);  p = fp16(softmax_j);  partial[h] = sum_j p_j Bm[g,h,j] -> fp32 scratch.  The last
+// CTA of a row to finish (ticket counter) adds the heads' partials in head order (deterministic), applies
+// y = fp16(sum + bias), f2 = fp16(f + fp16(gate * y)), ln2 = fp16(LN2(f2)) and re-arms the counter.  Rounding points
+// follow the fp16 autocast reference except that q and the per-head attention output are never materialised.
+// rows x heads CTAs keep the L2 round trips per CTA at three instead of fifteen for a one-CTA-per-row layout.
+constexpr int RA_THREADS = 256;
 __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
     const __half* __restrict__ feats, int rows_per_g, int C, int heads, int nrel, const __half* __restrict__ A,
     const __half* __restrict__ Bm, const float* __restrict__ bias, float gate, const float* __restrict__ g1,
     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
-    __half* __restrict__ feats2, __half* __restrict__ ln2out) {
+    float* __restrict__ scratch, int* __restrict__ tickets, __half* __restrict__ feats2, __half* __restrict__ ln2out) {
     pdl_launch_dependents();
-    // A / Bm are touched once per UNet evaluation, so they are never L2 resident when this kernel starts: every CTA asks
-    // L2 for its 1/rows_per_g slice of both (they are step invariant -> before the PDL wait, under the predecessor's tail)
-    if (threadIdx.x == 0) {
-        const int i = blockIdx.x % rows_per_g, gq = blockIdx.x / rows_per_g;
-        const size_t total = (size_t)heads * nrel * C * sizeof(__half);
-        const size_t chunk = ((total + rows_per_g - 1) / rows_per_g + 15) & ~(size_t)15;
-        const size_t off = (size_t)i * chunk;
-        if (off < total) {
-            const uint32_t n = (uint32_t)min(chunk, total - off);
-            const char* pa = reinterpret_cast<const char*>(A) + (size_t)gq * total + off;
-            const char* pb = reinterpret_cast<const char*>(Bm) + (size_t)gq * total + off;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(n) : "memory");
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pb), "r"(n) : "memory");
-        }
-    }
     pdl_wait();
     extern __shared__ float ra_smem[];
     float* xs = ra_smem;                 // [C] feature row, later f2
-    float* ls = xs + C;                  // [max(C, 2048)] LN1 output (fp16-rounded), later the partial sums of the out phase
-    float* lg = ls + max(C, 8 * RA_THREADS);   // [heads*nrel] logits, then probabilities
+    float* ls = xs + C;                  // [max(C, 2048)] LN1 output (fp16-rounded), later partial sums of the out phase
+    float* lg = ls + max(C, 8 * RA_THREADS);   // [nrel] logits, then probabilities
     __shared__ float red[RA_THREADS / 32];
-    const int row = blockIdx.x, g = row / rows_per_g;
-    const int HJ = heads * nrel;
+    __shared__ int is_last;
+    const int row = blockIdx.x, h = blockIdx.y, g = row / rows_per_g;
+    const int HJ = heads * nrel, nvec = C >> 3;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto block_sum = [&](float v) -> float {
 #pragma unroll
@@ -998,73 +987,64 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
     const float rstd = rsqrtf(block_sum(ss) / C + eps);
     for (int c = tid; c < C; c += RA_THREADS) ls[c] = r16f((xs[c] - mean) * rstd * g1[c] + b1[c]);
     __syncthreads();
-    // ---- logits: one warp per (head, relation) column, lanes over C in 16-byte vectors.  The loads of two columns
-    // (up to 2 x 5 vectors per lane, C <= 1280) are issued before any arithmetic: the phase is L2-latency bound.
-    const __half* Ag = A + (size_t)g * HJ * C;
-    const int nvec = C >> 3;
-    for (int hj0 = warp * 2; hj0 < HJ; hj0 += 2 * (RA_THREADS / 32)) {
-        uint4 u[2][5];
+    // ---- logits of this head: one warp per relation, lanes over C in 16-byte vectors (<= 5 loads in flight per lane)
+    const __half* Ah = A + ((size_t)g * HJ + (size_t)h * nrel) * C;
+    for (int j = warp; j < nrel; j += RA_THREADS / 32) {
+        uint4 u[5];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int i = 0; i < 5; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < nvec) u[i] = *reinterpret_cast<const uint4*>(Ah + (size_t)j * C + cv * 8);
+        }
+        float acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int cv = lane + 32 * i;
-                if (hj0 + q < HJ && cv < nvec) u[q][i] = *reinterpret_cast<const uint4*>(Ag + (size_t)(hj0 + q) * C + cv * 8);
-            }
+        for (int i = 0; i < 5; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < nvec) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u[i]);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int cv = lane + 32 * i;
-                if (hj0 + q < HJ && cv < nvec) {
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&u[q][i]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 f = __half22float2(h2[k]);
-                        acc += ls[cv * 8 + 2 * k] * f.x + ls[cv * 8 + 2 * k + 1] * f.y;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h2[k]);
+                    acc += ls[cv * 8 + 2 * k] * f.x + ls[cv * 8 + 2 * k + 1] * f.y;
                 }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0 && hj0 + q < HJ) lg[hj0 + q] = r16f(acc);
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) lg[j] = r16f(acc);
     }
     __syncthreads();
-    if (tid < heads) {                   // softmax over the relations of one head
-        float* pr = lg + tid * nrel;
+    if (tid == 0) {                      // softmax over the relations
         float mx = -INFINITY;
-        for (int j = 0; j < nrel; ++j) mx = fmaxf(mx, pr[j]);
+        for (int j = 0; j < nrel; ++j) mx = fmaxf(mx, lg[j]);
         float sum = 0.f;
         for (int j = 0; j < nrel; ++j) {
-            const float e = __expf(pr[j] - mx);
-            pr[j] = e;
+            const float e = __expf(lg[j] - mx);
+            lg[j] = e;
             sum += e;
         }
-        for (int j = 0; j < nrel; ++j) pr[j] = r16f(pr[j] / sum);
+        for (int j = 0; j < nrel; ++j) lg[j] = r16f(lg[j] / sum);
     }
     __syncthreads();
-    // ---- out = p . Bm + bias: the (head, relation) rows are split over P thread groups (all 256 threads stream Bm even
-    // at C = 320), sixteen independent loads in flight per thread; partial sums meet in shared memory in fixed order.
-    const __half* Bg = Bm + (size_t)g * HJ * C;
+    // ---- this head's share of p . Bm: relations split over P thread groups, all loads of a thread in flight together
+    const __half* Bh = Bm + ((size_t)g * HJ + (size_t)h * nrel) * C;
     const int P = max(1, RA_THREADS / nvec);
     {
         const int cv = tid % nvec, part = tid / nvec;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (part < P) {
-            for (int hb = part; hb < HJ; hb += P * 16) {
-                uint4 u[16];
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int jb = part; jb < nrel; jb += P * 8) {
+                uint4 u[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int hj = hb + i * P;
-                    if (hj < HJ) u[i] = *reinterpret_cast<const uint4*>(Bg + (size_t)hj * C + cv * 8);
+                for (int i = 0; i < 8; ++i) {
+                    const int j = jb + i * P;
+                    if (j < nrel) u[i] = *reinterpret_cast<const uint4*>(Bh + (size_t)j * C + cv * 8);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int hj = hb + i * P;
-                    if (hj < HJ) {
-                        const float p = lg[hj];
+                for (int i = 0; i < 8; ++i) {
+                    const int j = jb + i * P;
+                    if (j < nrel) {
+                        const float p = lg[j];
                         const __half2* h2 = reinterpret_cast<const __half2*>(&u[i]);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -1080,17 +1060,29 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
         }
     }
     __syncthreads();
-    float s2 = 0.f;
+    float* mine = scratch + ((size_t)row * heads + h) * C;
     for (int c = tid; c < C; c += RA_THREADS) {
         float acc = 0.f;
         for (int pp = 0; pp < P; ++pp) acc += ls[pp * C + c];
+        mine[c] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(&tickets[row], 1) == heads - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- last CTA of the row: heads in fixed order, bias, gated residual, LN2
+    const float* all = scratch + (size_t)row * heads * C;
+    float s2 = 0.f;
+    for (int c = tid; c < C; c += RA_THREADS) {
+        float acc = 0.f;
+        for (int hh = 0; hh < heads; ++hh) acc += __ldcg(all + (size_t)hh * C + c);
         const float y = r16f(acc + bias[c]);
         const float f2 = r16f(xs[c] + r16f(gate * y));
         xs[c] = f2;
         s2 += f2;
     }
-    __syncthreads();
-    // ---- LN2
     const float mean2 = block_sum(s2) / C;
     float ss2 = 0.f;
     for (int c = tid; c < C; c += RA_THREADS) {
@@ -1109,17 +1101,20 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
         *reinterpret_cast<uint4*>(feats2 + (size_t)row * C + cv * 8) = *reinterpret_cast<uint4*>(o1);
         *reinterpret_cast<uint4*>(ln2out + (size_t)row * C + cv * 8) = *reinterpret_cast<uint4*>(o2);
     }
+    if (tid == 0) tickets[row] = 0;      // re-armed for the next launch (graph replays)
 }
+// scratch: >= G*rows_per_g*heads*C floats; tickets: >= G*rows_per_g ints, zero before the first launch.
 int rela_attn_fused_launch(const __half* feats, int G, int rows_per_g, int C, int heads, int nrel, const __half* A,
                            const __half* Bm, const float* bias, float gate, const float* g1, const float* b1,
-                           const float* g2, const float* b2, float eps, __half* feats2, __half* ln2out, cudaStream_t st) {
-    const size_t smem = ((size_t)C + std::max<size_t>(C, 8 * RA_THREADS) + (size_t)heads * nrel) * sizeof(float);
-    if (C % 8 || C > 1280 || heads > RA_THREADS || smem > 48 * 1024) {
+                           const float* g2, const float* b2, float eps, float* scratch, int* tickets, __half* feats2,
+                           __half* ln2out, cudaStream_t st) {
+    const size_t smem = ((size_t)C + std::max<size_t>(C, 8 * RA_THREADS) + (size_t)nrel) * sizeof(float);
+    if (C % 8 || C > 1280 || nrel > 32 || smem > 48 * 1024) {
         set_error("rela_attn_fused: unsupported C=%d heads=%d nrel=%d", C, heads, nrel);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(rela_attn_fused_kernel, dim3(G * rows_per_g), dim3(RA_THREADS), smem, st, feats, rows_per_g, C, heads, nrel, A, Bm,
-                         bias, gate, g1, b1, g2, b2, eps, feats2, ln2out));
+    LTT_CUDA_OK(launch_k(rela_attn_fused_kernel, dim3(G * rows_per_g, heads), dim3(RA_THREADS), smem, st, feats, rows_per_g, C, heads, nrel,
+                         A, Bm, bias, gate, g1, b1, g2, b2, eps, scratch, tickets, feats2, ln2out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
