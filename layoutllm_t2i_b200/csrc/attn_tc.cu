@@ -19,7 +19,7 @@
 
 namespace ltt {
 
-constexpr int ATT_THREADS = 192;
+constexpr int att_threads(int nwg) { return 64 + 128 * nwg; }    // TMA warp, MMA warp, NWG softmax warpgroups
 
 struct AttnDeviceArgs {
     CUtensorMap qmap, kmap, vmap;
@@ -42,7 +42,8 @@ struct AttnCfg {
     static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
     static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + PBUF * P_BYTES;
-    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+    static constexpr int OFF_XCH = OFF_BAR + 256;                 // [2][128] floats: row max / row sum exchange between warpgroups
+    static constexpr int TOTAL = OFF_XCH + 1024 + 1024;
     static constexpr int TM_S = 0, TM_O = SBUF * BKV;
     static constexpr int TM_USED = SBUF * BKV + DV;
     static constexpr int TM_COLS = TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
@@ -64,8 +65,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // the number of softmax warps per SM -- the d=40 level is bound by the softmax warps' issue rate, not by the tensor pipe.
 // PBUF = number of P tiles in shared memory: with 2 (and SBUF = 2) the softmax of tile j+1 never waits for the tensor
 // core -- S(j+1) was produced while tile j was exponentiated and P(j+1) goes to the other buffer while PV(j) runs.
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB>
-__global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
+// NWG = softmax warpgroups: with 2 the columns of a score tile are split between two threads per query row (half the
+// serial TMEM-load -> exp -> store chain per tile); the pair agrees on the running reference through shared memory.
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG>
+__global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 128);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&s_empty[i], 128 * NWG);
+            mbar_init(&p_full[i], 128 * NWG);
             mbar_init(&pv_done[i], 1);
         }
         mbar_fence_init();
@@ -178,9 +181,16 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
         // reference, rescale O and l, and redo the tile.  P <= 256 fits fp16; l and O are fp32.
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
+        const int wg = (warp - 2) >> 2;                       // 0 .. NWG-1
+        constexpr int CW = BKV / NWG;                         // score columns per thread and tile
+        const int cb = wg * CW;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+        float* xch = reinterpret_cast<float*>(smem + C::OFF_XCH);   // [2][128]
         float m_used = -INFINITY, l = 0.f;
         const float sc = args.scale_log2;
+        // O columns (16-wide chunks) this thread rescales / writes: split between the warpgroups
+        constexpr int OSPLIT = ((DV / 16 + 1) / 2) * 16;
+        auto owns = [&](int c) { return NWG == 1 || (c < OSPLIT ? wg == 0 : wg == 1); };
         for (int j = 0; j < nt; ++j) {
             const int sb = j % SBUF, pb = j % PBUF;
             uint8_t* sP = smem + C::OFF_P + pb * C::P_BYTES;
@@ -193,25 +203,23 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                 mbar_wait(&pv_done[pb], ((j / PBUF) - 1) & 1);      // P[pb] is free again (PBUF == 1: and O is up to date)
                 tc_fence_after();
             }
-            // exponentiate the tile against reference `mref`, write P, return the row sum; track the raw tile maximum
+            // exponentiate this thread's columns against reference `mref`, write P, return their sum; or (store = false)
+            // only track the raw maximum
             auto pass = [&](auto tail_tag, auto store_tag, float mref, float& tmax) -> float {
                 constexpr bool TAIL = decltype(tail_tag)::value;
-                constexpr bool store = decltype(store_tag)::value;     // false: raw tile maximum only
+                constexpr bool store = decltype(store_tag)::value;
                 float rs = 0.f;
                 const float nm = -mref;
-                // software pipelined: the TMEM load of chunk c + 32 is in flight while chunk c is exponentiated
-                uint32_t vb[2][32];
-                tmem_ld32(ts, vb[0]);
 #pragma unroll
-                for (int c = 0; c < BKV; c += 32) {
-                    uint32_t(&v)[32] = vb[(c >> 5) & 1];
+                for (int c = 0; c < CW; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(ts + cb + c, v);
                     tmem_ld_wait();
-                    if (c + 32 < BKV) tmem_ld32(ts + c + 32, vb[((c >> 5) + 1) & 1]);
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         f[i] = __uint_as_float(v[i]);
-                        if (TAIL && c + i >= kvalid) f[i] = -INFINITY;
+                        if (TAIL && cb + c + i >= kvalid) f[i] = -INFINITY;
                         if (!store) tmax = fmaxf(tmax, f[i]);
                     }
                     if (store) {
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                                 rs += p0 + p1;
                                 h[i] = __floats2half2_rn(p0, p1);
                             }
-                            const int g8 = (c >> 3) + c8;              // 8-column group inside the tile
+                            const int g8 = ((cb + c) >> 3) + c8;       // 8-column group inside the tile
                             const int kc = g8 >> 3, u = g8 & 7;
                             *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
                                 *reinterpret_cast<uint4*>(h);
@@ -239,17 +247,25 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                 return tail ? pass(BoolTag<true>{}, BoolTag<true>{}, mref, unused) : pass(BoolTag<false>{}, BoolTag<true>{}, mref, unused);
             };
             // optimistic pass against the current reference; every p >= 0, so a row sum below the fp16 range proves
-            // that no single p overflowed -- otherwise (or on the first tile) fix the reference and redo the tile
+            // that no single p overflowed -- otherwise (or on the first tile) fix the reference and redo the tile.
+            // NWG == 2: the whole CTA votes, so both threads of a row always take the same path.
             float rs = 0.f;
             bool ok = false;
             if (j > 0) {
                 rs = exp_pass(m_used);
                 ok = rs <= 32768.0f;
             }
-            if (!__all_sync(0xffffffffu, ok)) {
+            const bool all_ok = NWG == 1 ? __all_sync(0xffffffffu, ok) : bar_red_and(1, 128 * NWG, ok);
+            if (!all_ok) {
                 float tmax = -INFINITY;
                 if (tail) pass(BoolTag<true>{}, BoolTag<false>{}, 0.f, tmax);
                 else pass(BoolTag<false>{}, BoolTag<false>{}, 0.f, tmax);
+                if (NWG == 2) {                     // row maximum over both halves
+                    xch[wg * 128 + r] = tmax;
+                    named_bar_sync(2, 128 * NWG);
+                    tmax = fmaxf(xch[r], xch[128 + r]);
+                    named_bar_sync(2, 128 * NWG);   // xch is reused by the next exchange
+                }
                 const float mx = tmax * sc;
                 const bool need = mx > m_used + 8.0f;
                 const float m_new = need ? mx : m_used;
@@ -262,6 +278,7 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
                     l *= f;
 #pragma unroll
                     for (int c = 0; c < DV; c += 16) {
+                        if (!owns(c)) continue;
                         uint32_t v[16];
                         tmem_ld16(trow + C::TM_O + c, v);
                         tmem_ld_wait();
@@ -282,11 +299,17 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
         }
         mbar_wait(&pv_done[(nt - 1) % PBUF], ((nt - 1) / PBUF) & 1);
         tc_fence_after();
+        if (NWG == 2) {                             // row sum over both halves
+            xch[wg * 128 + r] = l;
+            named_bar_sync(2, 128 * NWG);
+            l = xch[r] + xch[128 + r];
+        }
         const float inv = 1.0f / l;
         const bool valid = (q0 + r) < args.nq;
         __half* orow = args.out + ((size_t)b * args.nq + q0 + r) * args.ldo + head * args.dhead;
 #pragma unroll
         for (int c = 0; c < DV; c += 16) {
+            if (!owns(c)) continue;
             uint32_t v[16];
             tmem_ld16(trow + C::TM_O + c, v);
             tmem_ld_wait();
@@ -312,20 +335,20 @@ __global__ void __launch_bounds__(ATT_THREADS, MINB) attn_tc_kernel(const __grid
     }
 }
 
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
         if (getenv("LTT_VERBOSE")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, ATT_THREADS, C::TOTAL);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, att_threads(NWG), C::TOTAL);
             fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, PBUF, MINB, C::TOTAL, nb);
         }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB>, grid, dim3(ATT_THREADS), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -336,7 +359,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     const int rowlen = p.heads * p.dpad;
     int bkv, dv;
     static const int v40 = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;      // d = 40 variant (experiments)
-    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2) ? 64 : 128; dv = 48; }
+    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
@@ -375,14 +398,22 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     a.out = p.out; a.ldo = p.ldo;
     a.scale_log2 = p.scale * 1.4426950408889634f;
     dim3 grid((p.nq + 127) / 128, p.heads, p.B);
+    static const int vwg = getenv("LTT_ATTN_WG") ? atoi(getenv("LTT_ATTN_WG")) : 2;     // softmax warpgroups for d = 80 / 160 (A/B)
     if (dv == 48) {
         if (v40 == 1) return attn_launch_variant<64, 48, 64, 1, 1, 3>(a, grid, stream);
         if (v40 == 2) return attn_launch_variant<64, 48, 64, 2, 2, 2>(a, grid, stream);
         if (v40 == 3) return attn_launch_variant<64, 48, 128, 2, 2, 1>(a, grid, stream);
-        return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
+        if (v40 == 5) return attn_launch_variant<64, 48, 128, 2, 2, 1, 2>(a, grid, stream);
+        if (v40 == 7) return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
+        // default: two softmax warpgroups per CTA, two CTAs per SM (16 softmax warps per SM); short key sets (the
+        // 77-token text context) use 64-key tiles with S and P double buffered
+        if (bkv == 64) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
+        return attn_launch_variant<64, 48, 128, 1, 1, 2, 2>(a, grid, stream);
     }
-    if (dv == 80) return attn_launch_variant<128, 80, 128, 2, 2, 1>(a, grid, stream);
-    if (dv == 160) return attn_launch_variant<192, 160, 64, 2, 2, 1>(a, grid, stream);
+    if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)
+                                  : attn_launch_variant<128, 80, 128, 2, 2, 1>(a, grid, stream);
+    if (dv == 160) return vwg == 2 ? attn_launch_variant<192, 160, 64, 2, 2, 1, 2>(a, grid, stream)
+                                   : attn_launch_variant<192, 160, 64, 2, 2, 1>(a, grid, stream);
     return attn_launch_variant<64, 16, 128, 2, 2, 1>(a, grid, stream);
 }
 

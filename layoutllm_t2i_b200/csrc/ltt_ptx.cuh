@@ -365,6 +365,19 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// named barrier with an AND reduction of a predicate over the participating threads
+__device__ __forceinline__ bool bar_red_and(int id, int nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "bar.red.and.pred q, %1, %2, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}\n"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
+        : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
