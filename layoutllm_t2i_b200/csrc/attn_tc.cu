@@ -42,8 +42,8 @@ struct AttnCfg {
     static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
     static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
     static constexpr int OFF_BAR = OFF_P + PBUF * P_BYTES;
-    static constexpr int OFF_XCH = OFF_BAR + 256;                 // [2][128] floats: row max / row sum exchange between warpgroups
-    static constexpr int TOTAL = OFF_XCH + 1024 + 1024;
+    static constexpr int OFF_XCH = OFF_BAR + 256;                 // [4][128] floats: row max / row sum exchange between warpgroups
+    static constexpr int TOTAL = OFF_XCH + 2048 + 1024;
     static constexpr int TM_S = 0, TM_O = SBUF * BKV;
     static constexpr int TM_USED = SBUF * BKV + DV;
     static constexpr int TM_COLS = TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
@@ -189,8 +189,7 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
         float m_used = -INFINITY, l = 0.f;
         const float sc = args.scale_log2;
         // O columns (16-wide chunks) this thread rescales / writes: split between the warpgroups
-        constexpr int OSPLIT = ((DV / 16 + 1) / 2) * 16;
-        auto owns = [&](int c) { return NWG == 1 || (c < OSPLIT ? wg == 0 : wg == 1); };
+        auto owns = [&](int c) { return ((c >> 4) * NWG) / (DV / 16) == wg; };
         for (int j = 0; j < nt; ++j) {
             const int sb = j % SBUF, pb = j % PBUF;
             uint8_t* sP = smem + C::OFF_P + pb * C::P_BYTES;
@@ -260,10 +259,11 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                 float tmax = -INFINITY;
                 if (tail) pass(BoolTag<true>{}, BoolTag<false>{}, 0.f, tmax);
                 else pass(BoolTag<false>{}, BoolTag<false>{}, 0.f, tmax);
-                if (NWG == 2) {                     // row maximum over both halves
+                if (NWG > 1) {                      // row maximum over the warpgroups' column ranges
                     xch[wg * 128 + r] = tmax;
                     named_bar_sync(2, 128 * NWG);
-                    tmax = fmaxf(xch[r], xch[128 + r]);
+#pragma unroll
+                    for (int w = 0; w < NWG; ++w) tmax = fmaxf(tmax, xch[w * 128 + r]);
                     named_bar_sync(2, 128 * NWG);   // xch is reused by the next exchange
                 }
                 const float mx = tmax * sc;
@@ -299,10 +299,12 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
         }
         mbar_wait(&pv_done[(nt - 1) % PBUF], ((nt - 1) / PBUF) & 1);
         tc_fence_after();
-        if (NWG == 2) {                             // row sum over both halves
+        if (NWG > 1) {                              // row sum over the warpgroups, fixed order
             xch[wg * 128 + r] = l;
             named_bar_sync(2, 128 * NWG);
-            l = xch[r] + xch[128 + r];
+            l = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWG; ++w) l += xch[w * 128 + r];
         }
         const float inv = 1.0f / l;
         const bool valid = (q0 + r) < args.nq;
@@ -402,10 +404,10 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     if (dv == 48) {
         if (v40 == 1) return attn_launch_variant<64, 48, 64, 1, 1, 3>(a, grid, stream);
         if (v40 == 2) return attn_launch_variant<64, 48, 64, 2, 2, 2>(a, grid, stream);
-        if (v40 == 3) return attn_launch_variant<64, 48, 128, 2, 2, 1>(a, grid, stream);
-        if (v40 == 5) return attn_launch_variant<64, 48, 128, 2, 2, 1, 2>(a, grid, stream);
         if (v40 == 7) return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
-        // default: two softmax warpgroups per CTA, two CTAs per SM (16 softmax warps per SM); short key sets (the
+        // default: two softmax warpgroups per CTA, two CTAs per SM (16 softmax warps per SM; measured alternatives at
+        // 4096 x 4126 keys: 1 warpgroup 114 us, 2 warpgroups 103 us, 4 warpgroups 111 us, any 1-CTA/SM layout >= 129 us);
+        // short key sets (the
         // 77-token text context) use 64-key tiles with S and P double buffered
         if (bkv == 64) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
         return attn_launch_variant<64, 48, 128, 1, 1, 2, 2>(a, grid, stream);
