@@ -126,17 +126,17 @@ int ltt_op_rela_rects(const float* boxes, const float* masks, int B, int mo, int
     return rela_rects_launch(boxes, masks, B, mo, h, w, rects, (cudaStream_t)stream);
 }
 int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, int w, int C, void* feats16, void* stream) {
-    return rela_pool_launch(hid, rects, B, mo, h, w, C, (__half*)feats16, (cudaStream_t)stream);
+    return rela_pool_launch(hid, nullptr, nullptr, nullptr, nullptr, rects, B, mo, h, w, C, (__half*)feats16, (cudaStream_t)stream);
 }
 int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                         int mo, int h, int w, int C, float* out, void* stream) {
-    return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+    return rela_scatter_launch(hid, nullptr, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
                                nullptr, nullptr, 0.f, nullptr, (cudaStream_t)stream);
 }
 int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                            int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
                            void* ln16, void* stream) {
-    return rela_scatter_launch(hid, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+    return rela_scatter_launch(hid, nullptr, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
                                gamma, beta, eps, (__half*)ln16, (cudaStream_t)stream);
 }
 int ltt_op_rela_fold(const void* wq16, const void* wo16, const void* kv16, int G, int nrel, int heads, int d, float scale,

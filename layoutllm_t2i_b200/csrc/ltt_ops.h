@@ -14,7 +14,7 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1, int ld1, int B, int HW, int groups,
                            const float* gamma, const float* beta, float eps, int silu, __half* out, cudaStream_t st);
 int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
-                     __half* out16, float* out32, cudaStream_t st);
+                     __half* out16, float* out32, cudaStream_t st, float2* stats_out = nullptr);
 int conv_in_launch(const float* x, const float* w, const float* bias, int B, int Cin, int H, int W, int Cout,
                    __half* out, cudaStream_t st);
 int conv_out_launch(const __half* x, const __half* w, const float* bias, int B, int H, int W, int C, int Cout,
@@ -25,11 +25,11 @@ int timestep_embed_launch(const float* t, int B, int dim, __half* out, cudaStrea
 int posnet_input_launch(const float* boxes, const float* masks, const float* emb, const float* null_txt,
                         const float* null_pos, int rows, int in_dim, int nfreq, __half* out, cudaStream_t st);
 int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, cudaStream_t st);
-int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, int w, int C, __half* feats,
-                     cudaStream_t st);
-int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, const int* rects, int nb_feats, int B,
-                        int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
-                        __half* ln16, cudaStream_t st);
+int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, const float* gamma, const float* beta,
+                     const int* rects, int B, int mo, int h, int w, int C, __half* feats, cudaStream_t st);
+int rela_scatter_launch(const float* hid, const float2* stats, const float* gamma3, const float* beta3, const __half* x,
+                        const __half* feats, const int* rects, int nb_feats, int B, int mo, int h, int w, int C, float* out,
+                        const float* gamma, const float* beta, float eps, __half* ln16, cudaStream_t st);
 int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
                           int pitch_v, int B, int mo, int C, cudaStream_t st);
 int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G, int nrel, int heads, int d, float scale,

@@ -117,13 +117,14 @@ struct ltt_model {
     std::vector<size_t> skip_elems;
     __half *act0 = nullptr, *act1 = nullptr, *tnorm = nullptr;
     __half *xa = nullptr, *xb = nullptr, *xc = nullptr, *ln16 = nullptr, *ao = nullptr, *ffbuf = nullptr;
-    float *hid32 = nullptr, *xe32 = nullptr, *xf32 = nullptr;
+    float *xe32 = nullptr, *xf32 = nullptr;
     __half *feats = nullptr, *feats2 = nullptr, *feats3 = nullptr, *featln = nullptr, *featq = nullptr, *featao = nullptr,
            *featff = nullptr;
     std::map<int, __half*> qbuf, kbuf;   // keyed by head dim (pad columns of a buffer must stay zero)
     __half* vtbuf = nullptr;
     int rows_k_max = 0;
     double* gn_stats = nullptr;
+    float2* row_stats = nullptr;      // (mean, rstd) per token row of the relation block's norm3
     float* rela_scratch = nullptr;    // per-head partial sums of the fused relation attention
     int* rela_tickets = nullptr;
     __half *temb16 = nullptr, *te_h = nullptr, *semb = nullptr, *ev_all = nullptr;
@@ -629,11 +630,16 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     }
     RC(tap(m, st, s.p + ":fuser", x16, DT_F16, M, C));
     // RelationCrossAttention (attention.py:315-359) + the caller's (out + x) / 2 (:398)
-    RC(ln(m, st, x16, DT_F16, M, C, s.r_ln3, nullptr, m->hid32));
+    // norm3 is never materialised: one pass leaves (mean, rstd) per row, the pool and scatter kernels normalise on the fly
+    {
+        m->launches++;
+        ProfScope ps(m, st, PC_LN, 0.0, (double)M * C * 2.0);
+        RC(layernorm_launch(x16, DT_F16, M, C, s.r_ln3.g, s.r_ln3.b, 1e-5f, nullptr, nullptr, st, m->row_stats));
+    }
     const int ng = m->n_grounded;
     const __half* feats_final = nullptr;
     if (ng > 0) {
-        RC(rela_pool_launch(m->hid32, m->rects[level], ng, mo, H, W, C, m->feats, st));
+        RC(rela_pool_launch(nullptr, x16, m->row_stats, s.r_ln3.g, s.r_ln3.b, m->rects[level], ng, mo, H, W, C, m->feats, st));
         m->launches++;
         const int R = ng * mo;
         if (m->rela_fused) {
@@ -668,7 +674,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         feats_final = m->feats3;
     }
     // scatter + the block's norm2 in one kernel
-    RC(rela_scatter_launch(m->hid32, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
+    RC(rela_scatter_launch(nullptr, m->row_stats, s.r_ln3.g, s.r_ln3.b, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
                            m->ln16, st));
     m->launches++;
     RC(tap(m, st, s.p + ":rela", m->xe32, DT_F32, M, C));
@@ -913,7 +919,7 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->ln16, max_tok * 2));
     RC(A(&m->ao, max_tok * 2));
     RC(A(&m->ffbuf, max_ff * 2));
-    RC(A(&m->hid32, max_tok * 4));
+    RC(A(&m->row_stats, (size_t)B * H * W * sizeof(float2)));
     RC(A(&m->xe32, max_tok * 4));
     RC(A(&m->xf32, max_tok * 4));
     const size_t fe = (size_t)B * mo * maxC;

@@ -382,7 +382,7 @@ __device__ __forceinline__ void ln_load8<float>(const float* p, float (&v)[8]) {
 template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, __half* __restrict__ out16,
-                                 float* __restrict__ out32) {
+                                 float* __restrict__ out32, float2* __restrict__ stats_out) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -419,6 +419,10 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const fl
 #pragma unroll
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / C + eps);
+    if (stats_out) {                   // statistics only: consumers normalise on the fly (relation pool / scatter)
+        if (lane == 0) stats_out[row] = make_float2(mean, rstd);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int j = i * 32 + lane;
@@ -445,7 +449,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const fl
 }
 
 int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
-                     __half* out16, float* out32, cudaStream_t st) {
+                     __half* out16, float* out32, cudaStream_t st, float2* stats_out) {
     if (C % 8 || C > 1280) {
         set_error("layernorm: unsupported C=%d", C);
         return -1;
@@ -453,9 +457,9 @@ int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamm
     const int wpb = 8;
     const int blocks = (M + wpb - 1) / wpb;
     if (x_dtype == DT_F16)
-        LTT_CUDA_OK(launch_k(layernorm_kernel<__half>, dim3(blocks), dim3(wpb * 32), 0, st, (const __half*)x, M, C, gamma, beta, eps, out16, out32));
+        LTT_CUDA_OK(launch_k(layernorm_kernel<__half>, dim3(blocks), dim3(wpb * 32), 0, st, (const __half*)x, M, C, gamma, beta, eps, out16, out32, stats_out));
     else
-        LTT_CUDA_OK(launch_k(layernorm_kernel<float>, dim3(blocks), dim3(wpb * 32), 0, st, (const float*)x, M, C, gamma, beta, eps, out16, out32));
+        LTT_CUDA_OK(launch_k(layernorm_kernel<float>, dim3(blocks), dim3(wpb * 32), 0, st, (const float*)x, M, C, gamma, beta, eps, out16, out32, stats_out));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -743,13 +747,21 @@ int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int
 }
 
 // feats[b, i, :] = mean over the box of hid (fp32) -> fp16; zero for unused slots.  CTA = (64 channels, slot, b),
-// 16 pixel lanes x 16 channel quads, shuffle-free smem reduction over the pixel lanes.
-__global__ void rela_pool_kernel(const float* __restrict__ hid, const int* __restrict__ rects, int mo, int w, int HW,
-                                 int C, __half* __restrict__ feats) {
+// 16 pixel lanes x 16 channel quads, shuffle-free smem reduction over the pixel lanes.  hid is either a materialised
+// fp32 tensor or (hid == nullptr) the LayerNorm of the fp16 tensor x16 evaluated on the fly from per-row statistics:
+// hid[p][c] = (x16[p][c] - mean_p) * rstd_p * gamma[c] + beta[c]  (same expression / order as layernorm_kernel).
+__global__ void rela_pool_kernel(const float* __restrict__ hid, const __half* __restrict__ x16, const float2* __restrict__ stats,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ rects,
+                                 int mo, int w, int HW, int C, __half* __restrict__ feats) {
     pdl_launch_dependents();
-    pdl_wait();
     const int i = blockIdx.y, b = blockIdx.z, cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c = blockIdx.x * 64 + cq * 4;
+    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!hid) {
+        g4 = *reinterpret_cast<const float4*>(gamma + c);
+        b4 = *reinterpret_cast<const float4*>(beta + c);
+    }
+    pdl_wait();
     const int* rc = rects + ((size_t)b * mo + i) * 5;
     __half* o = feats + ((size_t)b * mo + i) * C + c;
     if (!rc[4]) {
@@ -759,10 +771,28 @@ __global__ void rela_pool_kernel(const float* __restrict__ hid, const int* __res
     const int t = rc[0], bt = rc[1], l = rc[2], r = rc[3];
     const int rw = r - l, area = rw * (bt - t);
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int p = pl; p < area; p += 16) {
+    auto value = [&](int p) -> float4 {
         const int y = t + p / rw, x = l + p % rw;
-        const float4 v = *reinterpret_cast<const float4*>(hid + ((size_t)b * HW + y * w + x) * C + c);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const size_t row = (size_t)b * HW + y * w + x;
+        if (hid) return *reinterpret_cast<const float4*>(hid + row * C + c);
+        const uint2 u = *reinterpret_cast<const uint2*>(x16 + row * C + c);
+        const float2 st = stats[row];
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4((f0.x - st.x) * st.y * g4.x + b4.x, (f0.y - st.x) * st.y * g4.y + b4.y,
+                           (f1.x - st.x) * st.y * g4.z + b4.z, (f1.y - st.x) * st.y * g4.w + b4.w);
+    };
+    // four pixels in flight per thread; accumulation order = pixel order of this lane (as the single-pixel loop)
+    for (int p = pl; p < area; p += 64) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (p + 16 * k < area) v[k] = value(p + 16 * k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (p + 16 * k < area) {
+                acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+            }
     }
     __shared__ float4 red[256];
     red[threadIdx.x] = acc;
@@ -780,13 +810,14 @@ __global__ void rela_pool_kernel(const float* __restrict__ hid, const int* __res
         *reinterpret_cast<uint2*>(o) = u;
     }
 }
-int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, int w, int C, __half* feats,
-                     cudaStream_t st) {
+int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, const float* gamma, const float* beta,
+                     const int* rects, int B, int mo, int h, int w, int C, __half* feats, cudaStream_t st) {
     if (C % 64) {
         set_error("rela_pool: C %% 64 != 0 (C=%d)", C);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(rela_pool_kernel, dim3(dim3(C / 64, mo, B)), dim3(256), 0, st, hid, rects, mo, w, h * w, C, feats));
+    LTT_CUDA_OK(launch_k(rela_pool_kernel, dim3(dim3(C / 64, mo, B)), dim3(256), 0, st, hid, x16, stats, gamma, beta, rects, mo, w, h * w,
+                         C, feats));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -797,7 +828,8 @@ int rela_pool_launch(const float* hid, const int* rects, int B, int mo, int h, i
 // (fp32 two-pass statistics, as layernorm_kernel).  C <= 8 * blockDim.x.
 constexpr int RS_THREADS = 160;
 __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
-    const float* __restrict__ hid, const __half* __restrict__ x, const __half* __restrict__ feats,
+    const float* __restrict__ hid, const float2* __restrict__ stats, const float* __restrict__ gamma3,
+    const float* __restrict__ beta3, const __half* __restrict__ x, const __half* __restrict__ feats,
     const int* __restrict__ rects, int nb_feats, int mo, int w, int HW, int C, float* __restrict__ out,
     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ ln16) {
     pdl_launch_dependents();
@@ -835,11 +867,26 @@ __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
                 acc[2 * j + 1] += f.y;
             }
         }
-        const float4 h0 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c);
-        const float4 h1 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c + 4);
-        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const uint4 xu = *reinterpret_cast<const uint4*>(x + (size_t)row * C + c);
         const __half2* xh = reinterpret_cast<const __half2*>(&xu);
+        float hv[8];
+        if (hid) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c);
+            const float4 h1 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c + 4);
+            hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+        } else {      // hid = LayerNorm(x) from the row statistics (same expression / order as layernorm_kernel)
+            const float2 st = stats[row];
+            const float4 ga = *reinterpret_cast<const float4*>(gamma3 + c), gb = *reinterpret_cast<const float4*>(gamma3 + c + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(beta3 + c), bb = *reinterpret_cast<const float4*>(beta3 + c + 4);
+            const float g3[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            const float b3[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 xv = __half22float2(xh[j]);
+                hv[2 * j] = (xv.x - st.x) * st.y * g3[2 * j] + b3[2 * j];
+                hv[2 * j + 1] = (xv.y - st.x) * st.y * g3[2 * j + 1] + b3[2 * j + 1];
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 xv = __half22float2(xh[j]);
@@ -892,14 +939,14 @@ __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
     }
 }
 // gamma == nullptr: scatter only (ln16 ignored).
-int rela_scatter_launch(const float* hid, const __half* x, const __half* feats, const int* rects, int nb_feats, int B,
-                        int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
-                        __half* ln16, cudaStream_t st) {
+int rela_scatter_launch(const float* hid, const float2* stats, const float* gamma3, const float* beta3, const __half* x,
+                        const __half* feats, const int* rects, int nb_feats, int B, int mo, int h, int w, int C, float* out,
+                        const float* gamma, const float* beta, float eps, __half* ln16, cudaStream_t st) {
     if (mo > 32 || C % 8 || C > 8 * RS_THREADS) {
         set_error("rela_scatter: unsupported mo=%d C=%d", mo, C);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(rela_scatter_ln_kernel, dim3(B * h * w), dim3(RS_THREADS), 0, st, hid, x, feats, rects, nb_feats, mo, w,
+    LTT_CUDA_OK(launch_k(rela_scatter_ln_kernel, dim3(B * h * w), dim3(RS_THREADS), 0, st, hid, stats, gamma3, beta3, x, feats, rects, nb_feats, mo, w,
                          h * w, C, out, gamma, beta, eps, gamma ? ln16 : (__half*)nullptr));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
