@@ -960,26 +960,69 @@ int rela_scatter_launch(const float* hid, const float2* stats, const float* gamm
 // no C x C weight is streamed per step and the branch's q-GEMM, attention and out-GEMM launches (three ~7 us floors on
 // 30 rows) become part of one row kernel together with both LayerNorms and the gated residual.
 // A, Bm: [G][heads*nrel][C] fp16.
-__global__ void rela_fold_kernel(const __half* __restrict__ wq, const __half* __restrict__ wo, const __half* __restrict__ kv,
-                                 int nrel, int heads, int d, float scale, __half* __restrict__ A, __half* __restrict__ Bm) {
+// One block = 128 output channels of one (batch element, head): every weight element is read once per batch element
+// and reused for all relations (accumulators in registers), K / V head slices sit in shared memory.
+constexpr int RF_MAXREL = 32;
+__global__ void __launch_bounds__(128) rela_fold_kernel(const __half* __restrict__ wq, const __half* __restrict__ wo,
+                                                        const __half* __restrict__ kv, int nrel, int heads, int d, float scale,
+                                                        __half* __restrict__ A, __half* __restrict__ Bm) {
+    extern __shared__ float rf_smem[];
+    float* ks = rf_smem;                 // [nrel][d]
+    float* vs = ks + nrel * d;           // [nrel][d]
     const int C = heads * d, HJ = heads * nrel;
-    const int g = blockIdx.z, hj = blockIdx.y, h = hj / nrel, j = hj - h * nrel;
+    const int h = blockIdx.y, g = blockIdx.z;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const __half* kr = kv + ((size_t)g * nrel + j) * 2 * C + h * d;      // k_j, head h
-    const __half* vr = kr + C;                                          // v_j, head h
-    float a = 0.f, b = 0.f;
-    for (int cc = 0; cc < d; ++cc) {
-        a += __half2float(wq[(size_t)(h * d + cc) * C + c]) * __half2float(kr[cc]);
-        b += __half2float(wo[(size_t)c * C + h * d + cc]) * __half2float(vr[cc]);
+    for (int i = threadIdx.x; i < nrel * d; i += blockDim.x) {
+        const int j = i / d, cc = i - j * d;
+        const __half* kr = kv + ((size_t)g * nrel + j) * 2 * C + h * d + cc;
+        ks[i] = __half2float(kr[0]);
+        vs[i] = __half2float(kr[C]);
     }
-    A[((size_t)g * HJ + hj) * C + c] = __float2half_rn(a * scale);
-    Bm[((size_t)g * HJ + hj) * C + c] = __float2half_rn(b);
+    __syncthreads();
+    if (c >= C) return;
+    float acc[RF_MAXREL];
+#pragma unroll
+    for (int j = 0; j < RF_MAXREL; ++j) acc[j] = 0.f;
+    for (int cc = 0; cc < d; ++cc) {     // A: Wq rows of head h, coalesced over the output channel c
+        const float w = __half2float(wq[(size_t)(h * d + cc) * C + c]);
+#pragma unroll
+        for (int j = 0; j < RF_MAXREL; ++j)
+            if (j < nrel) acc[j] += w * ks[j * d + cc];
+    }
+#pragma unroll
+    for (int j = 0; j < RF_MAXREL; ++j)
+        if (j < nrel) A[((size_t)g * HJ + h * nrel + j) * C + c] = __float2half_rn(acc[j] * scale);
+#pragma unroll
+    for (int j = 0; j < RF_MAXREL; ++j) acc[j] = 0.f;
+    const __half* wr = wo + (size_t)c * C + h * d;        // Bm: row c of Wo, columns of head h (16-byte vectors)
+    for (int c8 = 0; c8 < (d >> 3); ++c8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(wr + c8 * 8);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            const int cc = c8 * 8 + 2 * e;
+#pragma unroll
+            for (int j = 0; j < RF_MAXREL; ++j)
+                if (j < nrel) {
+                    acc[j] += f.x * vs[j * d + cc];
+                    acc[j] += f.y * vs[j * d + cc + 1];
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RF_MAXREL; ++j)
+        if (j < nrel) Bm[((size_t)g * HJ + h * nrel + j) * C + c] = __float2half_rn(acc[j]);
 }
 int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G, int nrel, int heads, int d, float scale,
                      __half* A, __half* Bm, cudaStream_t st) {
     const int C = heads * d;
-    rela_fold_kernel<<<dim3((C + 127) / 128, heads * nrel, G), 128, 0, st>>>(wq, wo, kv, nrel, heads, d, scale, A, Bm);
+    const size_t smem = (size_t)2 * nrel * d * sizeof(float);
+    if (nrel > RF_MAXREL || d % 8 || smem > 48 * 1024) {
+        set_error("rela_fold: unsupported nrel=%d d=%d", nrel, d);
+        return -1;
+    }
+    rela_fold_kernel<<<dim3((C + 127) / 128, heads, G), 128, smem, st>>>(wq, wo, kv, nrel, heads, d, scale, A, Bm);
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

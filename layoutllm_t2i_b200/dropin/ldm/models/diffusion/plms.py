@@ -31,6 +31,12 @@ class PLMSSampler(object):
         """Step tables (reference :25-56): ddim_alphas is torch fp32, ddim_alphas_prev numpy fp64, sigmas 0."""
         if ddim_eta != 0:
             raise ValueError('ddim_eta must be 0 for PLMS')
+        # The reference rebuilds these tables on every sample() call; they only depend on (steps, discretisation) and
+        # the diffusion's alphas_cumprod, and every rebuild costs ~10 host<->device copies that drain the stream (the GPU
+        # would idle between images).  Same inputs -> keep the tables of the previous call.
+        key = (int(ddim_num_steps), ddim_discretize, float(ddim_eta), self.diffusion.alphas_cumprod.data_ptr())
+        if getattr(self, "_sched_key", None) == key:
+            return
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
                                                   num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
         acp = self.diffusion.alphas_cumprod
@@ -51,6 +57,10 @@ class PLMSSampler(object):
         self.register_buffer('ddim_alphas_prev', alphas_prev)
         self.register_buffer('ddim_sqrt_one_minus_alphas', np.sqrt(1. - alphas))
         self.register_buffer('ddim_sigmas_for_original_num_steps', torch.zeros_like(self.alphas_cumprod))
+        # host copies for the fused loop (ltt_plms_sample takes host tables): no device read-back per image
+        self._host_tabs = (self._host(self.ddim_alphas), np.asarray(self.ddim_alphas_prev),
+                           self._host(self.ddim_sqrt_one_minus_alphas))
+        self._sched_key = key
 
     @torch.no_grad()
     def sample(self, S, shape, input, uc=None, guidance_scale=1, mask=None, x0=None):
@@ -104,8 +114,9 @@ class PLMSSampler(object):
         if alphas is not None and any(a == 0 for a in alphas) and model.first_conv_restorable \
                 and not getattr(model, "_sd_conv_active", False):
             sd_conv = model.sd_first_conv()
-        out = eng.plms_sample(x, self.ddim_timesteps, self._host(self.ddim_alphas), self.ddim_alphas_prev,
-                              self._host(self.ddim_sqrt_one_minus_alphas), alphas, guidance if use_cfg else 1.0, sd_conv)
+        a_host, a_prev_host, s1m_host = self._host_tabs
+        out = eng.plms_sample(x, self.ddim_timesteps, a_host, a_prev_host, s1m_host, alphas, guidance if use_cfg else 1.0,
+                              sd_conv)
         # leave the module tree in the state the reference loop would (last gate value, permanent first-conv swap)
         if alphas is not None:
             self.set_alpha_scale(model, alphas[-1])
