@@ -183,6 +183,35 @@ def cpu_pair_seconds(sd_cpu, inputs, H, W, scale, n_threads):
     return time.perf_counter() - t0
 
 
+def gpu_eager_pair_ms(sd_cpu, inputs, scale, dev, reps=3):
+    """One [cond, uncond] evaluation pair of the oracle port run as EAGER PyTorch on the GPU under fp16 autocast -- the
+    stand-in for the reference's own 1-GPU eager path (/root/reference cannot travel to the GPU box; the oracle issues
+    the same F.* sequence).  A reported baseline only: nothing of the product path runs here."""
+    from oracle import unet_oracle as uo
+    sd = {k: v.to(dev) for k, v in sd_cpu.items()}
+    inp = {k: v.to(dev) for k, v in inputs.items()}
+    B = inp["x"].shape[0]
+    ts = torch.full((B,), 981, dtype=torch.long, device=dev)
+    grounding = dict(boxes=inp["boxes"], masks=inp["masks"], positive_embeddings=inp["text_embeddings"])
+    cond = dict(x=inp["x"], timesteps=ts, context=inp["context"], relations=inp["relations"], grounding_input=grounding)
+    unc = dict(x=inp["x"], timesteps=ts, context=inp["uc"], relations=inp["relations"])
+
+    def pair():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            uo.unet_forward(sd, UNET_CFG, cond, scale=scale)
+            uo.unet_forward(sd, UNET_CFG, unc, scale=scale)
+    for _ in range(2):
+        pair()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        pair()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def cpu_state_dict():
     """Random-init fp32 weights of the architecture on the host (values do not affect CPU timing)."""
     from oracle import unet_oracle as uo
@@ -377,6 +406,16 @@ def main():
             sd = cpu_state_dict()
             hin = {k: v.clone() for k, v in synthetic_host_inputs(B, lat, lat, args.boxes, 0, pin=False).items()}
             tp = [cpu_pair_seconds(sd, hin, lat, lat, 1.0, n_threads) for _ in range(args.cpu_baseline_pairs)]
+            try:      # the same port as eager fp16-autocast PyTorch on this GPU (context for the ">= 6x eager GPU" target)
+                ms1 = gpu_eager_pair_ms(sd, hin, 1.0, dev)
+                ms0 = gpu_eager_pair_ms(sd, hin, 0.0, dev)
+                line["reference_gpu_eager"] = dict(
+                    value=B / ((n1 * ms1 + (evals - n1) * ms0) / 1e3), unit="images/s", kind="port", dtype="fp16 autocast",
+                    ms_per_pair=dict(gate1=ms1, gate0=ms0),
+                    sample=f"3 [cond, uncond] evaluation pairs per gate value of the oracle port as eager PyTorch on the same GPU "
+                           f"(two separate B={B} forwards per pair, as the reference's sampler does); extrapolated to {evals} pairs per image")
+            except Exception as ex:  # noqa: BLE001
+                line["reference_gpu_eager"] = dict(unavailable=repr(ex)[:200])
             line["cpu_baseline"] = dict(value=B / (evals * float(np.mean(tp))), unit="images/s", cores=n_threads, kind="port",
                                         sample=f"{len(tp)} [cond, uncond] UNet evaluation pair(s) of the oracle port (fp32, torch CPU, "
                                                f"{n_threads} threads) at latent {lat}x{lat}, B={B}; extrapolated x{evals} pairs per image")
