@@ -279,6 +279,9 @@ ALL = [
     ("attention d=160 nq=256 nk=286", check_attention, dict(B=2, heads=8, d=160, nq=256, nk=286), 3e-3),
     ("attention d=160 nq=64 nk=77", check_attention, dict(B=1, heads=8, d=160, nq=64, nk=77), 3e-3),
     ("attention d=40 nq=4096 nk=77", check_attention, dict(B=1, heads=8, d=40, nq=4096, nk=77), 3e-3),
+    ("attention d=40 nq=100 nk=37 (partial q tile, 64-key tail tile)", check_attention, dict(B=2, heads=8, d=40, nq=100, nk=37), 3e-3),
+    ("attention d=40 nq=200 nk=129 (128-key tile + 1-key tail)", check_attention, dict(B=1, heads=8, d=40, nq=200, nk=129), 3e-3),
+    ("attention d=40 peaky logits (rescale path, 2 warpgroups)", check_attention, dict(B=1, heads=8, d=40, nq=300, nk=700, qscale=6.0), 5e-3),
     ("attention d=80 peaky logits (rescale path)", check_attention, dict(B=1, heads=8, d=80, nq=300, nk=700, qscale=6.0), 5e-3),
     ("attention d=8 nq=256 nk=286", check_attention, dict(B=2, heads=8, d=8, nq=256, nk=286), 3e-3),
     ("attention d=16 nq=64 nk=94", check_attention, dict(B=2, heads=8, d=16, nq=64, nk=94), 3e-3),
@@ -292,6 +295,7 @@ ALL = [
     ("groupnorm 1x9216 960 (slab not staged)", check_groupnorm, dict(B=1, HW=9216, c0=640, c1=320, silu=True, eps=1e-5), 2e-3),
     ("relation attention folded C=320 10 relations", check_rela_attn_fused, dict(G=2, C=320, heads=8, nrel=10), 2e-3),
     ("relation attention folded C=1280 10 relations", check_rela_attn_fused, dict(G=1, C=1280, heads=8, nrel=10), 2e-3),
+    ("relation attention folded C=640 1 relation", check_rela_attn_fused, dict(G=2, C=640, heads=8, nrel=1), 2e-3),
     ("relation attention folded C=64 3 relations", check_rela_attn_fused, dict(G=3, C=64, heads=8, nrel=3), 2e-3),
     ("relation attention 30x10 d=40", check_small_attention, dict(B=2, nq=30, nk=10, heads=8, d=40), 3e-3),
     ("relation attention 30x10 d=160", check_small_attention, dict(B=1, nq=30, nk=10, heads=8, d=160), 3e-3),
