@@ -983,11 +983,17 @@ __global__ void __launch_bounds__(128) rela_fold_kernel(const __half* __restrict
     float acc[RF_MAXREL];
 #pragma unroll
     for (int j = 0; j < RF_MAXREL; ++j) acc[j] = 0.f;
-    for (int cc = 0; cc < d; ++cc) {     // A: Wq rows of head h, coalesced over the output channel c
-        const float w = __half2float(wq[(size_t)(h * d + cc) * C + c]);
+    for (int cc0 = 0; cc0 < d; cc0 += 8) {     // A: Wq rows of head h, coalesced over the output channel c; d % 8 == 0
+        __half wv[8];                          // eight independent loads in flight (the loop is L2-latency bound)
 #pragma unroll
-        for (int j = 0; j < RF_MAXREL; ++j)
-            if (j < nrel) acc[j] += w * ks[j * d + cc];
+        for (int e = 0; e < 8; ++e) wv[e] = wq[(size_t)(h * d + cc0 + e) * C + c];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float w = __half2float(wv[e]);
+#pragma unroll
+            for (int j = 0; j < RF_MAXREL; ++j)
+                if (j < nrel) acc[j] += w * ks[j * d + cc0 + e];
+        }
     }
 #pragma unroll
     for (int j = 0; j < RF_MAXREL; ++j)
@@ -995,19 +1001,26 @@ __global__ void __launch_bounds__(128) rela_fold_kernel(const __half* __restrict
 #pragma unroll
     for (int j = 0; j < RF_MAXREL; ++j) acc[j] = 0.f;
     const __half* wr = wo + (size_t)c * C + h * d;        // Bm: row c of Wo, columns of head h (16-byte vectors)
-    for (int c8 = 0; c8 < (d >> 3); ++c8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(wr + c8 * 8);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    for (int c8 = 0; c8 < (d >> 3); c8 += 4) {
+        uint4 u4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(h2[e]);
-            const int cc = c8 * 8 + 2 * e;
+        for (int q = 0; q < 4; ++q)
+            if (c8 + q < (d >> 3)) u4[q] = *reinterpret_cast<const uint4*>(wr + (c8 + q) * 8);
 #pragma unroll
-            for (int j = 0; j < RF_MAXREL; ++j)
-                if (j < nrel) {
-                    acc[j] += f.x * vs[j * d + cc];
-                    acc[j] += f.y * vs[j * d + cc + 1];
-                }
+        for (int q = 0; q < 4; ++q) {
+            if (c8 + q >= (d >> 3)) continue;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u4[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                const int cc = (c8 + q) * 8 + 2 * e;
+#pragma unroll
+                for (int j = 0; j < RF_MAXREL; ++j)
+                    if (j < nrel) {
+                        acc[j] += f.x * vs[j * d + cc];
+                        acc[j] += f.y * vs[j * d + cc + 1];
+                    }
+            }
         }
     }
 #pragma unroll
