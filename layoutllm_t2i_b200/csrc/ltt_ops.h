@@ -48,7 +48,9 @@ int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, i
                        float* e_t_out, const float* e_first, const float* old1, const float* old2, const float* old3,
                        float a_t, float a_prev, float sqrt_1m_at, float* x_out, size_t n, cudaStream_t st);
 
-int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, cudaStream_t st);
+int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, const __half* ev_src,
+                     __half* ev_dst, int ev_len, cudaStream_t st);
+int fill_tvals_launch(const float* host_vals, int n, float* out, cudaStream_t st);
 
 int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int Cs, __half* dst, int Kdst, int koff,
                      cudaStream_t st);

@@ -124,6 +124,10 @@ struct ltt_model {
     __half* vtbuf = nullptr;
     int rows_k_max = 0;
     double* gn_stats = nullptr;
+    // time-embedding table of a sampler run (ltt_plms_sample): [64][emb_total] fp16 + its inputs
+    __half *ev_tab = nullptr, *tt_temb = nullptr, *tt_h = nullptr, *tt_s = nullptr;
+    float* tt_tab = nullptr;
+    int ev_tab_rows = 0;
     float2* row_stats = nullptr;      // (mean, rstd) per token row of the relation block's norm3
     float* rela_scratch = nullptr;    // per-head partial sums of the fused relation attention
     int* rela_tickets = nullptr;
@@ -708,7 +712,8 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     return 0;
 }
 
-static int forward_impl(ltt_model* m, const float* x, const float* t, float alpha_scale, float* eps_out, cudaStream_t st) {
+static int forward_impl(ltt_model* m, const float* x, const float* t, float alpha_scale, float* eps_out, cudaStream_t st,
+                        bool skip_temb = false) {
     if (!m->finalized || m->B == 0) {
         set_error("ltt_unet_forward: call ltt_finalize and ltt_set_conditioning first");
         return -8;
@@ -719,7 +724,9 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
     m->taps.clear();
     m->tap_used = 0;
     ProfScope ps_fw(m, st, PC_FORWARD, 0.0, 0.0);
-    // time embedding -> SiLU(emb) -> all emb_layers at once
+    // time embedding -> SiLU(emb) -> all emb_layers at once (skip_temb: ev_all was filled by the sampler from the table it
+    // precomputed for all of its timesteps)
+    if (!skip_temb) {
     RC(timestep_embed_launch(t, B, mc, m->temb16, st));
     m->launches++;
     {
@@ -730,6 +737,7 @@ static int forward_impl(ltt_model* m, const float* x, const float* t, float alph
         e2.act = ACT_SILU;
         RC(r.gemm(1, B, 4 * mc, {GemmSrc{m->te_h, 4 * mc, 4 * mc, 1}}, m->te2, e2, 1));
         RC(r.gemm(1, B, m->emb_total, {GemmSrc{m->semb, 4 * mc, 4 * mc, 1}}, m->emb_all, epi_out(m->ev_all, m->emb_total), 1));
+    }
     }
     int H = m->H, W = m->W, level = 0, ch = mc;
     __half* cur = nullptr;
@@ -818,18 +826,19 @@ static void drop_graphs(ltt_model* m) {
 // captured once per (gate scale, first-conv variant) into a CUDA graph -- all operand addresses are library-owned and
 // stable between ltt_set_conditioning geometry changes -- and replayed on the caller's stream.  The first call of a key
 // runs eagerly (sets function attributes / occupancy caches that must not happen during capture).
-static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st) {
-    if (!m->use_graphs || m->tap_buf || m->prof_on) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st, bool skip_temb = false) {
+    if (!m->use_graphs || m->tap_buf || m->prof_on) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
     uint32_t abits;
     memcpy(&abits, &alpha_scale, 4);
-    const uint64_t key = (uint64_t)abits | ((uint64_t)(m->sd_conv_w ? 1 : 0) << 32) | ((uint64_t)m->n_grounded << 33);
+    const uint64_t key = (uint64_t)abits | ((uint64_t)(m->sd_conv_w ? 1 : 0) << 32) | ((uint64_t)m->n_grounded << 33) |
+                         ((uint64_t)(skip_temb ? 1 : 0) << 62);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
-        if (m->graph_seen[key]++ == 0) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+        if (m->graph_seen[key]++ == 0) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
         if (!m->capture_stream) LTT_CUDA_OK(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
         const int64_t l0 = m->launches;
         LTT_CUDA_OK(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, m->capture_stream);
+        const int rc = forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, m->capture_stream, skip_temb);
         cudaGraph_t g = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &g);
         const int64_t nl = m->launches - l0;
@@ -840,7 +849,7 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st) {
             if (rc) return rc;
             // capture not possible: stay on the eager path
             m->use_graphs = false;
-            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
         }
         ltt_model::GraphEntry ge;
         const cudaError_t ie = cudaGraphInstantiate(&ge.exec, g, 0);
@@ -848,7 +857,7 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st) {
         if (ie != cudaSuccess) {
             cudaGetLastError();
             m->use_graphs = false;
-            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st);
+            return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
         }
         ge.launches = nl;
         if (m->graphs.size() >= 16) drop_graphs(m);
@@ -1017,6 +1026,8 @@ void ltt_destroy(ltt_model* m) {
     for (auto& kv : m->params) cudaFree(kv.second.dev);
     if (m->sd_conv_w) cudaFree(m->sd_conv_w);
     if (m->sd_conv_b) cudaFree(m->sd_conv_b);
+    for (void* p : {(void*)m->ev_tab, (void*)m->tt_tab, (void*)m->tt_temb, (void*)m->tt_h, (void*)m->tt_s})
+        if (p) cudaFree(p);
     delete m;
 }
 
@@ -1182,10 +1193,48 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
     LTT_CUDA_OK(cudaSetDevice(m->device));
     const ltt_unet_config& c = m->cfg;
     const size_t n = (size_t)Bimg * c.in_channels * m->H * m->W;
+    // The time-embedding branch (timestep_embedding -> time_embed MLP -> every ResBlock's emb_layers) depends on t only:
+    // evaluate it ONCE for all S + 1 evaluation timesteps (three GEMMs over S + 1 rows) instead of 4 launches per
+    // evaluation; plms_prep broadcasts the evaluation's row to the buffer the conv epilogues read.
+    const int E = S + 1;
+    const bool hoist = E <= 64;
+    if (hoist) {
+        std::vector<float> tv;
+        for (int i = 0; i < S; ++i) {
+            const int index = S - 1 - i;
+            tv.push_back((float)timesteps_host[index]);
+            if (i == 0) tv.push_back((float)timesteps_host[std::max(index - 1, 0)]);
+        }
+        const int mc = c.model_channels;
+        if (m->ev_tab_rows < E) {
+            for (void* p : {(void*)m->ev_tab, (void*)m->tt_tab, (void*)m->tt_temb, (void*)m->tt_h, (void*)m->tt_s})
+                if (p) cudaFree(p);
+            LTT_CUDA_OK(cudaMalloc(&m->ev_tab, (size_t)64 * m->emb_total * 2));
+            LTT_CUDA_OK(cudaMalloc(&m->tt_tab, 64 * 4));
+            LTT_CUDA_OK(cudaMalloc(&m->tt_temb, (size_t)64 * mc * 2));
+            LTT_CUDA_OK(cudaMalloc(&m->tt_h, (size_t)64 * 4 * mc * 2));
+            LTT_CUDA_OK(cudaMalloc(&m->tt_s, (size_t)64 * 4 * mc * 2));
+            m->ev_tab_rows = 64;
+        }
+        RC(fill_tvals_launch(tv.data(), E, m->tt_tab, st));
+        RC(timestep_embed_launch(m->tt_tab, E, mc, m->tt_temb, st));
+        Run r{m, st, m->B};
+        GemmEpilogue e1 = epi_out(m->tt_h, 4 * mc);
+        e1.act = ACT_SILU;
+        RC(r.gemm(1, E, 4 * mc, {GemmSrc{m->tt_temb, mc, mc, 1}}, m->te0, e1, 1));
+        GemmEpilogue e2 = epi_out(m->tt_s, 4 * mc);
+        e2.act = ACT_SILU;
+        RC(r.gemm(1, E, 4 * mc, {GemmSrc{m->tt_h, 4 * mc, 4 * mc, 1}}, m->te2, e2, 1));
+        RC(r.gemm(1, E, m->emb_total, {GemmSrc{m->tt_s, 4 * mc, 4 * mc, 1}}, m->emb_all, epi_out(m->ev_tab, m->emb_total), 1));
+        m->launches += 2;
+    }
+    int eval_idx = 0;
     auto eval = [&](const float* x, int tval) -> int {
         // [cond ; uncond] batch of the same latent + timestep vector, written on the device (no host sync in the loop)
         m->launches++;
-        return plms_prep_launch(x, m->x_in, n, cfg ? 2 : 1, m->t_in, m->B, (float)tval, st);
+        const __half* ev = hoist ? m->ev_tab + (size_t)eval_idx * m->emb_total : nullptr;
+        ++eval_idx;
+        return plms_prep_launch(x, m->x_in, n, cfg ? 2 : 1, m->t_in, m->B, (float)tval, ev, m->ev_all, m->emb_total, st);
     };
     LTT_CUDA_OK(cudaMemcpyAsync(m->pl_x, x_inout, n * 4, cudaMemcpyDeviceToDevice, st));
     int nold = 0;
@@ -1200,14 +1249,14 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
         const int tnext = timesteps_host[std::max(index - 1, 0)];
         const float a_t = alphas_host[index], a_prev = alphas_prev_host[index], s1m = sqrt_1m_alphas_host[index];
         RC(eval(m->pl_x, tv));
-        RC(forward_cached(m, scale, st));
+        RC(forward_cached(m, scale, st, hoist));
         float* e_cur = m->pl_e[ring];
         if (nold == 0) {
             // Euler predictor, second evaluation at t_next, e' = (e_t + e_next) / 2, step from the ORIGINAL x
             RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 0, m->pl_x, e_cur, nullptr, nullptr, nullptr,
                                   nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
             RC(eval(m->pl_xsave, tnext));
-            RC(forward_cached(m, scale, st));
+            RC(forward_cached(m, scale, st, hoist));
             RC(plms_update_launch(m->eps_buf, m->eps_buf + n, guidance, cfg, 1, m->pl_x, nullptr, e_cur, nullptr, nullptr,
                                   nullptr, a_t, a_prev, s1m, m->pl_xsave, n, st));
         } else {

@@ -1442,8 +1442,11 @@ int plms_update_launch(const float* eps_c, const float* eps_u, float guidance, i
 
 // UNet inputs of one sampler evaluation: x_in = [x ; x] (cond and uncond rows see the same latent, plms.py:116-122) and
 // the timestep vector, written on the device so the sampler loop never synchronises with the host.
+// ev_src != nullptr: the time-embedding row of this evaluation (precomputed for every sampler step, see
+// ltt_plms_sample) is broadcast to the B rows of the per-evaluation buffer the ResBlock epilogues read.
 __global__ void plms_prep_kernel(const float* __restrict__ x, float* __restrict__ x_in, size_t n, int copies,
-                                 float* __restrict__ t_in, int B, float tval) {
+                                 float* __restrict__ t_in, int B, float tval, const uint4* __restrict__ ev_src,
+                                 uint4* __restrict__ ev_dst, int ev_vecs) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1452,10 +1455,38 @@ __global__ void plms_prep_kernel(const float* __restrict__ x, float* __restrict_
         const float v = x[i];
         for (int c = 0; c < copies; ++c) x_in[(size_t)c * n + i] = v;
     }
+    if (ev_src)
+        for (size_t i = gid; i < (size_t)ev_vecs; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 v = ev_src[i];
+            for (int b = 0; b < B; ++b) ev_dst[(size_t)b * ev_vecs + i] = v;
+        }
 }
-int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, cudaStream_t st) {
+int plms_prep_launch(const float* x, float* x_in, size_t n, int copies, float* t_in, int B, float tval, const __half* ev_src,
+                     __half* ev_dst, int ev_len, cudaStream_t st) {
+    if (ev_src && ev_len % 8) {
+        set_error("plms_prep: embedding row length %d is not a multiple of 8", ev_len);
+        return -1;
+    }
     const int blocks = (int)std::min<size_t>((std::max<size_t>(n, (size_t)B) + 255) / 256, 148 * 4);
-    LTT_CUDA_OK(launch_k(plms_prep_kernel, dim3(blocks), dim3(256), 0, st, x, x_in, n, copies, t_in, B, tval));
+    LTT_CUDA_OK(launch_k(plms_prep_kernel, dim3(blocks), dim3(256), 0, st, x, x_in, n, copies, t_in, B, tval,
+                         reinterpret_cast<const uint4*>(ev_src), reinterpret_cast<uint4*>(ev_dst), ev_len / 8));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// t_tab[i] = v[i]: the sampler's evaluation timesteps, passed by value (no host buffer to keep alive, no staging copy)
+struct TVals { float v[64]; };
+__global__ void fill_tvals_kernel(TVals tv, int n, float* __restrict__ out) {
+    if ((int)threadIdx.x < n) out[threadIdx.x] = tv.v[threadIdx.x];
+}
+int fill_tvals_launch(const float* host_vals, int n, float* out, cudaStream_t st) {
+    if (n > 64) {
+        set_error("fill_tvals: more than 64 values");
+        return -1;
+    }
+    TVals tv;
+    for (int i = 0; i < 64; ++i) tv.v[i] = i < n ? host_vals[i] : 0.f;
+    fill_tvals_kernel<<<1, 64, 0, st>>>(tv, n, out);
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
