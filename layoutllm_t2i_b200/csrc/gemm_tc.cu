@@ -925,7 +925,8 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
                 }
             }
         }
-        for (int sp = 1; sp <= 8; ++sp) {
+        static const int max_split = getenv("LTT_GEMM_MAXSPLIT") ? atoi(getenv("LTT_GEMM_MAXSPLIT")) : 8;     // experiments only
+        for (int sp = 1; sp <= max_split; ++sp) {
             int resident = num_sms;
             if (sp > 1) {
                 if (sp * 2 > iters) break;
