@@ -300,7 +300,19 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT when the first communicator is created; the contract is ONE JSON line
+        # on stdout, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     B, lat, S = args.batch, args.size // 8, args.plms_steps
     model = build_model(dev)
@@ -390,7 +402,8 @@ def main():
                              for k, v in prof.items()},
                     note="per-class CUDA-event times from one extra instrumented image batch after the timed region")
         h2d = sum(v.numel() * v.element_size() for v in host.values())
-        line = dict(metric="images_per_sec_512x512_50plms_6boxes" if args.size == 512 else f"images_per_sec_{args.size}",
+        line = dict(metric="images_per_sec_512x512_50plms_6boxes" if (args.size == 512 and S == 50 and args.boxes == 6) else
+                           f"images_per_sec_{args.size}x{args.size}_{S}plms_{args.boxes}boxes",
                     value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f16",
                     data="synthetic (seeded noise/text/box tensors, random-init weights of the LayoutLLM-T2I UNet)",
