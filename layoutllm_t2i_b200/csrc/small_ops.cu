@@ -747,10 +747,12 @@ int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int
 }
 
 // feats[b, i, :] = mean over the box of hid (fp32) -> fp16; zero for unused slots.  CTA = (64 channels, slot, b),
-// 16 pixel lanes x 16 channel quads, shuffle-free smem reduction over the pixel lanes.  hid is either a materialised
+// RP_LANES pixel lanes x 16 channel quads (a box of a 64x64 latent holds up to 4096 pixels and only the valid slots do
+// work, so the pixel loop is the critical path: 64 lanes x 4 pixels in flight), smem reduction over the pixel lanes.  hid is either a materialised
 // fp32 tensor or (hid == nullptr) the LayerNorm of the fp16 tensor x16 evaluated on the fly from per-row statistics:
 // hid[p][c] = (x16[p][c] - mean_p) * rstd_p * gamma[c] + beta[c]  (same expression / order as layernorm_kernel).
-__global__ void rela_pool_kernel(const float* __restrict__ hid, const __half* __restrict__ x16, const float2* __restrict__ stats,
+constexpr int RP_LANES = 64;
+__global__ void __launch_bounds__(16 * RP_LANES) rela_pool_kernel(const float* __restrict__ hid, const __half* __restrict__ x16, const float2* __restrict__ stats,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ rects,
                                  int mo, int w, int HW, int C, __half* __restrict__ feats) {
     pdl_launch_dependents();
@@ -783,19 +785,27 @@ __global__ void rela_pool_kernel(const float* __restrict__ hid, const __half* __
                            (f1.x - st.x) * st.y * g4.z + b4.z, (f1.y - st.x) * st.y * g4.w + b4.w);
     };
     // four pixels in flight per thread; accumulation order = pixel order of this lane (as the single-pixel loop)
-    for (int p = pl; p < area; p += 64) {
+    for (int p = pl; p < area; p += 4 * RP_LANES) {
         float4 v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (p + 16 * k < area) v[k] = value(p + 16 * k);
+            if (p + RP_LANES * k < area) v[k] = value(p + RP_LANES * k);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (p + 16 * k < area) {
+            if (p + RP_LANES * k < area) {
                 acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
             }
     }
-    __shared__ float4 red[256];
+    __shared__ float4 red[16 * RP_LANES];
     red[threadIdx.x] = acc;
+    __syncthreads();
+    if (pl < 16) {                                // two-level reduction over the pixel lanes, fixed order: deterministic
+        for (int k = pl + 16; k < RP_LANES; k += 16) {
+            const float4 v = red[k * 16 + cq];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        red[threadIdx.x] = acc;
+    }
     __syncthreads();
     if (pl == 0) {
         for (int k = 1; k < 16; ++k) {
@@ -816,7 +826,7 @@ int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, c
         set_error("rela_pool: C %% 64 != 0 (C=%d)", C);
         return -1;
     }
-    LTT_CUDA_OK(launch_k(rela_pool_kernel, dim3(dim3(C / 64, mo, B)), dim3(256), 0, st, hid, x16, stats, gamma, beta, rects, mo, w, h * w,
+    LTT_CUDA_OK(launch_k(rela_pool_kernel, dim3(dim3(C / 64, mo, B)), dim3(16 * RP_LANES), 0, st, hid, x16, stats, gamma, beta, rects, mo, w, h * w,
                          C, feats));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
