@@ -2,13 +2,15 @@
 //
 //   D[m, n] = sum_k A[m, k] * Wp[n, k]      fp16 x fp16 -> fp32 in TMEM
 //
-// One CTA computes a 128 x BN output tile.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
-// tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  A-tiles are fetched by
-// 4-D TMA boxes (64 channels x tw x th x tb pixels = 128 rows) straight out of the NHWC activation; the nine taps of
-// a 3x3 convolution are nine shifted boxes accumulated into the same TMEM tile, padding comes from TMA's
-// out-of-bounds zero fill, so no im2col buffer ever exists.  Channel-concatenated inputs and the ResBlock's 1x1
-// skip convolution are extra A sources appended along K.  gridDim.z > 1 = split-K: partial tiles go to an fp32
-// workspace and the last CTA to arrive (atomic ticket) sums the slabs in fixed order and runs the epilogue.
+// One CTA computes 128 x BN output tiles (persistent, accumulator double buffered in TMEM).  Warp roles: warp 0 = TMA
+// producer, warp 1 = TMEM owner + tcgen05.mma issuer (both loops run warp-converged, one elected lane issues), warps
+// 2.. = EPI_WGS epilogue warpgroups (TMEM -> registers -> fused epilogue -> global).  A-tiles are fetched by 4-D TMA
+// boxes (64 channels x tw x th x tb pixels = 128 rows) straight out of the NHWC activation; the nine taps of a 3x3
+// convolution are nine shifted boxes accumulated into the same TMEM tile, padding comes from TMA's out-of-bounds zero
+// fill, so no im2col buffer ever exists.  Channel-concatenated inputs and the ResBlock's 1x1 skip convolution are
+// extra A sources appended along K.  splits > 1 = split-K over a thread-block cluster: the K range is divided over the
+// cluster ranks, partial accumulators meet in distributed shared memory and are summed in fixed rank order.
+// PAIR = CTA-pair mode (cta_group::2): a 2-CTA cluster computes 256 x BN tiles, each CTA stages half of the B tile.
 //
 // Replaces (reference, /root/reference/GLIGEN/ldm/modules): every nn.Linear / nn.Conv2d on the UNet path --
 // attention.py:108-112,153-157 (q/k/v/out projections), :38-65 (GEGLU feed-forward), :425-433 (proj_in/out),
@@ -482,12 +484,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue warps (2..9): two warpgroups, each
+        // ---------------------------------------------------------------- epilogue warps (2 .. 2 + 4*EPI_WGS): each
         // thread owns one tile row (TMEM lane) and its warpgroup's share of the 32-column chunks
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;            // tile row
         const int wg = (warp - 2) >> 2;         // 0 .. EPI_WGS-1
-        const int et = threadIdx.x - 64;        // 0..255
+        const int et = threadIdx.x - 64;        // 0 .. EPI_THREADS-1
         const GemmEpilogue& e = args.epi;
         const bool geglu = e.act == ACT_GEGLU;
         const int Nout = geglu ? args.N / 2 : args.N;
