@@ -3,9 +3,10 @@
 // lazy (thresholded) rescale of O, so O is touched by the CUDA cores only when a row maximum jumps.
 //
 // One CTA = 128 query rows of one (batch, head).  warp 0: TMA producer (Q once, K / V^T tiles double buffered),
-// warp 1: tcgen05.mma issuer, warps 2..5: one softmax thread per query row (TMEM lane).  P is written to shared
-// memory in the 128-B-swizzled K-major layout and consumed as the A operand of the PV MMA; V arrives transposed
-// ([C, keys], keys contiguous -- written that way by the QKV projection's epilogue) so it is a K-major B operand.
+// warp 1: tcgen05.mma issuer (both warp-converged with elected issue), then NWG softmax warpgroups: NWG threads per
+// query row (TMEM lane), each owning BKV / NWG columns of the score tile.  P is written to shared memory in the
+// 128-B-swizzled K-major layout and consumed as the A operand of the PV MMA; V arrives transposed ([C, keys], keys
+// contiguous -- written that way by the QKV projection's epilogue) so it is a K-major B operand.
 // Head dims 40 / 80 / 160 run as K = 48 / 80 / 160 for QK^T (zero padded columns) and N = 48 / 80 / 160 for PV.
 //
 // Replaces the einsum / softmax / einsum triple of the reference's attention modules
