@@ -50,12 +50,15 @@ void ltt_destroy(ltt_model* m);
 /* model.load_state_dict (txt2img.py:106): one call per state_dict entry, reference key names and shapes
  * (SURVEY.md Appendix B); `data` is an fp32 DEVICE or HOST pointer (is_host != 0).  Unknown keys return -5. */
 int ltt_load_param(ltt_model* m, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
-/* Repack everything loaded so far into the device-native fp16 layouts; must precede the first forward.  May be
- * called again after more ltt_load_param calls (weights changed). */
+/* Repack everything loaded so far into the device-native fp16 layouts; must precede the first forward.  Consumes
+ * (frees) the fp32 staging copies of every matrix it repacked: after a weight change load the WHOLE state_dict again
+ * (as model.load_state_dict does) before calling it again. */
 int ltt_finalize(ltt_model* m);
 /* UNetModel.restore_first_conv_from_SD (openaimodel.py:393-405): substitute input_blocks.0.0 (weight [Cm,4,3,3],
- * bias [Cm], fp32 device or host).  Permanent, like the reference. */
+ * bias [Cm], fp32 device or host).  Permanent, like the reference, until ltt_clear_first_conv (a later
+ * model.load_state_dict overwrites the swapped conv in the reference too). */
 int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int is_host);
+int ltt_clear_first_conv(ltt_model* m);
 
 /* Per-image conditioning (everything UNetModel.forward derives from the non-x inputs, openaimodel.py:413-446):
  * context [B,77,ctx], relations [B,R,ctx], boxes [B,max_objs,4], masks [B,max_objs], pos_emb [B,max_objs,in_dim],
@@ -68,9 +71,10 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
 
 /* UNetModel.forward (openaimodel.py:413-459) with the cached conditioning: x [B,4,H,W] fp32 NCHW, timesteps [B]
  * (fp32 values of the integer steps), gate scale as written by set_alpha_scale (txt2img.py:46-50);
- * eps_out [B,4,H,W] fp32 NCHW (values are fp16-rounded, as the autocast reference returns). */
-int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, float alpha_scale, float* eps_out,
-                     void* stream);
+ * eps_out [B,4,H,W] fp32 NCHW (values are fp16-rounded, as the autocast reference returns).  B, H, W are the shape
+ * of x and must equal what ltt_set_conditioning cached (-1 otherwise: no out-of-bounds access on a stale cache). */
+int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, int B, int H, int W, float alpha_scale,
+                     float* eps_out, void* stream);
 
 /* PLMSSampler.plms_sampling (plms.py:64-163) for a batch whose conditioning was set with
  * ltt_set_conditioning(B = 2*Bimg, n_grounded = Bimg) when guidance != 1 (else B = Bimg):

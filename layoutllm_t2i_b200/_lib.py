@@ -36,8 +36,9 @@ _SIGS = {
     "ltt_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
     "ltt_finalize": (_i, [_vp]),
     "ltt_set_first_conv": (_i, [_vp, _vp, _vp, _i]),
+    "ltt_clear_first_conv": (_i, [_vp]),
     "ltt_set_conditioning": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "ltt_unet_forward": (_i, [_vp, _vp, _vp, _f, _vp, _vp]),
+    "ltt_unet_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "ltt_plms_sample": (_i, [_vp, _vp, _i, _i, C.POINTER(_i), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f),
                              C.POINTER(_f), _f, _vp, _vp, _vp]),
     "ltt_launch_count": (_i64, [_vp]),

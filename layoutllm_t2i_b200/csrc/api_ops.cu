@@ -7,22 +7,15 @@
 using namespace ltt;
 
 namespace ltt {
-// process-wide split-K scratch for operator-level calls (model handles own theirs)
-static GemmWorkspace g_ws;
+// SM count of the current device for operator-level calls (model handles query their own)
 static int g_sms = 0;
 int ensure_global_ws() {
-    if (g_ws.partials) return 0;
+    if (g_sms) return 0;
     int dev = 0;
     LTT_CUDA_OK(cudaGetDevice(&dev));
     LTT_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_ws.partial_bytes = (size_t)64 << 20;
-    g_ws.n_counters = 4096;
-    LTT_CUDA_OK(cudaMalloc(&g_ws.partials, g_ws.partial_bytes));
-    LTT_CUDA_OK(cudaMalloc(&g_ws.counters, g_ws.n_counters * sizeof(int)));
-    LTT_CUDA_OK(cudaMemset(g_ws.counters, 0, g_ws.n_counters * sizeof(int)));
     return 0;
 }
-const GemmWorkspace& global_ws() { return g_ws; }
 int global_sms() { return g_sms; }
 }  // namespace ltt
 
@@ -50,7 +43,7 @@ int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, co
     p.epi.bias = bias; p.epi.act = act; p.epi.res = res; p.epi.res_dtype = res_dtype; p.epi.ldr = ldr;
     p.epi.gate = gate; p.epi.has_gate = has_gate; p.epi.out = out; p.epi.out_dtype = out_dtype; p.epi.ldo = ldo;
     p.w_static = op_w_static();
-    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+    return gemm_tc_launch(p, global_sms(), (cudaStream_t)stream);
 }
 
 int ltt_op_pack_geglu(const float* w, int rows, int K, void* out_f16, void* stream) {
@@ -71,7 +64,7 @@ int ltt_op_conv3x3(const void* x, int B, int H, int W, int C, const void* w_pack
     p.epi.bias = bias; p.epi.rowvec = (const __half*)rowvec; p.epi.ld_rowvec = N;
     p.epi.out = out; p.epi.out_dtype = DT_F16; p.epi.ldo = N;
     p.w_static = op_w_static();
-    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+    return gemm_tc_launch(p, global_sms(), (cudaStream_t)stream);
 }
 
 int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int heads, int dpad, void* q, int rows_q,
@@ -85,7 +78,7 @@ int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int h
     p.epi.C = C; p.epi.dhead = C / heads; p.epi.dpad = dpad; p.epi.rows_q = rows_q; p.epi.rows_k = rows_k;
     p.epi.pitch_v = pitch_v; p.epi.tokens = tokens;
     p.w_static = op_w_static();
-    return gemm_tc_launch(p, global_ws(), global_sms(), (cudaStream_t)stream);
+    return gemm_tc_launch(p, global_sms(), (cudaStream_t)stream);
 }
 
 int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,

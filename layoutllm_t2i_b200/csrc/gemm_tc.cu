@@ -840,7 +840,7 @@ struct Variant {
     }
 };
 
-int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, cudaStream_t stream) {
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     GemmDeviceArgs a;
     memset(&a, 0, sizeof(a));
     a.B = p.B; a.H = p.H; a.W = p.W; a.N = p.N;
@@ -970,7 +970,6 @@ int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, c
         int rc = make_tmap_f16(&a.bmap, p.w, 2, dims, str, box);
         if (rc) return rc;
     }
-    (void)ws;
     if (use_pair) {
         const int cu = ((mtiles + 1) / 2) * ntiles;
         switch (BN) {

@@ -96,15 +96,8 @@ struct GemmProblem {
     GemmEpilogue epi;
 };
 
-// workspace for split-K partials (fp32) and tile counters; sizes in bytes returned by gemm_workspace_bytes().
-struct GemmWorkspace {
-    float* partials = nullptr;
-    size_t partial_bytes = 0;
-    int* counters = nullptr;
-    int n_counters = 0;
-};
-
-int gemm_tc_launch(const GemmProblem& p, const GemmWorkspace& ws, int num_sms, cudaStream_t stream);
+// (split-K partial sums meet in distributed shared memory of a thread-block cluster: no global workspace)
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused attention core:  O[b, i, h*d:(h+1)*d] = softmax_j(q_i . k_j * scale) v_j   (flash-style, S/O in TMEM)

@@ -54,7 +54,12 @@ struct StW {
     Lin r_q, r_kv, r_out, r_ff1, r_ff2;
     float f_ta = 0, f_td = 0, r_ta = 0, r_td = 0;   // tanh(alpha)
     // per-conditioning caches
-    __half *c2_k = nullptr, *c2_vt = nullptr, *fg_k = nullptr, *fg_vt = nullptr, *r_kvbuf = nullptr;
+    __half *c2_k = nullptr, *c2_vt = nullptr, *r_kvbuf = nullptr;
+    // self-attention K [B, rows_k, heads*dpad] / V^T [B, C, rows_k] of THIS block: rows [0, N) are rewritten by every
+    // QKV projection, rows [N, N + max_objs) hold the block's grounding-token K / V (fuser.linear -> norm1 -> to_k / to_v,
+    // step invariant) and are written once per conditioning -- the gated self-attention reads N + max_objs keys in place
+    __half *kb = nullptr, *vtb = nullptr;
+    int rows_k = 0;
     __half *r_A = nullptr, *r_Bm = nullptr;          // relation keys / values folded through to_q / to_out (rela_fold_kernel)
 };
 
@@ -120,9 +125,9 @@ struct ltt_model {
     float *xe32 = nullptr, *xf32 = nullptr;
     __half *feats = nullptr, *feats2 = nullptr, *feats3 = nullptr, *featln = nullptr, *featq = nullptr, *featao = nullptr,
            *featff = nullptr;
-    std::map<int, __half*> qbuf, kbuf;   // keyed by head dim (pad columns of a buffer must stay zero)
-    __half* vtbuf = nullptr;
-    int rows_k_max = 0;
+    std::map<int, __half*> qbuf;         // keyed by head dim (pad columns of a buffer must stay zero)
+    __half *cond_pin = nullptr, *cond_h1 = nullptr, *cond_h2 = nullptr;   // PositionNet / fuser.linear scratch rows
+    std::vector<std::string> packed_keys;   // fp32 staging copies that ltt_finalize frees after repacking
     double* gn_stats = nullptr;
     // time-embedding table of a sampler run (ltt_plms_sample): [64][emb_total] fp16 + its inputs
     __half *ev_tab = nullptr, *tt_temb = nullptr, *tt_h = nullptr, *tt_s = nullptr;
@@ -134,18 +139,23 @@ struct ltt_model {
     __half *temb16 = nullptr, *te_h = nullptr, *semb = nullptr, *ev_all = nullptr;
     float *x_in = nullptr, *t_in = nullptr, *eps_buf = nullptr;
     float *pl_x = nullptr, *pl_xsave = nullptr, *pl_e[4] = {nullptr, nullptr, nullptr, nullptr};
-    GemmWorkspace ws;
     int64_t launches = 0;
     // CUDA graphs of the UNet evaluation, keyed by (gate scale, first-conv variant, grounded rows)
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int64_t replays = 0; };
     std::map<uint64_t, GraphEntry> graphs;
     std::map<uint64_t, int> graph_seen;
     cudaStream_t capture_stream = nullptr;
     bool use_graphs = true;
     bool rela_fused = true;           // LTT_RELA_UNFUSED=1: q-GEMM / attention / out-GEMM as separate launches (A/B checks)
     // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
-    struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
-    bool prof_on = false;
+    // prof_mode 1: eager launches, every class launch bracketed by events.  prof_mode 2: the brackets are external
+    // event-record nodes INSIDE the captured CUDA graph of the evaluation (the mode the timed path runs in); a record then
+    // holds the times of the graph's last replay and is weighted by the graph's replay count in ltt_profile_report.
+    struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; uint64_t gkey; bool in_graph; };
+    int prof_mode = 0;
+    bool prof_on = false;             // prof_mode == 1
+    bool capturing = false;
+    uint64_t capture_key = 0;
     std::vector<ProfRec> prof;
     // debug taps (ltt_debug_set_taps): named fp32 copies of intermediate activations
     struct Tap { std::string name; int64_t offset, rows, cols; };
@@ -180,6 +190,7 @@ static int pack_linear(ltt_model* m, const std::string& wkey, const char* bkey_o
     void* p;
     RC(m->warena.alloc(&p, (size_t)N * K * 2));
     RC(pack_rows_launch(w->dev, N, K, (__half*)p, 0, geglu, 0));
+    m->packed_keys.push_back(wkey);
     out->w = (__half*)p; out->N = N; out->K = K; out->bias = nullptr;
     if (bkey_or_null) {
         GETP(b, std::string(bkey_or_null))
@@ -214,6 +225,7 @@ static int pack_concat(ltt_model* m, const std::vector<std::string>& keys, Lin* 
         RC(pack_rows_launch(w->dev, (int)w->shape[0], K, (__half*)p, off, 0, 0));
         off += (int)w->shape[0];
     }
+    for (auto& k : keys) m->packed_keys.push_back(k);
     out->w = (__half*)p; out->N = N; out->K = K; out->bias = nullptr;
     return 0;
 }
@@ -236,6 +248,7 @@ static int build_res(ltt_model* m, const std::string& p, int cin, int cout, int 
         void* q;
         RC(m->warena.alloc(&q, (size_t)cout * 9 * cin * 2));
         RC(pack_conv_launch(w->dev, cout, cin, 9, 0, cin, (__half*)q, 9 * cin, 0, 0));
+        m->packed_keys.push_back(p + ".in_layers.2.weight");
         r.conv1 = Lin{(__half*)q, b->dev, cout, 9 * cin};
     }
     r.has_skip = cin != cout;
@@ -246,6 +259,7 @@ static int build_res(ltt_model* m, const std::string& p, int cin, int cout, int 
         void* q;
         RC(m->warena.alloc(&q, (size_t)cout * K * 2));
         RC(pack_conv_launch(w->dev, cout, cout, 9, 0, cout, (__half*)q, K, 0, 0));
+        m->packed_keys.push_back(p + ".out_layers.3.weight");
         const float* bias = b->dev;
         if (r.has_skip) {
             GETP(sw, p + ".skip_connection.weight")
@@ -254,6 +268,7 @@ static int build_res(ltt_model* m, const std::string& p, int cin, int cout, int 
             RC(pack_conv_launch(sw->dev, cout, cin, 1, 0, c_first, (__half*)q, K, 9 * cout, 0));
             if (c_first < cin)
                 RC(pack_conv_launch(sw->dev, cout, cin, 1, c_first, cin - c_first, (__half*)q, K, 9 * cout + c_first, 0));
+            m->packed_keys.push_back(p + ".skip_connection.weight");
             std::vector<float> hb(cout), hs(cout);
             LTT_CUDA_OK(cudaMemcpy(hb.data(), b->dev, cout * 4, cudaMemcpyDeviceToHost));
             LTT_CUDA_OK(cudaMemcpy(hs.data(), sb->dev, cout * 4, cudaMemcpyDeviceToHost));
@@ -323,6 +338,7 @@ static int build_conv(ltt_model* m, const std::string& p, int C, std::vector<Con
     void* q;
     RC(m->warena.alloc(&q, (size_t)C * 9 * C * 2));
     RC(pack_conv_launch(w->dev, C, C, 9, 0, C, (__half*)q, 9 * C, 0, 0));
+    m->packed_keys.push_back(p + ".weight");
     c.conv = Lin{(__half*)q, b->dev, C, 9 * C};
     dst->push_back(c);
     return 0;
@@ -332,6 +348,7 @@ static int build_conv(ltt_model* m, const std::string& p, int C, std::vector<Con
 static int build_plan(ltt_model* m) {
     const ltt_unet_config& c = m->cfg;
     m->warena.release();
+    m->packed_keys.clear();
     m->in_blocks.clear(); m->out_blocks.clear(); m->mid.clear();
     m->res.clear(); m->st.clear(); m->downs.clear(); m->ups.clear();
     m->emb_total = 0;
@@ -416,6 +433,7 @@ static int build_plan(ltt_model* m) {
         void* q;
         RC(m->warena.alloc(&q, (size_t)c.out_channels * 9 * mc * 2));
         RC(pack_conv_launch(w->dev, c.out_channels, mc, 9, 0, mc, (__half*)q, 9 * mc, 0, 0));
+        m->packed_keys.push_back("out.2.weight");
         m->out_w = (__half*)q; m->out_b = b->dev;
     }
     RC(lin(m, "time_embed.0", &m->te0));
@@ -443,6 +461,15 @@ static int build_plan(ltt_model* m) {
         m->null_txt = a->dev; m->null_pos = b->dev;
     }
     LTT_CUDA_OK(cudaDeviceSynchronize());
+    // The fp32 staging copies of every repacked matrix (5 GB for the full UNet) are dead weight from here on: only
+    // biases, norm affine parameters, the gates and the 4-channel first conv are read in fp32 by the kernels.
+    for (auto& k : m->packed_keys) {
+        auto it = m->params.find(k);
+        if (it == m->params.end()) continue;
+        cudaFree(it->second.dev);
+        m->params.erase(it);
+    }
+    m->packed_keys.clear();
     return 0;
 }
 
@@ -452,16 +479,21 @@ struct ProfScope {
     ltt_model* m;
     cudaStream_t st;
     int idx = -1;
+    bool graph = false;
     ProfScope(ltt_model* m_, cudaStream_t st_, int cls, double flops, double bytes) : m(m_), st(st_) {
-        if (!m->prof_on) return;
-        ltt_model::ProfRec r{cls, flops, bytes, nullptr, nullptr};
+        graph = m->prof_mode == 2 && m->capturing;
+        if (!m->prof_on && !graph) return;
+        ltt_model::ProfRec r{cls, flops, bytes, nullptr, nullptr, graph ? m->capture_key : 0, graph};
         if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
-        cudaEventRecord(r.e0, st);
+        if (graph) cudaEventRecordWithFlags(r.e0, st, cudaEventRecordExternal);
+        else cudaEventRecord(r.e0, st);
         m->prof.push_back(r);
         idx = (int)m->prof.size() - 1;
     }
     ~ProfScope() {
-        if (idx >= 0) cudaEventRecord(m->prof[idx].e1, st);
+        if (idx < 0) return;
+        if (graph) cudaEventRecordWithFlags(m->prof[idx].e1, st, cudaEventRecordExternal);
+        else cudaEventRecord(m->prof[idx].e1, st);
     }
 };
 
@@ -504,7 +536,7 @@ struct Run {
         ProfScope ps(m, st, PC_GEMM, 2.0 * Mrows * N * p.Ktot,
                      2.0 * (Mrows * p.Ktot / (srcs.begin()->taps == 9 ? 9.0 : 1.0) + (double)N * p.Ktot) +
                          Mrows * nout * (p.epi.out_dtype == DT_F32 ? 4.0 : 2.0));
-        return gemm_tc_launch(p, m->ws, m->sms, st);
+        return gemm_tc_launch(p, m->sms, st);
     }
 };
 
@@ -587,16 +619,17 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     cudaStream_t st = r.st;
     const int B = r.B, N = H * W, C = s.C, M = B * N;
     const int mo = m->cfg.max_objs;
-    const int rows_k = m->rows_k_max, pitch_v = m->rows_k_max;
+    const int rows_k = s.rows_k, pitch_v = s.rows_k;
     __half* qb = m->qbuf[s.d];
-    __half* kb = m->kbuf[s.d];
+    __half* kb = s.kb;
+    __half* vtb = s.vtb;
     // GroupNorm (eps 1e-6) -> proj_in
     RC(groupnorm(m, st, x_in, C, nullptr, 0, B, N, s.gn, 1e-6f, 0, m->tnorm));
     RC(r.gemm(H, W, C, {GemmSrc{m->tnorm, C, C, 1}}, s.proj_in, epi_out(m->xa, C)));
     // attn1
     RC(ln(m, st, m->xa, DT_F16, M, C, s.ln1, m->ln16, nullptr));
-    RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.a1_qkv, epi_qkv(s, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, 0)));
-    RC(attention(m, st, s, B, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, N, m->ao));
+    RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.a1_qkv, epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0)));
+    RC(attention(m, st, s, B, qb, N, kb, rows_k, vtb, pitch_v, N, N, m->ao));
     {
         GemmEpilogue e = epi_out(m->xb, C);
         e.res = m->xa; e.ldr = C;
@@ -606,14 +639,11 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     RC(tap(m, st, s.p + ":proj_in", m->xa, DT_F16, M, C));
     RC(tap(m, st, s.p + ":attn1", m->xb, DT_F16, M, C));
     if (alpha_scale != 0.0f) {
-        // GatedSelfAttentionDense (attention.py:226-234): visual queries only, 30 cached grounding K/V rows appended
+        // GatedSelfAttentionDense (attention.py:226-234): visual queries only; the 30 grounding K/V rows of this block sit
+        // behind the N visual rows of its K / V^T buffers since ltt_set_conditioning
         RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
-        RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_qkv, epi_qkv(s, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, 0)));
-        const int rowlen = s.heads * s.dpad;
-        RC(ground_kv_copy_launch(s.fg_k, kb + (size_t)N * rowlen, (size_t)rows_k * rowlen, rowlen, s.fg_vt, m->vtbuf + N,
-                                 (size_t)C * pitch_v, pitch_v, B, mo, C, st));
-        m->launches += 1;
-        RC(attention(m, st, s, B, qb, N, kb, rows_k, m->vtbuf, pitch_v, N, N + mo, m->ao));
+        RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_qkv, epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0)));
+        RC(attention(m, st, s, B, qb, N, kb, rows_k, vtb, pitch_v, N, N + mo, m->ao));
         {
             GemmEpilogue e = epi_out(m->xa, C);
             e.res = m->xb; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_ta;
@@ -820,6 +850,17 @@ static void drop_graphs(ltt_model* m) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     m->graphs.clear();
     m->graph_seen.clear();
+    // event-record nodes of instrumented graphs die with them
+    std::vector<ltt_model::ProfRec> keep;
+    for (auto& r : m->prof) {
+        if (r.in_graph) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        } else {
+            keep.push_back(r);
+        }
+    }
+    m->prof.swap(keep);
 }
 
 // One UNet evaluation from the static buffers x_in / t_in into eps_buf.  The ~600-750 launches of an evaluation are
@@ -831,14 +872,17 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st, bool
     uint32_t abits;
     memcpy(&abits, &alpha_scale, 4);
     const uint64_t key = (uint64_t)abits | ((uint64_t)(m->sd_conv_w ? 1 : 0) << 32) | ((uint64_t)m->n_grounded << 33) |
-                         ((uint64_t)(skip_temb ? 1 : 0) << 62);
+                         ((uint64_t)(skip_temb ? 1 : 0) << 62) | ((uint64_t)(m->prof_mode == 2 ? 1 : 0) << 61);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
         if (m->graph_seen[key]++ == 0) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
         if (!m->capture_stream) LTT_CUDA_OK(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
         const int64_t l0 = m->launches;
         LTT_CUDA_OK(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
+        m->capturing = true;
+        m->capture_key = key;
         const int rc = forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, m->capture_stream, skip_temb);
+        m->capturing = false;
         cudaGraph_t g = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &g);
         const int64_t nl = m->launches - l0;
@@ -864,6 +908,7 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st, bool
         it = m->graphs.emplace(key, ge).first;
     }
     LTT_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    it->second.replays++;
     m->launches += it->second.launches;
     return 0;
 }
@@ -872,7 +917,7 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st, bool
 static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n_rel) {
     drop_graphs(m);
     m->carena.release();
-    m->qbuf.clear(); m->kbuf.clear(); m->rects.clear(); m->skips.clear();
+    m->qbuf.clear(); m->rects.clear(); m->skips.clear();
     const ltt_unet_config& c = m->cfg;
     const int mc = c.model_channels, mo = c.max_objs;
     m->B = B; m->H = H; m->W = W; m->ctx_len = ctx_len; m->n_rel = n_rel;
@@ -893,7 +938,8 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
                     ch = r.cout;
                     cin_extra = 0;
                 } else if (L.kind == L_ST) {
-                    const StW& s = m->st[L.idx];
+                    StW& s = m->st[L.idx];
+                    s.rows_k = (h * w + mo + 63) / 64 * 64;
                     max_tok = std::max(max_tok, (size_t)B * h * w * s.C);
                     max_ff = std::max(max_ff, (size_t)B * h * w * 4 * s.C);
                     max_norm = std::max(max_norm, (size_t)B * h * w * s.C);
@@ -937,19 +983,22 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->featff, max_featff * 2));
     RC(A(&m->rela_scratch, fe * c.num_heads * 4));
     RC(A(&m->rela_tickets, (size_t)B * mo * 4, true));
-    // attention operand buffers: q/k per head padding (pad columns stay zero for ever), one V^T buffer
-    m->rows_k_max = (H * W + mo + 63) / 64 * 64;
-    size_t max_vt = 0;
+    // attention operand buffers: q per head dim (pad columns stay zero for ever); K / V^T per block (see StW)
     for (auto& s : m->st) {
         if (!m->qbuf.count(s.d)) {
-            __half *q, *k;
+            __half* q;
             RC(A(&q, (size_t)B * H * W * s.heads * s.dpad * 2, true));
-            RC(A(&k, (size_t)B * m->rows_k_max * s.heads * s.dpad * 2, true));
-            m->qbuf[s.d] = q; m->kbuf[s.d] = k;
+            m->qbuf[s.d] = q;
         }
-        max_vt = std::max(max_vt, (size_t)B * s.C * m->rows_k_max);
     }
-    RC(A(&m->vtbuf, max_vt * 2, true));
+    // PositionNet / fuser.linear scratch of ltt_set_conditioning: R = B * max_objs rows of up to max(maxC, 512) columns
+    {
+        const size_t R = (size_t)B * mo;
+        const size_t wide = std::max<size_t>({(size_t)maxC, 512, (size_t)c.grounding_out_dim});
+        RC(A(&m->cond_pin, R * (c.grounding_in_dim + 8 * c.fourier_freqs) * 2));
+        RC(A(&m->cond_h1, R * wide * 2));
+        RC(A(&m->cond_h2, R * wide * 2));
+    }
     RC(A(&m->gn_stats, (size_t)B * 64 * sizeof(double)));
     RC(A(&m->temb16, (size_t)B * mc * 2));
     RC(A(&m->te_h, (size_t)B * 4 * mc * 2));
@@ -959,10 +1008,6 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->x_in, xin * 4)); RC(A(&m->t_in, B * 4)); RC(A(&m->eps_buf, xout * 4));
     RC(A(&m->pl_x, xin * 4)); RC(A(&m->pl_xsave, xin * 4));
     for (int i = 0; i < 4; ++i) RC(A(&m->pl_e[i], xout * 4));
-    m->ws.partial_bytes = (size_t)96 << 20;
-    m->ws.n_counters = 8192;
-    RC(A(&m->ws.partials, m->ws.partial_bytes));
-    RC(A(&m->ws.counters, m->ws.n_counters * sizeof(int), true));
     // conditioning tensors
     RC(A(&m->ctx16, (size_t)B * ctx_len * c.context_dim * 2));
     RC(A(&m->rel16, (size_t)B * n_rel * c.context_dim * 2));
@@ -979,8 +1024,8 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
         const int rowlen = s.heads * s.dpad;
         RC(A(&s.c2_k, (size_t)B * ctx_len * rowlen * 2, true));
         RC(A(&s.c2_vt, (size_t)B * s.C * 128 * 2, true));
-        RC(A(&s.fg_k, (size_t)B * mo * rowlen * 2, true));
-        RC(A(&s.fg_vt, (size_t)B * s.C * 32 * 2, true));
+        RC(A(&s.kb, (size_t)B * s.rows_k * rowlen * 2, true));
+        RC(A(&s.vtb, (size_t)B * s.C * s.rows_k * 2, true));
         RC(A(&s.r_kvbuf, (size_t)B * n_rel * 2 * s.C * 2, true));
         RC(A(&s.r_A, (size_t)B * s.heads * n_rel * s.C * 2, true));
         RC(A(&s.r_Bm, (size_t)B * s.heads * n_rel * s.C * 2, true));
@@ -1082,6 +1127,16 @@ int ltt_set_first_conv(ltt_model* m, const float* weight, const float* bias, int
     return 0;
 }
 
+int ltt_clear_first_conv(ltt_model* m) {
+    if (!m) return -1;
+    LTT_CUDA_OK(cudaSetDevice(m->device));
+    LTT_CUDA_OK(cudaDeviceSynchronize());
+    if (m->sd_conv_w) cudaFree(m->sd_conv_w);
+    if (m->sd_conv_b) cudaFree(m->sd_conv_b);
+    m->sd_conv_w = m->sd_conv_b = nullptr;
+    return 0;
+}
+
 int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const float* relations, int n_rel,
                          const float* boxes, const float* masks, const float* pos_emb, int B, int n_grounded,
                          int H, int W, void* stream) {
@@ -1114,11 +1169,11 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
         LTT_CUDA_OK(cudaMemcpyAsync(m->emb_f, pos_emb, (size_t)n_grounded * mo * c.grounding_in_dim * 4, cudaMemcpyDeviceToDevice, st));
     }
     Run r{m, st, B};
-    // PositionNet (text_grounding_net.py:26-43): scratch rows live in ffbuf / ln16
+    // PositionNet (text_grounding_net.py:26-43) on dedicated scratch rows
     const int R = B * mo, pin = c.grounding_in_dim + 8 * c.fourier_freqs;
-    __half* pin16 = m->ffbuf;
-    __half* h1 = m->ln16;
-    __half* h2 = m->ao;
+    __half* pin16 = m->cond_pin;
+    __half* h1 = m->cond_h1;
+    __half* h2 = m->cond_h2;
     RC(posnet_input_launch(m->boxes_f, m->masks_f, m->emb_f, m->null_txt, m->null_pos, R, c.grounding_in_dim, c.fourier_freqs, pin16, st));
     {
         GemmEpilogue e = epi_out(h1, 512);
@@ -1134,8 +1189,24 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
         RC(rela_rects_launch(m->boxes_f, m->masks_f, B, mo, h, w, m->rects[l], st));
         h /= 2; w /= 2;
     }
+    int sti = 0;
+    std::vector<int> st_tokens(m->st.size(), 0);      // visual tokens N of every transformer block, in m->st order
+    {
+        int hh = H, ww = W;
+        auto visit = [&](const std::vector<Layer>& ls) {
+            for (auto& L : ls) {
+                if (L.kind == L_ST) st_tokens[L.idx] = hh * ww;
+                else if (L.kind == L_DOWN) { hh /= 2; ww /= 2; }
+                else if (L.kind == L_UP) { hh *= 2; ww *= 2; }
+            }
+        };
+        for (auto& ls : m->in_blocks) visit(ls);
+        visit(m->mid);
+        for (auto& ls : m->out_blocks) visit(ls);
+    }
     for (auto& s : m->st) {
         const int C = s.C;
+        const int Ntok = st_tokens[sti++];
         // attn2 K/V of the text context (attention.py:122-143)
         {
             GemmEpilogue e = epi_qkv(s, nullptr, 0, s.c2_k, ctx_len, s.c2_vt, 128, ctx_len, 1);
@@ -1147,7 +1218,8 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
         {
             Lin kv = s.f_qkv;
             kv.w = s.f_qkv.w + (size_t)C * C; kv.N = 2 * C;
-            GemmEpilogue e = epi_qkv(s, nullptr, 0, s.fg_k, mo, s.fg_vt, 32, mo, 1);
+            // rows [Ntok, Ntok + mo) of the block's own K / V^T buffers (never touched by the per-step QKV projections)
+            GemmEpilogue e = epi_qkv(s, nullptr, 0, s.kb + (size_t)Ntok * s.heads * s.dpad, s.rows_k, s.vtb + Ntok, s.rows_k, mo, 1);
             RC(r.gemm(1, mo, 2 * C, {GemmSrc{h2, C, C, 1}}, kv, e));
         }
         // relation K/V (attention.py:348-349)
@@ -1158,13 +1230,17 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
     return 0;
 }
 
-int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, float alpha_scale, float* eps_out,
-                     void* stream) {
+int ltt_unet_forward(ltt_model* m, const float* x, const float* timesteps, int B, int H, int W, float alpha_scale,
+                     float* eps_out, void* stream) {
     if (!m) return -1;
     LTT_CUDA_OK(cudaSetDevice(m->device));
     if (!m->finalized || m->B == 0) {
         set_error("ltt_unet_forward: call ltt_finalize and ltt_set_conditioning first");
         return -8;
+    }
+    if (B != m->B || H != m->H || W != m->W) {
+        set_error("ltt_unet_forward: x is [%d,*,%d,%d] but the cached conditioning is for [%d,*,%d,%d]", B, H, W, m->B, m->H, m->W);
+        return -1;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const ltt_unet_config& c = m->cfg;
@@ -1278,12 +1354,19 @@ int64_t ltt_launch_count(const ltt_model* m) { return m ? m->launches : 0; }
 
 int ltt_profile_enable(ltt_model* m, int on) {
     if (!m) return -1;
+    if (on == 2 && m->prof_mode == 2) {      // keep the instrumented graphs, restart the replay counts
+        for (auto& kv : m->graphs) kv.second.replays = 0;
+        return 0;
+    }
+    LTT_CUDA_OK(cudaDeviceSynchronize());
+    if (m->prof_mode == 2) drop_graphs(m);   // instrumented graphs reference the events destroyed below
     for (auto& r : m->prof) {
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
     m->prof.clear();
-    m->prof_on = on != 0;
+    m->prof_mode = on;
+    m->prof_on = on == 1;
     return 0;
 }
 
@@ -1294,9 +1377,18 @@ int ltt_profile_report(ltt_model* m, int cls, double* ms, double* flops, double*
     int64_t n = 0;
     for (auto& r : m->prof) {
         if (r.cls != cls) continue;
+        double w = 1.0;
+        if (r.in_graph) {
+            auto it = m->graphs.find(r.gkey);
+            if (it == m->graphs.end() || it->second.replays == 0) continue;
+            w = (double)it->second.replays;
+        }
         float e = 0;
-        if (cudaEventElapsedTime(&e, r.e0, r.e1) != cudaSuccess) continue;
-        t += e; f += r.flops; b += r.bytes; ++n;
+        if (cudaEventElapsedTime(&e, r.e0, r.e1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        t += w * e; f += w * r.flops; b += w * r.bytes; n += (int64_t)w;
     }
     if (ms) *ms = t;
     if (flops) *flops = f;

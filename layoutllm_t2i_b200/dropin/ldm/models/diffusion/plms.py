@@ -34,7 +34,8 @@ class PLMSSampler(object):
         # The reference rebuilds these tables on every sample() call; they only depend on (steps, discretisation) and
         # the diffusion's alphas_cumprod, and every rebuild costs ~10 host<->device copies that drain the stream (the GPU
         # would idle between images).  Same inputs -> keep the tables of the previous call.
-        key = (int(ddim_num_steps), ddim_discretize, float(ddim_eta), self.diffusion.alphas_cumprod.data_ptr())
+        acp_ = self.diffusion.alphas_cumprod
+        key = (int(ddim_num_steps), ddim_discretize, float(ddim_eta), acp_.data_ptr(), acp_._version)
         if getattr(self, "_sched_key", None) == key:
             return
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
@@ -114,8 +115,14 @@ class PLMSSampler(object):
         if alphas is not None and any(a == 0 for a in alphas) and model.first_conv_restorable \
                 and not getattr(model, "_sd_conv_active", False):
             sd_conv = model.sd_first_conv()
+        if alphas is None:
+            # no gate schedule: the reference never calls set_alpha_scale and every step runs with whatever `.scale` the
+            # fuser modules currently hold (plms.py:79-87)
+            alphas_lib = [model.fuser_scale()] * len(self.ddim_timesteps)
+        else:
+            alphas_lib = alphas
         a_host, a_prev_host, s1m_host = self._host_tabs
-        out = eng.plms_sample(x, self.ddim_timesteps, a_host, a_prev_host, s1m_host, alphas, guidance if use_cfg else 1.0,
+        out = eng.plms_sample(x, self.ddim_timesteps, a_host, a_prev_host, s1m_host, alphas_lib, guidance if use_cfg else 1.0,
                               sd_conv)
         # leave the module tree in the state the reference loop would (last gate value, permanent first-conv swap)
         if alphas is not None:

@@ -26,7 +26,7 @@ class TimestepEmbedSequential(nn.Sequential):
 
 
 class Upsample(nn.Module):
-    """nearest x2 + conv3x3 (reference :57-85) -> library: conv kernel with /2 input indexing."""
+    """nearest x2 + conv3x3 (reference :57-85) -> library: nearest-x2 copy kernel + the implicit-GEMM conv."""
 
     def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
         super().__init__()
@@ -149,7 +149,13 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ engine plumbing
     def _mark_stale(self, *a, **k):
+        # load_state_dict: the checkpoint's input_blocks.0.0 overwrites a swapped first conv, as in the reference
         self._engine_stale = True
+        self._sd_conv_active = False
+
+    def _param_version(self):
+        # in-place edits (optimizer step, EMA swap, p.data.copy_) bump the tensors' version counters
+        return sum(p._version for p in self.parameters())
 
     def _apply(self, fn, *a, **k):      # .to() / .cuda() / .half(): device copies change -> re-upload lazily
         self._engine_stale = True
@@ -176,12 +182,16 @@ class UNetModel(nn.Module):
         if self._engine is None:
             self._engine = Engine(dict(self.engine_config(), max_objs=max_objs), dev)
             self._engine_stale = True
-        if self._engine_stale:
+        version = self._param_version()
+        if self._engine_stale or version != getattr(self, "_engine_version", None):
             self._engine.load_state_dict(self.state_dict())
             self._engine.finalize()
             if self._sd_conv is not None and getattr(self, "_sd_conv_active", False):
                 self._engine.set_first_conv(*self._sd_conv)
+            else:
+                self._engine.clear_first_conv()
             self._engine_stale = False
+            self._engine_version = version
             self._cond_key = None
         return self._engine
 
@@ -233,6 +243,7 @@ class UNetModel(nn.Module):
         self.first_conv_type = "SD"
         if self._engine is not None and not self._engine_stale:
             self._engine.set_first_conv(w, b)
+            self._engine_version = self._param_version()     # the in-place copy above is already in the engine
 
     def restore_first_conv_from_GLIGEN(self):
         raise NotImplementedError("not implemented in the reference either (openaimodel.py:410-411)")

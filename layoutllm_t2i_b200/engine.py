@@ -77,6 +77,10 @@ class Engine:
         w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         L.check(self._lib.ltt_set_first_conv(self._h, L.ptr(w), L.ptr(b), 0 if w.is_cuda else 1), "ltt_set_first_conv")
 
+    def clear_first_conv(self) -> None:
+        """Back to the checkpoint's own input_blocks.0.0 (what a later model.load_state_dict does in the reference)."""
+        L.check(self._lib.ltt_clear_first_conv(self._h), "ltt_clear_first_conv")
+
     # ------------------------------------------------------------------ per-image conditioning
     def set_conditioning(self, context: torch.Tensor, relations: torch.Tensor, grounding: Optional[dict],
                          H: int, W: int, n_grounded: Optional[int] = None) -> None:
@@ -107,11 +111,14 @@ class Engine:
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, alpha_scale: float = 1.0) -> torch.Tensor:
         """UNetModel.forward (reference openaimodel.py:413-459) on the cached conditioning -> eps [B,4,H,W] fp32."""
         xx = _f32c(x, self.device)
-        tt = _f32c(timesteps, self.device)
+        tt = _f32c(timesteps, self.device).reshape(-1)
+        if xx.dim() != 4 or xx.shape[1] != self.cfg["in_channels"] or tt.numel() != xx.shape[0]:
+            raise L.LttError(f"Engine.forward: x {tuple(xx.shape)} / timesteps {tuple(tt.shape)} do not form a "
+                             f"[B,{self.cfg['in_channels']},H,W] batch with one timestep per sample")
         out = torch.empty(xx.shape[0], self.cfg["out_channels"], xx.shape[2], xx.shape[3], device=self.device)
-        with torch.cuda.device(self.device):
-            L.check(self._lib.ltt_unet_forward(self._h, L.ptr(xx), L.ptr(tt), float(alpha_scale), L.ptr(out),
-                                               L.stream_ptr()), "ltt_unet_forward")
+        with torch.cuda.device(self.device):      # the library checks (B, H, W) against the cached conditioning
+            L.check(self._lib.ltt_unet_forward(self._h, L.ptr(xx), L.ptr(tt), xx.shape[0], xx.shape[2], xx.shape[3],
+                                               float(alpha_scale), L.ptr(out), L.stream_ptr()), "ltt_unet_forward")
         self._keep_fw = (xx, tt)
         return out
 

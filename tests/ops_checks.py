@@ -237,16 +237,129 @@ def check_rela_scatter_ln(B, nb, h, w, C, seed=0):
     L.check(L.lib().ltt_op_rela_scatter_ln(L.ptr(hid), L.ptr(x), L.ptr(feats), L.ptr(rects), nb, B, mo, h, w, C, L.ptr(out),
                                            L.ptr(g), L.ptr(bt), 1e-5, L.ptr(ln16), L.stream_ptr()), "rela_scatter_ln")
     torch.cuda.synchronize()
-    rc = rects.cpu()
+    from oracle import unet_oracle as uo
     add = torch.zeros(B, h, w, C, device=DEV)
-    for b in range(nb):
-        for i in range(mo):
-            t, bo, le, ri, ok = [int(v) for v in rc[b, i]]
-            if ok:
-                add[b, t:bo, le:ri] += feats[b, i].float() / mo
+    for b, row in enumerate(uo.box_pixel_rects(boxes.cpu(), masks.cpu(), h, w)[:nb]):      # the ORACLE's rectangles
+        for i, (t, bo, le, ri) in enumerate(row):
+            add[b, t:bo, le:ri] += feats[b, i].float() / mo
     ref = ((hid + add.view(B, h * w, C)) + x.float()) * 0.5
     ref_ln = F.layer_norm(ref, (C,), g, bt, 1e-5)
     return max(rel(out, ref), rel(ln16.float(), ref_ln) / 4)
+
+
+# ------------------------------------------------------------------------------------------------ small ops vs the oracle
+def check_rela_rects(B, h, w, seed=0):
+    """Integer box rectangles incl. the truncation and `break` rules against oracle.box_pixel_rects (bit-exact)."""
+    from oracle import unet_oracle as uo
+    mo = 30
+    g0 = torch.Generator().manual_seed(seed)
+    boxes = torch.zeros(B, mo, 4)
+    masks = torch.zeros(B, mo)
+    for b in range(B):
+        n = [0, 1, 7, 30][b % 4]
+        xy = torch.rand(n, 2, generator=g0) * 0.7
+        wh = torch.rand(n, 2, generator=g0) * 0.5 + 0.01
+        boxes[b, :n] = torch.cat([xy, xy + wh], dim=-1)        # may exceed 1.0: the min(x1*w, w) clamp
+        masks[b, :n] = 1
+        if n >= 7:
+            boxes[b, 3] = torch.tensor([0.5, 0.2, 0.5 + 1e-4, 0.9])   # degenerate (l == r): ends the scan for this sample
+    rects = torch.zeros(B, mo, 5, device=DEV, dtype=torch.int32)
+    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes.to(DEV)), L.ptr(masks.to(DEV)), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
+    torch.cuda.synchronize()
+    ref = uo.box_pixel_rects(boxes, masks, h, w)
+    got = rects.cpu()
+    bad = 0
+    for b in range(B):
+        for i in range(mo):
+            ok = int(got[b, i, 4])
+            if i < len(ref[b]):
+                bad += (ok != 1) or (tuple(int(v) for v in got[b, i, :4]) != tuple(ref[b][i]))
+            else:
+                bad += ok != 0
+    return float(bad)
+
+
+def check_rela_pool(B, h, w, C, seed=0):
+    """Per-box mean pool of the (materialised fp32) LN3 output against torch slicing on the oracle's rectangles."""
+    from oracle import unet_oracle as uo
+    mo = 30
+    g0 = torch.Generator().manual_seed(seed)
+    boxes = torch.zeros(B, mo, 4)
+    masks = torch.zeros(B, mo)
+    for b in range(B):
+        n = 3 + 4 * b
+        xy = torch.rand(n, 2, generator=g0) * 0.6
+        wh = torch.rand(n, 2, generator=g0) * 0.4 + 0.05
+        boxes[b, :n] = torch.cat([xy, (xy + wh).clamp(max=1.0)], dim=-1)
+        masks[b, :n] = 1
+    rects = torch.zeros(B, mo, 5, device=DEV, dtype=torch.int32)
+    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes.to(DEV)), L.ptr(masks.to(DEV)), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
+    hid = rn(B, h * w, C, seed=seed + 1) * 2 + 0.3
+    feats = torch.full((B, mo, C), 9.0, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_rela_pool(L.ptr(hid), L.ptr(rects), B, mo, h, w, C, L.ptr(feats), L.stream_ptr()), "rela_pool")
+    ref = torch.zeros(B, mo, C, device=DEV)
+    hv = hid.view(B, h, w, C)
+    for b, row in enumerate(uo.box_pixel_rects(boxes, masks, h, w)):
+        for i, (t, bo, le, ri) in enumerate(row):
+            ref[b, i] = hv[b, t:bo, le:ri].reshape(-1, C).mean(dim=0)
+    return rel(feats.float(), ref)
+
+
+def check_posnet_input(rows, seed=0):
+    """PositionNet input rows [emb*m + (1-m)*null | fourier(box)*m + (1-m)*null] against the oracle (fp16 rounding only)."""
+    from oracle import unet_oracle as uo
+    boxes = torch.rand(rows, 4, generator=torch.Generator().manual_seed(seed)).to(DEV)
+    masks = (torch.arange(rows) % 3 != 2).float().to(DEV)
+    emb = rn(rows, 768, seed=seed + 1)
+    ntxt, npos = rn(768, seed=seed + 2, scale=0.05), rn(64, seed=seed + 3, scale=0.05)
+    out = torch.empty(rows, 832, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_posnet_input(L.ptr(boxes), L.ptr(masks), L.ptr(emb), L.ptr(ntxt), L.ptr(npos), rows, 768, 8,
+                                        L.ptr(out), L.stream_ptr()), "posnet_input")
+    m = masks[:, None]
+    ref = torch.cat([emb * m + (1 - m) * ntxt, uo.fourier_embed(boxes.cpu(), 8).to(DEV) * m + (1 - m) * npos], dim=-1)
+    return rel(out.float(), ref.half().float())
+
+
+def check_timestep_embedding(dim, seed=0):
+    """[cos | sin] timestep embedding of every PLMS timestep (1 .. 981) against the oracle, rounded to fp16."""
+    from oracle import unet_oracle as uo
+    t = torch.arange(1, 1000, 20, dtype=torch.float32, device=DEV)
+    out = torch.empty(t.numel(), dim, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_timestep_embedding(L.ptr(t), t.numel(), dim, L.ptr(out), L.stream_ptr()), "timestep_embedding")
+    return rel(out.float(), uo.timestep_embedding(t.cpu(), dim).half().float().to(DEV))
+
+
+def check_plms_update(mode, use_cfg=True, seed=0, n=2 * 4 * 64 * 64):
+    """CFG combine + Euler / Adams-Bashforth + x_prev against the reference's expressions (plms.py:116-161) evaluated by
+    torch on fp16 eps tensors, which is what those lines compute under autocast (x and the schedule scalars are fp32)."""
+    h = lambda s: rn(n, seed=seed + s).half()
+    e_c, e_u, o1, o2, o3, ef = h(0), h(1), h(2), h(3), h(4), h(5)
+    x = rn(n, seed=seed + 6)
+    a_t, a_prev, guidance = 0.41, 0.47, 7.5
+    s1m = math.sqrt(1 - a_t)
+    f32 = lambda t: t.float().contiguous()
+    e_t_out, x_out = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L.check(L.lib().ltt_op_plms_update(L.ptr(f32(e_c)), L.ptr(f32(e_u)), guidance, int(use_cfg), mode, L.ptr(x), L.ptr(e_t_out),
+                                       L.ptr(f32(ef)), L.ptr(f32(o1)), L.ptr(f32(o2)), L.ptr(f32(o3)), a_t, a_prev, s1m,
+                                       L.ptr(x_out), n, L.stream_ptr()), "plms_update")
+    e = e_u + guidance * (e_c - e_u) if use_cfg else e_c             # fp16 arithmetic, as under autocast
+    if mode == 0:
+        ep = e
+    elif mode == 1:
+        ep = (ef + e) / 2
+    elif mode == 2:
+        ep = (3 * e - o1) / 2
+    elif mode == 3:
+        ep = (23 * e - 16 * o1 + 5 * o2) / 12
+    else:
+        ep = (55 * e - 59 * o1 + 37 * o2 - 9 * o3) / 24
+    at, ap, sq = (torch.full((1,), v, device=DEV) for v in (a_t, a_prev, s1m))
+    pred_x0 = (x - sq * ep) / at.sqrt()
+    ref = ap.sqrt() * pred_x0 + (1. - ap).sqrt() * ep
+    err = rel(x_out, ref)
+    if mode != 1:
+        err = max(err, rel(e_t_out, e.float()))
+    return err
 
 
 ALL = [
@@ -307,4 +420,18 @@ ALL = [
     ("layernorm f16 4096x320", check_layernorm, dict(M=4096, C=320, dtype=torch.float16), 1e-4),
     ("layernorm f32 1000x1280", check_layernorm, dict(M=1000, C=1280, dtype=torch.float32), 1e-4),
     ("layernorm f16 90x64", check_layernorm, dict(M=90, C=64, dtype=torch.float16), 1e-4),
+    ("rela rects 8x64x64 vs oracle (truncation, clamp, break rule)", check_rela_rects, dict(B=8, h=64, w=64), 0.5),
+    ("rela rects 4x24x16 vs oracle", check_rela_rects, dict(B=4, h=24, w=16, seed=3), 0.5),
+    ("rela rects 5x8x8 vs oracle", check_rela_rects, dict(B=5, h=8, w=8, seed=5), 0.5),
+    ("rela pool 2x64x64 C=320 vs oracle rectangles", check_rela_pool, dict(B=2, h=64, w=64, C=320), 1e-3),
+    ("rela pool 3x8x8 C=1280 vs oracle rectangles", check_rela_pool, dict(B=3, h=8, w=8, C=1280), 1e-3),
+    ("PositionNet input rows (Fourier + null mixing) vs oracle", check_posnet_input, dict(rows=90), 1e-3),
+    ("timestep embedding dim 320, all PLMS timesteps vs oracle", check_timestep_embedding, dict(dim=320), 1e-3),
+    ("timestep embedding dim 64 vs oracle", check_timestep_embedding, dict(dim=64), 1e-3),
+    ("plms update mode 0 (Euler predictor) vs reference expressions", check_plms_update, dict(mode=0), 1e-6),
+    ("plms update mode 1 (e' = (e_t + e_next)/2)", check_plms_update, dict(mode=1), 1e-6),
+    ("plms update mode 2 (AB2)", check_plms_update, dict(mode=2), 1e-6),
+    ("plms update mode 3 (AB3)", check_plms_update, dict(mode=3), 1e-6),
+    ("plms update mode 4 (AB4)", check_plms_update, dict(mode=4), 1e-6),
+    ("plms update mode 4 without CFG", check_plms_update, dict(mode=4, use_cfg=False), 1e-6),
 ]

@@ -1,0 +1,210 @@
+"""Parity against the UNMODIFIED reference modules (oracle/_ref, staged by oracle/make_ref.py) on the GPU.
+
+The "reference fp16 output" of BASELINE.json:north_star is the reference's own UNetModel / PLMSSampler with fp32 weights
+under ``torch.autocast('cuda', torch.float16)``.  These checks compare, on identical seeded
+noise / text-embedding / box inputs:
+  * the oracle port (oracle/unet_oracle.py) with the reference, fp32 and autocast -- pins the port on CUDA;
+  * the sm_100a engine (through the C-ABI) with the reference under autocast, at BASELINE configs 1-4;
+  * the reference with ITSELF under settings that do not change its arithmetic specification (batch composition, cuBLAS
+    reduced-precision reduction, cuDNN autotuning): the fp16 noise floor any second implementation sits on;
+  * a teacher-forced 50-step PLMS trace (reference sampler drives, the engine re-evaluates every recorded x_t).
+Used by tests/test_reference_gpu.py and tools/gpu_parity_steps.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import model_checks as mc
+from oracle import ref_loader as rl
+from oracle import unet_oracle as uo
+
+DEV = "cuda"
+rel = mc.rel
+_REF = {}
+
+
+def reference_for(cfg: dict, seed: int):
+    """(reference UNetModel on the GPU, its state_dict on the host) -- cached; same weights as model_checks.engine_for."""
+    key = (repr(sorted((k, repr(v)) for k, v in cfg.items())), seed)
+    if key not in _REF:
+        e, sd = mc.engine_for(cfg, seed)
+        _REF[key] = (rl.build_unet(cfg, sd, DEV), sd)
+    return _REF[key]
+
+
+def synth(B, H, W, n_boxes, seed=4321, degenerate=False, distinct=False):
+    syn = uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=n_boxes, seed=seed)
+    if distinct:      # per-sample prompts / relations (train_rl.py batches, GLIGEN/interface.py:479-540)
+        g = torch.Generator().manual_seed(seed + 99)
+        syn["context"] = torch.randn(B, 77, 768, generator=g)
+        syn["relations"][:, :3] = torch.randn(B, 3, 768, generator=g)
+    if degenerate and n_boxes >= 2:
+        syn["grounding"]["boxes"][B - 1, 1] = torch.tensor([0.30, 0.2, 0.3001, 0.9])
+    return mc.to_dev(syn)
+
+
+def check_port_vs_reference(cfg, seed, B, H, W, n_boxes, t, scale, autocast):
+    """oracle port vs the reference modules on CUDA (max over cond / uncond)."""
+    ref, sd = reference_for(cfg, seed)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = synth(B, H, W, n_boxes, degenerate=True)
+    worst = 0.0
+    for cond in (True, False):
+        r = rl.unet_eps(ref, syn, t, scale, cond, autocast)
+        o = mc.oracle_eps(sd_dev, cfg, syn, t, scale, cond, autocast)
+        worst = max(worst, rel(o, r))
+    return worst
+
+
+def engine_vs_reference(cfg, seed, B, H, W, n_boxes, t, scale, autocast=True, distinct=False, degenerate=False):
+    """(cond err, uncond err) of the engine's [cond ; uncond] evaluation against the reference."""
+    e, sd = mc.engine_for(cfg, seed)
+    ref, _ = reference_for(cfg, seed)
+    syn = synth(B, H, W, n_boxes, distinct=distinct, degenerate=degenerate)
+    ec, eu = mc.engine_eps_pair(e, syn, t, scale, H, W)
+    rc = rl.unet_eps(ref, syn, t, scale, True, autocast)
+    ru = rl.unet_eps(ref, syn, t, scale, False, autocast)
+    return rel(ec, rc), rel(eu, ru)
+
+
+def check_engine_vs_reference(**kw):
+    return max(engine_vs_reference(**kw))
+
+
+def reference_noise(cfg, seed, H, W, n_boxes, t, scale):
+    """rel-L2 between two autocast-fp16 runs of the REFERENCE on the same sample under settings that leave its
+    arithmetic specification unchanged.  Returns {variant: rel-L2 vs the plain run}."""
+    ref, _ = reference_for(cfg, seed)
+    syn1 = synth(1, H, W, n_boxes)
+    base = rl.unet_eps(ref, syn1, t, scale, True, True)
+    out = {}
+    # (a) the same sample evaluated as row 0 of a batch of two different samples (other GEMM shapes -> other kernels)
+    syn2 = synth(2, H, W, n_boxes, distinct=True)
+    for k in ("x", "context", "uc", "relations"):
+        syn2[k][0] = syn1[k][0]
+    for k in ("boxes", "masks", "positive_embeddings"):
+        syn2["grounding"][k][0] = syn1["grounding"][k][0]
+    syn2["x"][1] = torch.randn_like(syn2["x"][1])
+    out["batched_with_another_sample"] = rel(rl.unet_eps(ref, syn2, t, scale, True, True)[:1], base)
+    # (b) cuBLAS fp16 reduced-precision reductions off (PyTorch default: on)
+    flag = torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction
+    torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction = not flag
+    try:
+        out["cublas_reduced_precision_reduction_toggled"] = rel(rl.unet_eps(ref, syn1, t, scale, True, True), base)
+    finally:
+        torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction = flag
+    # (c) cuDNN autotuning, which the reference's set_seed() turns on (txt2img.py:57)
+    bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = not bench
+    try:
+        out["cudnn_benchmark_toggled"] = rel(rl.unet_eps(ref, syn1, t, scale, True, True), base)
+    finally:
+        torch.backends.cudnn.benchmark = bench
+    # (d) determinism control: the very same call again
+    out["same_call_again"] = rel(rl.unet_eps(ref, syn1, t, scale, True, True), base)
+    # context: distance of the reference's fp16 run from its own fp32 run
+    out["fp16_vs_fp32_reference"] = rel(base, rl.unet_eps(ref, syn1, t, scale, True, False))
+    return out
+
+
+def check_engine_within_reference_noise(cfg, seed, H, W, n_boxes, t, scale, factor=1.1):
+    """err(engine, reference fp16) / (factor * noise floor): < 1 passes.  Noise floor = the reference against itself
+    when the sample is merely batched with another one."""
+    noise = reference_noise(cfg, seed, H, W, n_boxes, t, scale)
+    err = check_engine_vs_reference(cfg=cfg, seed=seed, B=1, H=H, W=W, n_boxes=n_boxes, t=t, scale=scale)
+    floor = noise["batched_with_another_sample"]
+    print(f"engine vs reference fp16: {err:.3e}; reference vs itself: {noise}")
+    return err / (factor * floor)
+
+
+# ------------------------------------------------------------------------------------------------ teacher-forced PLMS
+def reference_trace(cfg, seed, B, H, W, n_boxes, S=50, guidance=7.5, autocast=True, sd_first_conv=True):
+    """Run the reference PLMSSampler.sample (plms.py:59-108) on the reference UNet and record every evaluation."""
+    ref, _ = reference_for(cfg, seed)
+    syn = synth(B, H, W, n_boxes, seed=555)
+    rec = rl.Recorder(ref)
+    sampler = rl.build_sampler(rec, DEV)
+    inp = rl.model_inputs(ref, syn, 0, True)
+    inp["x"], inp["timesteps"] = syn["x"].clone(), None
+    gliv = {k: v.detach().clone() for k, v in ref.input_blocks[0][0].state_dict().items()}
+    ctx = torch.autocast("cuda", dtype=torch.float16) if autocast else torch.autocast("cuda", enabled=False)
+    with ctx:
+        out = sampler.sample(S=S, shape=tuple(syn["x"].shape), input=inp, uc=syn["uc"], guidance_scale=guidance)
+    sdw = {k: v.detach().clone() for k, v in ref.input_blocks[0][0].state_dict().items()}
+    # undo the permanent first-conv swap so the cached reference model stays the GLIGEN one
+    ref.input_blocks[0][0].load_state_dict(gliv)
+    if hasattr(ref, "GLIGEN_first_conv_state_dict"):
+        del ref.GLIGEN_first_conv_state_dict
+    return syn, rec.calls, out.float(), sdw, sampler
+
+
+def teacher_forced_table(cfg, seed, B, H, W, n_boxes, S=50, guidance=7.5):
+    """Per-evaluation rel-L2 of the engine's eps (cond, uncond) and of the CFG-combined eps on the reference's own x_t."""
+    syn, calls, ref_final, sdw, sampler = reference_trace(cfg, seed, B, H, W, n_boxes, S, guidance)
+    e, sd = mc.engine_for(cfg, seed, "trace")
+    ctx, relations = mc.cfg_batch(syn, B)
+    e.set_conditioning(ctx, relations, syn["grounding"], H, W)
+    rows = []
+    swapped = False
+    for i in range(0, len(calls), 2):
+        c, u = calls[i], calls[i + 1]
+        assert c["cond"] and not u["cond"] and c["t"] == u["t"]
+        if c["scale"] == 0.0 and not swapped:
+            e.set_first_conv(sdw["weight"], sdw["bias"])
+            swapped = True
+        x2 = torch.cat([c["x"], c["x"]]).float()
+        tt = torch.full((2 * B,), float(c["t"]), device=DEV)
+        out = e.forward(x2, tt, c["scale"])
+        ec, eu = out[:B], out[B:]
+        cfg_e = eu + guidance * (ec - eu)
+        cfg_r = u["eps"] + guidance * (c["eps"] - u["eps"])
+        rows.append(dict(eval=i // 2, t=c["t"], gate=c["scale"], first_conv="SD" if swapped else "GLIGEN",
+                         eps_cond=rel(ec, c["eps"]), eps_uncond=rel(eu, u["eps"]), eps_cfg=rel(cfg_e, cfg_r)))
+    # free-running: the engine's own 50-step loop from the same noise
+    e2, _ = mc.engine_for(cfg, seed, "trace_free")
+    e2.set_conditioning(ctx, relations, syn["grounding"], H, W)
+    tabs = (sampler.ddim_timesteps, sampler.ddim_alphas.cpu().numpy(), np.asarray(sampler.ddim_alphas_prev),
+            sampler.ddim_sqrt_one_minus_alphas.cpu().numpy() if torch.is_tensor(sampler.ddim_sqrt_one_minus_alphas)
+            else np.asarray(sampler.ddim_sqrt_one_minus_alphas))
+    ours = e2.plms_sample(syn["x"], tabs[0], tabs[1], tabs[2], tabs[3], rl.alpha_generator(S), guidance,
+                          (sdw["weight"], sdw["bias"]))
+    return rows, rel(ours, ref_final), ref_final, ours
+
+
+def check_teacher_forced(cfg, seed, B, H, W, n_boxes, S, guidance=7.5):
+    rows, free, _, _ = teacher_forced_table(cfg, seed, B, H, W, n_boxes, S, guidance)
+    worst = max(max(r["eps_cond"], r["eps_uncond"]) for r in rows)
+    print(f"teacher-forced {len(rows)} evaluations: worst per-evaluation eps rel-L2 {worst:.3e}; free-running final latent {free:.3e}")
+    return worst
+
+
+FULL = mc.FULL
+TINY = mc.TINY
+
+ALL = [
+    ("oracle port vs reference modules, tiny, fp32 CUDA", check_port_vs_reference,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, autocast=False), 1e-5),
+    ("oracle port vs reference modules, tiny, autocast fp16", check_port_vs_reference,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, autocast=True), 3e-3),
+    ("oracle port vs reference modules, full 64x64, fp32 CUDA", check_port_vs_reference,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=6, t=481, scale=1.0, autocast=False), 1e-5),
+    ("engine vs REFERENCE fp16, tiny, degenerate box", check_engine_vs_reference,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, degenerate=True), 3e-3),
+    ("engine vs REFERENCE fp16, full 64x64 B=1 2 boxes (config 1/2)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=2, t=981, scale=1.0), 3e-3),
+    ("engine vs REFERENCE fp32, full 64x64 B=1 2 boxes (config 1)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=2, t=981, scale=1.0, autocast=False), 5e-3),
+    ("engine within the reference's own fp16 noise floor, full 64x64", check_engine_within_reference_noise,
+     dict(cfg=FULL, seed=0, H=64, W=64, n_boxes=6, t=481, scale=1.0), 1.0),
+    ("engine vs REFERENCE fp16, full 64x64 B=8 1 box, per-sample prompts (config 3)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=8, H=64, W=64, n_boxes=1, t=601, scale=1.0, distinct=True), 3e-3),
+    ("engine vs REFERENCE fp16, full 64x64 B=8 30 boxes (config 3)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=8, H=64, W=64, n_boxes=30, t=601, scale=1.0, distinct=True), 3e-3),
+    ("engine vs REFERENCE fp16, full 96x96 B=4 6 boxes, gate 1 (config 4)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=4, H=96, W=96, n_boxes=6, t=801, scale=1.0), 3e-3),
+    ("engine vs REFERENCE fp16, full 96x96 B=4 6 boxes, gate 0 (config 4)", check_engine_vs_reference,
+     dict(cfg=FULL, seed=0, B=4, H=96, W=96, n_boxes=6, t=201, scale=0.0), 3e-3),
+    ("teacher-forced 50-step PLMS vs REFERENCE sampler, full 64x64 B=1 6 boxes (config 2)", check_teacher_forced,
+     dict(cfg=FULL, seed=0, B=1, H=64, W=64, n_boxes=6, S=50), 3e-3),
+]
