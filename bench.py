@@ -13,7 +13,7 @@ read back to the host.  Weights are random-init tensors of the LayoutLLM-T2I arc
 N > 1: every rank samples its own batch slice (no data-path collective) and the final latents are all-gathered once
 per step over NCCL; weak scaling (per-GPU batch fixed) unless --global-batch is given.
 
-`--impl reference`: the reference algorithm's CPU path (oracle port of the reference's PyTorch modules, fp32, all
+`--impl reference`: the reference's own UNetModel (byte-identical copies under oracle/_ref; fp32 torch CPU, all
 host threads) on a bounded sample of the same workload: each step = one [cond, uncond] UNet evaluation pair at the
 workload's size; images/sec = 1 / (51 pairs x t_pair).
 """
@@ -167,39 +167,58 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
-def cpu_pair_seconds(sd_cpu, inputs, H, W, scale, n_threads):
-    """One [cond, uncond] UNet evaluation pair of the oracle port on the host (fp32, all threads)."""
-    from oracle import unet_oracle as uo
+def reference_kind():
+    """"reference": the reference's own UNetModel from the byte-identical copies under oracle/_ref (oracle/make_ref.py);
+    "port": the oracle restatement (only when the staged copy is missing)."""
+    from oracle import ref_loader as rl
+    return "reference" if rl.available() else "port"
+
+
+class ReferenceUNet:
+    """The reference algorithm on a device of choice: one [cond, uncond] evaluation pair = two separate B-sample forwards,
+    exactly as the reference sampler issues them (plms.py:116-122)."""
+
+    def __init__(self, sd_cpu, dev):
+        from oracle import ref_loader as rl
+        self.kind, self.dev = reference_kind(), dev
+        if self.kind == "reference":
+            self.model = rl.build_unet(UNET_CFG, sd_cpu, dev)
+        else:
+            self.sd = {k: v.to(dev) for k, v in sd_cpu.items()}
+
+    def pair(self, inputs, scale, autocast):
+        from oracle import ref_loader as rl
+        from oracle import unet_oracle as uo
+        inp = {k: v.to(self.dev) for k, v in inputs.items()}
+        syn = dict(x=inp["x"], context=inp["context"], uc=inp["uc"], relations=inp["relations"],
+                   grounding=dict(boxes=inp["boxes"], masks=inp["masks"], positive_embeddings=inp["text_embeddings"]))
+        if self.kind == "reference":
+            rl.unet_eps(self.model, syn, 981, scale, True, autocast)
+            rl.unet_eps(self.model, syn, 981, scale, False, autocast)
+            return
+        B = inp["x"].shape[0]
+        ts = torch.full((B,), 981, dtype=torch.long, device=self.dev)
+        cond = dict(x=inp["x"], timesteps=ts, context=inp["context"], relations=inp["relations"], grounding_input=syn["grounding"])
+        unc = dict(x=inp["x"], timesteps=ts, context=inp["uc"], relations=inp["relations"])
+        with torch.no_grad(), torch.autocast(torch.device(self.dev).type, dtype=torch.float16, enabled=autocast):
+            uo.unet_forward(self.sd, UNET_CFG, cond, scale=scale)
+            uo.unet_forward(self.sd, UNET_CFG, unc, scale=scale)
+
+
+def cpu_pair_seconds(ref, inputs, scale, n_threads):
+    """One [cond, uncond] UNet evaluation pair of the reference on the host (fp32, all threads)."""
     torch.set_num_threads(n_threads)
-    B = inputs["x"].shape[0]
-    ts = torch.full((B,), 981, dtype=torch.long)
-    grounding = dict(boxes=inputs["boxes"], masks=inputs["masks"], positive_embeddings=inputs["text_embeddings"])
-    cond = dict(x=inputs["x"], timesteps=ts, context=inputs["context"], relations=inputs["relations"], grounding_input=grounding)
-    unc = dict(x=inputs["x"], timesteps=ts, context=inputs["uc"], relations=inputs["relations"])
     t0 = time.perf_counter()
-    with torch.no_grad():
-        uo.unet_forward(sd_cpu, UNET_CFG, cond, scale=scale)
-        uo.unet_forward(sd_cpu, UNET_CFG, unc, scale=scale)
+    ref.pair(inputs, scale, autocast=False)
     return time.perf_counter() - t0
 
 
-def gpu_eager_pair_ms(sd_cpu, inputs, scale, dev, reps=3):
-    """One [cond, uncond] evaluation pair of the oracle port run as EAGER PyTorch on the GPU under fp16 autocast -- the
-    stand-in for the reference's own 1-GPU eager path (/root/reference cannot travel to the GPU box; the oracle issues
-    the same F.* sequence).  A reported baseline only: nothing of the product path runs here."""
-    from oracle import unet_oracle as uo
-    sd = {k: v.to(dev) for k, v in sd_cpu.items()}
-    inp = {k: v.to(dev) for k, v in inputs.items()}
-    B = inp["x"].shape[0]
-    ts = torch.full((B,), 981, dtype=torch.long, device=dev)
-    grounding = dict(boxes=inp["boxes"], masks=inp["masks"], positive_embeddings=inp["text_embeddings"])
-    cond = dict(x=inp["x"], timesteps=ts, context=inp["context"], relations=inp["relations"], grounding_input=grounding)
-    unc = dict(x=inp["x"], timesteps=ts, context=inp["uc"], relations=inp["relations"])
-
+def gpu_eager_pair_ms(ref, inputs, scale, reps=3):
+    """One [cond, uncond] evaluation pair of the reference's own modules as EAGER PyTorch on the GPU under fp16 autocast
+    (the reference's 1-GPU eager path of north_star's ">= 6x" target).  A reported baseline only: nothing of the
+    product path runs here."""
     def pair():
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            uo.unet_forward(sd, UNET_CFG, cond, scale=scale)
-            uo.unet_forward(sd, UNET_CFG, unc, scale=scale)
+        ref.pair(inputs, scale, autocast=True)
     for _ in range(2):
         pair()
     torch.cuda.synchronize()
@@ -236,22 +255,23 @@ def run_reference(args, rank):
     n_threads = os.cpu_count() or 1
     lat = args.size // 8
     inputs = synthetic_host_inputs(args.batch, lat, lat, args.boxes, 0, pin=False)
-    sd = cpu_state_dict()
+    ref = ReferenceUNet(cpu_state_dict(), "cpu")
     evals = args.plms_steps + 1
     for _ in range(args.warmup):
-        cpu_pair_seconds(sd, inputs, lat, lat, 1.0, n_threads)
+        cpu_pair_seconds(ref, inputs, 1.0, n_threads)
     t = []
     for i in range(args.steps):
-        t.append(cpu_pair_seconds(sd, inputs, lat, lat, 1.0 if i % 2 == 0 else 0.0, n_threads))
+        t.append(cpu_pair_seconds(ref, inputs, 1.0 if i % 2 == 0 else 0.0, n_threads))
     t_pair = float(np.mean(t))
     value = args.batch / (evals * t_pair)
-    sample = (f"each step = 1 [cond, uncond] UNet evaluation pair (2 of the {2 * evals} per image) at latent {lat}x{lat}, "
-              f"B={args.batch}, fp32, alternating gate 1/0; images/sec = B / ({evals} x mean pair time)")
+    sample = (f"each step = 1 [cond, uncond] UNet evaluation pair (2 of the {2 * evals} per image) of the reference's UNetModel "
+              f"({ref.kind}) at latent {lat}x{lat}, B={args.batch}, fp32 torch CPU, alternating gate 1/0; "
+              f"images/sec = B / ({evals} x mean pair time)")
     line = dict(metric="images_per_sec_512x512_50plms_6boxes" if args.size == 512 else f"images_per_sec_{args.size}",
                 impl="reference", value=value, unit="images/s", n_gpus=0, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * t_pair, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=workload_config(args, 1),
-                cpu_baseline=dict(value=value, unit="images/s", cores=n_threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=value, unit="images/s", cores=n_threads, kind=ref.kind, sample=sample),
                 e2e=dict(value=value, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -367,11 +387,22 @@ def main():
     clk = clocks.stop() if clocks else None
     finite = bool(torch.isfinite(z).all().item())
 
-    # per-kernel-class device times (CUDA events on the launch stream) over one more image batch of the same workload
-    eng.profile(True)
+    # per-kernel-class device times IN THE TIMED MODE: the class brackets are external event-record nodes inside the
+    # captured CUDA graphs of the evaluation (ltt_profile_enable(m, 2)); one image batch captures the instrumented
+    # graphs, a second one is measured.  Each bracket holds the times of its graph's last replay and is weighted by the
+    # graph's replay count, i.e. the per-class sums cover every evaluation of the image batch.
+    eng.profile(2)
     one_image_batch(devin, False)
+    eng.profile(2)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    one_image_batch(devin, False)
+    pe1.record()
+    torch.cuda.synchronize()
+    ms_instrumented = pe0.elapsed_time(pe1)
     prof = eng.profile_report()
-    eng.profile(False)
+    eng.profile(0)
 
     if rank == 0:
         pk = peaks()
@@ -382,25 +413,40 @@ def main():
         n1 = sum(1 for a in alpha_generator(S) if a != 0) + 1          # +1: the Euler predictor's second evaluation
         gf1, gf0 = GF_FWD.get(lat, GF_FWD[64])
         f_alg_tf = 2 * B * (n1 * gf1 + (evals - n1) * gf0) / 1e3          # cond + uncond, fuser elided at alpha = 0
-        dom = max(("gemm_tc", "attn_tc", "groupnorm", "layernorm"), key=lambda k: prof[k]["ms"])
-        d = prof[dom]
+        # The event nodes cost the programmatic-dependent-launch overlap between neighbouring kernels, so the
+        # instrumented image batch is a little slower than a timed one: every class time is scaled by
+        # (timed ms per step) / (instrumented ms per step), which makes the classes sum to <= ms_per_step.
+        step_ms = ms_dev / args.steps
+        k_scale = step_ms / ms_instrumented
+        cls = {k: dict(v, ms_raw=v["ms"], ms=v["ms"] * k_scale) for k, v in prof.items()}
+        named = ("gemm_tc", "attn_tc", "groupnorm", "layernorm")
+        other_ms = max(step_ms - sum(cls[k]["ms"] for k in named), 0.0)
+        dom = max(named, key=lambda k: cls[k]["ms"])
+        d = cls[dom]
         if dom in ("gemm_tc", "attn_tc"):
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             roof = dict(bound="tensor", kernel=dom, achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None)
         else:
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], traffic=None)
-        try:      # DRAM bytes per launch of the class, from the committed ncu pass over the same workload (profiles/)
-            roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))["per_launch_bytes"].get(dom)
-            roof["traffic_note"] = "dram__bytes_read+write per launch, class average over one evaluation (profiles/r01_dram_traffic.json)"
+        try:      # DRAM bytes per launch of the class, from the committed ncu pass of THIS build over the same workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+            roof["traffic"] = tr["per_launch_bytes"].get(dom)
+            roof["traffic_note"] = tr.get("note", "dram__bytes_read+write per launch, class average over one evaluation pair")
         except Exception:  # noqa: BLE001
             pass
         roof.update(peak_source=pk["source"], launches=d["launches"], avg_launch_us=1e3 * d["ms"] / max(d["launches"], 1),
-                    share_of_unet_time=d["ms"] / max(prof["forward"]["ms"], 1e-9),
-                    classes={k: dict(ms=round(v["ms"], 3), launches=v["launches"],
-                                     tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else None))
-                             for k, v in prof.items()},
-                    note="per-class CUDA-event times from one extra instrumented image batch after the timed region")
+                    alg_bytes_per_launch=d["bytes"] / max(d["launches"], 1), alg_flops_per_launch=d["flops"] / max(d["launches"], 1),
+                    share_of_step=d["ms"] / step_ms,
+                    classes=dict({k: dict(ms=round(v["ms"], 3), ms_instrumented=round(v["ms_raw"], 3), launches=v["launches"],
+                                          alg_tflop=round(v["flops"] / 1e12, 3), alg_gbytes=round(v["bytes"] / 1e9, 3),
+                                          tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else None))
+                                  for k, v in cls.items() if k in named},
+                                 other=dict(ms=round(other_ms, 3))),
+                    ms_per_step=round(step_ms, 3), ms_per_step_instrumented=round(ms_instrumented, 3),
+                    note="class times: external CUDA-event nodes inside the replayed graphs of one more image batch of the same "
+                         "workload (last replay x replay count per graph), scaled by ms_per_step / ms_per_step_instrumented; "
+                         "classes + other = ms_per_step")
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         line = dict(metric="images_per_sec_512x512_50plms_6boxes" if (args.size == 512 and S == 50 and args.boxes == 6) else
                            f"images_per_sec_{args.size}x{args.size}_{S}plms_{args.boxes}boxes",
@@ -418,20 +464,26 @@ def main():
             n_threads = os.cpu_count() or 1
             sd = cpu_state_dict()
             hin = {k: v.clone() for k, v in synthetic_host_inputs(B, lat, lat, args.boxes, 0, pin=False).items()}
-            tp = [cpu_pair_seconds(sd, hin, lat, lat, 1.0, n_threads) for _ in range(args.cpu_baseline_pairs)]
-            try:      # the same port as eager fp16-autocast PyTorch on this GPU (context for the ">= 6x eager GPU" target)
-                ms1 = gpu_eager_pair_ms(sd, hin, 1.0, dev)
-                ms0 = gpu_eager_pair_ms(sd, hin, 0.0, dev)
+            ref = ReferenceUNet(sd, "cpu")
+            tp = [cpu_pair_seconds(ref, hin, 1.0, n_threads) for _ in range(args.cpu_baseline_pairs)]
+            line["cpu_baseline"] = dict(value=B / (evals * float(np.mean(tp))), unit="images/s", cores=n_threads, kind=ref.kind,
+                                        sample=f"{len(tp)} [cond, uncond] UNet evaluation pair(s) of the reference's UNetModel ({ref.kind}; fp32, "
+                                               f"torch CPU, {n_threads} threads) at latent {lat}x{lat}, B={B}; extrapolated x{evals} pairs per image")
+            try:      # the same modules as eager fp16-autocast PyTorch on this GPU (context for the ">= 6x eager GPU" target)
+                if ref.kind == "reference":
+                    ref.model.to(dev)
+                    ref.dev = dev
+                else:
+                    ref = ReferenceUNet(sd, dev)
+                ms1 = gpu_eager_pair_ms(ref, hin, 1.0)
+                ms0 = gpu_eager_pair_ms(ref, hin, 0.0)
                 line["reference_gpu_eager"] = dict(
-                    value=B / ((n1 * ms1 + (evals - n1) * ms0) / 1e3), unit="images/s", kind="port", dtype="fp16 autocast",
+                    value=B / ((n1 * ms1 + (evals - n1) * ms0) / 1e3), unit="images/s", kind=ref.kind, dtype="fp16 autocast",
                     ms_per_pair=dict(gate1=ms1, gate0=ms0),
-                    sample=f"3 [cond, uncond] evaluation pairs per gate value of the oracle port as eager PyTorch on the same GPU "
-                           f"(two separate B={B} forwards per pair, as the reference's sampler does); extrapolated to {evals} pairs per image")
+                    sample=f"3 [cond, uncond] evaluation pairs per gate value of the reference's UNetModel ({ref.kind}) as eager PyTorch on the "
+                           f"same GPU (two separate B={B} forwards per pair, as the reference's sampler does); extrapolated to {evals} pairs per image")
             except Exception as ex:  # noqa: BLE001
                 line["reference_gpu_eager"] = dict(unavailable=repr(ex)[:200])
-            line["cpu_baseline"] = dict(value=B / (evals * float(np.mean(tp))), unit="images/s", cores=n_threads, kind="port",
-                                        sample=f"{len(tp)} [cond, uncond] UNet evaluation pair(s) of the oracle port (fp32, torch CPU, "
-                                               f"{n_threads} threads) at latent {lat}x{lat}, B={B}; extrapolated x{evals} pairs per image")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -142,8 +142,10 @@ class Engine:
 
     PROFILE_CLASSES = ("gemm_tc", "attn_tc", "groupnorm", "layernorm", "forward")
 
-    def profile(self, on: bool) -> None:
-        L.check(self._lib.ltt_profile_enable(self._h, int(on)), "ltt_profile_enable")
+    def profile(self, mode) -> None:
+        """0 / False: off.  1 / True: eager launches, every class launch bracketed by CUDA events.  2: the brackets are
+        event-record nodes inside the replayed CUDA graphs (calling it again with 2 restarts the replay counts)."""
+        L.check(self._lib.ltt_profile_enable(self._h, int(mode)), "ltt_profile_enable")
 
     def profile_report(self) -> dict:
         """{class: {ms, flops, bytes, launches}} of the launches since profile(True) (CUDA events on the launch stream)."""

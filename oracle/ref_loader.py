@@ -42,9 +42,14 @@ def reference_tree():
     sys.modules.update(_REF_MODULES)
     saved_path = list(sys.path)
     sys.path[:] = [REF_GLIGEN] + [p for p in saved_path if not _ours(p)]
+    # the drop-in import hook (layoutllm_t2i_b200/dropin/_ltt_dropin_hook.py) would serve its own modules: park it
+    hooks = [f for f in sys.meta_path if type(f).__name__ == "DropinFinder"]
+    for f in hooks:
+        sys.meta_path.remove(f)
     try:
         yield
     finally:
+        sys.meta_path[:0] = hooks
         for k in [k for k in sys.modules if k.split(".")[0] in _PKGS]:
             _REF_MODULES[k] = sys.modules.pop(k)
         sys.modules.update(saved)

@@ -1,5 +1,5 @@
 """bench.py --impl reference (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys.
-Runs the oracle port on a 16x16 latent so the CPU suite stays fast."""
+Runs the reference UNetModel (oracle/_ref when staged, else the oracle port) on a 16x16 latent so the CPU suite stays fast."""
 import json
 import os
 import subprocess
@@ -17,7 +17,7 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == dict(value=d["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert d["config"]["latent"] == 16
 
