@@ -106,6 +106,37 @@ int ltt_debug_tap_info(const ltt_model* m, int idx, char* name, int name_cap, in
                        int64_t* cols);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * VAE decode + image post-processing  (replaces ldm.models.autoencoder.AutoencoderKL.decode, autoencoder.py:40-44 ->
+ * ldm.modules.diffusionmodules.model.Decoder.forward, model.py:538-568; and the callers' clamp / *255 / uint8 / HWC
+ * conversion, txt2img.py:320-323, GLIGEN/interface.py:541-545)
+ * -------------------------------------------------------------------------------------------------------------- */
+typedef struct ltt_vae ltt_vae;
+
+/* AutoencoderKL.__init__ (autoencoder.py:17-30) / Decoder.__init__ (model.py:462-536) hyper-parameters
+ * (GLIGEN/configs/coco2014.yaml:33-52); attn_resolutions must be empty (only the mid attention block exists). */
+typedef struct {
+    int ch, out_ch;
+    int n_levels;
+    int ch_mult[8];
+    int num_res_blocks;
+    int z_channels, embed_dim;
+    float scale_factor;
+} ltt_vae_config;
+
+int ltt_vae_create(const ltt_vae_config* cfg, int device, ltt_vae** out);
+void ltt_vae_destroy(ltt_vae* v);
+/* autoencoder.load_state_dict (txt2img.py:107): reference key names ("decoder.up.3.block.0.conv1.weight",
+ * "post_quant_conv.bias", ...), fp32 device or host pointers; encoder.* / quant_conv.* keys are not needed. */
+int ltt_vae_load_param(ltt_vae* v, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
+int ltt_vae_finalize(ltt_vae* v);
+/* decode(z): z [B, z_channels, h, w] fp32 NCHW latents (as PLMSSampler.sample returns them).  Outputs (either may be
+ * NULL): img_f32 [B, out_ch, 8h, 8w] fp32 NCHW = the tensor AutoencoderKL.decode returns (fp16-rounded values, as under
+ * autocast); img_u8 [B, 8h, 8w, out_ch] uint8 = uint8((clamp(img, -1, 1) * 0.5 + 0.5) * 255), the HWC image the callers
+ * hand to PIL -- fused into the last convolution, ready for ONE pinned device-to-host copy.  h * w % 64 == 0. */
+int ltt_vae_decode(ltt_vae* v, const float* z, int B, int h, int w, float* img_f32, uint8_t* img_u8, void* stream);
+int64_t ltt_vae_launch_count(const ltt_vae* v);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Operator-level API (the same kernels, exposed one by one for parity tests and profiling)
  * -------------------------------------------------------------------------------------------------------------- */
 

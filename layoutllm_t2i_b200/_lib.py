@@ -25,6 +25,11 @@ class UNetConfig(C.Structure):
                 ("fourier_freqs", C.c_int), ("max_objs", C.c_int)]
 
 
+class VaeConfig(C.Structure):
+    _fields_ = [("ch", C.c_int), ("out_ch", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8),
+                ("num_res_blocks", C.c_int), ("z_channels", C.c_int), ("embed_dim", C.c_int), ("scale_factor", C.c_float)]
+
+
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); mirrors include/ltt_b200.h one to one
@@ -47,6 +52,12 @@ _SIGS = {
     "ltt_debug_set_taps": (_i, [_vp, _vp, _i64]),
     "ltt_debug_tap_count": (_i, [_vp]),
     "ltt_debug_tap_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ltt_vae_create": (_i, [C.POINTER(VaeConfig), _i, C.POINTER(_vp)]),
+    "ltt_vae_destroy": (None, [_vp]),
+    "ltt_vae_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "ltt_vae_finalize": (_i, [_vp]),
+    "ltt_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ltt_vae_launch_count": (_i64, [_vp]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
     "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),
     "ltt_op_pack_conv3x3": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -92,8 +92,12 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int c0, int ld0, 
         for (int k = 0; k < 4; ++k) {
             const float2 m = mr[b * 32 + (c + 2 * k) / cpg];     // cpg is even: a channel pair never straddles groups
             const float2 v = __half22float2(h[k]);
-            float a = r16f((v.x - m.x) * m.y * g[2 * k] + bt[2 * k]);
-            float d = r16f((v.y - m.x) * m.y * g[2 * k + 1] + bt[2 * k + 1]);
+            float a = (v.x - m.x) * m.y * g[2 * k] + bt[2 * k];
+            float d = (v.y - m.x) * m.y * g[2 * k + 1] + bt[2 * k + 1];
+            if (silu != 2) {      // 2: swish on the fp32 normalised value (VAE: GroupNorm output stays fp32 under autocast)
+                a = r16f(a);
+                d = r16f(d);
+            }
             if (silu) {
                 a = siluf(a);
                 d = siluf(d);
@@ -291,10 +295,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 f = __half22float2(h[k]);
-                    __half2 y = __floats2half2_rn(fmaf(f.x, g[2 * k], bt[2 * k]), fmaf(f.y, g[2 * k + 1], bt[2 * k + 1]));
-                    if (silu) {
-                        const float2 yf = __half22float2(y);
-                        y = __floats2half2_rn(siluf(yf.x), siluf(yf.y));
+                    const float y0 = fmaf(f.x, g[2 * k], bt[2 * k]), y1 = fmaf(f.y, g[2 * k + 1], bt[2 * k + 1]);
+                    __half2 y;
+                    if (silu == 2) {      // swish on the fp32 value, one rounding (VAE blocks under autocast)
+                        y = __floats2half2_rn(siluf(y0), siluf(y1));
+                    } else {
+                        y = __floats2half2_rn(y0, y1);
+                        if (silu) {       // GroupNorm32 casts back to fp16 before the SiLU (UNet ResBlock)
+                            const float2 yf = __half22float2(y);
+                            y = __floats2half2_rn(siluf(yf.x), siluf(yf.y));
+                        }
                     }
                     o[k] = y;
                 }

@@ -81,3 +81,25 @@ def test_reference_sampler_records_102_evaluations():
     sampler.sample(S=50, shape=(1, 4, 8, 8), input=inp, uc=torch.zeros(1, 77, 768), guidance_scale=7.5)
     assert len(rec.calls) == 102
     assert sum(1 for c in rec.calls if c["scale"] == 1.0) == 32 and rec.calls[0]["t"] == 981 and rec.calls[-1]["t"] == 1
+
+
+@needs_ref
+def test_dropin_autoencoder_has_the_reference_state_dict_grammar():
+    """`autoencoder.load_state_dict(saved_ckpt["autoencoder"])` is strict in the callers (txt2img.py:107)."""
+    import contextlib
+    import io
+    dropin = os.path.join(ROOT, "layoutllm_t2i_b200", "dropin")
+    if dropin not in sys.path:
+        sys.path.insert(0, dropin)
+    from ldm.models.autoencoder import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    with rl.reference_tree(), contextlib.redirect_stdout(io.StringIO()):
+        from ldm.models.autoencoder import AutoencoderKL as Ref
+        ref = Ref(dd, 4, 0.18215)
+    ours = AutoencoderKL(dd, 4, 0.18215)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs) == list(os_) and all(rs[k].shape == os_[k].shape for k in rs)
+    ours.load_state_dict(rs)          # strict
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        ours.decode(torch.zeros(1, 4, 8, 8))
