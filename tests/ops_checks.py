@@ -337,11 +337,12 @@ def check_plms_update(mode, use_cfg=True, seed=0, n=2 * 4 * 64 * 64):
     x = rn(n, seed=seed + 6)
     a_t, a_prev, guidance = 0.41, 0.47, 7.5
     s1m = math.sqrt(1 - a_t)
-    f32 = lambda t: t.float().contiguous()
+    c32, u32, f32_, p1, p2, p3 = (t.float().contiguous() for t in (e_c, e_u, ef, o1, o2, o3))    # kept alive across the call
     e_t_out, x_out = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
-    L.check(L.lib().ltt_op_plms_update(L.ptr(f32(e_c)), L.ptr(f32(e_u)), guidance, int(use_cfg), mode, L.ptr(x), L.ptr(e_t_out),
-                                       L.ptr(f32(ef)), L.ptr(f32(o1)), L.ptr(f32(o2)), L.ptr(f32(o3)), a_t, a_prev, s1m,
+    L.check(L.lib().ltt_op_plms_update(L.ptr(c32), L.ptr(u32), guidance, int(use_cfg), mode, L.ptr(x), L.ptr(e_t_out),
+                                       L.ptr(f32_), L.ptr(p1), L.ptr(p2), L.ptr(p3), a_t, a_prev, s1m,
                                        L.ptr(x_out), n, L.stream_ptr()), "plms_update")
+    torch.cuda.synchronize()
     e = e_u + guidance * (e_c - e_u) if use_cfg else e_c             # fp16 arithmetic, as under autocast
     if mode == 0:
         ep = e

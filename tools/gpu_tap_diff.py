@@ -1,4 +1,8 @@
-"""Per-layer error table: engine vs autocast-fp16 oracle vs fp32 oracle (all on the GPU).
+"""Per-layer error table: engine vs autocast-fp16 oracle vs fp32 oracle (all on the GPU), next to the noise floor of the
+fp16 computation itself: `ac~/ac` = the SAME autocast computation with the input latent perturbed below fp16 resolution
+(x * (1 + 5e-5 n): about a tenth of the latent values round to the neighbouring fp16 number at the first conv), and `*/w16` =
+distance to the fp32 computation with fp16-ROUNDED weights (weight rounding is common to every fp16 implementation, so
+this isolates the activation-rounding noise).
 usage: python tools/gpu_tap_diff.py [tiny|full] [scale] [t]"""
 import os
 import sys
@@ -24,26 +28,34 @@ x2 = torch.cat([syn["x"], syn["x"]])
 out, taps = e.forward_with_taps(x2, torch.full((2 * B,), float(t), device="cuda"), scale)
 
 
-def oracle(autocast):
+def oracle(autocast, sdd=None, xin=None):
+    sdd = sd_dev if sdd is None else sdd
+    xin = syn["x"] if xin is None else xin
     res = []
     for cond in (True, False):
         tp = {}
-        inp = dict(x=syn["x"], timesteps=torch.full((B,), t, dtype=torch.long, device="cuda"),
+        inp = dict(x=xin, timesteps=torch.full((B,), t, dtype=torch.long, device="cuda"),
                    relations=syn["relations"], context=syn["context"] if cond else syn["uc"])
         if cond:
             inp["grounding_input"] = syn["grounding"]
         with torch.no_grad():
             if autocast:
                 with torch.autocast("cuda", dtype=torch.float16):
-                    o = uo.unet_forward(sd_dev, cfg, inp, scale=scale, taps=tp)
+                    o = uo.unet_forward(sdd, cfg, inp, scale=scale, taps=tp)
             else:
-                o = uo.unet_forward(sd_dev, cfg, inp, scale=scale, taps=tp)
+                o = uo.unet_forward(sdd, cfg, inp, scale=scale, taps=tp)
         tp["eps"] = o
         res.append(tp)
     return res
 
 
 ac, f32 = oracle(True), oracle(False)
+# weights (and Linear / Conv biases) rounded to fp16 as autocast does at every call; norm parameters and gates stay fp32
+sd16 = {k: (v if ("norm" in k or "alpha" in k or k.endswith("layers.0.weight") or k.endswith("layers.0.bias") or k.startswith("out.0"))
+            else v.half().float()) for k, v in sd_dev.items()}
+w16 = oracle(False, sd16)
+xp = syn["x"] * (1 + 5e-5 * torch.randn(syn["x"].shape, generator=torch.Generator().manual_seed(1)).to("cuda"))
+acp = oracle(True, None, xp)
 
 
 def flat(v):
@@ -54,13 +66,16 @@ def flat(v):
     return v.reshape(-1, v.shape[-1])
 
 
-print(f"{'tap':46s} {'dtype(ac)':10s} {'eng/ac':>10s} {'eng/f32':>10s} {'ac/f32':>10s}")
-for name, v in taps.items():
+def both(r, name):
+    return torch.cat([flat(r[0][name]), flat(r[1][name])])
+
+
+print(f"{'tap':46s} {'dtype(ac)':10s} {'eng/ac':>10s} {'ac~/ac':>10s} {'eng/f32':>10s} {'ac/f32':>10s} {'eng/w16':>10s} {'ac/w16':>10s} {'w16/f32':>10s}")
+for name, v in list(taps.items()) + [("eps", out)]:
     if name not in ac[0]:
         continue
-    a = torch.cat([flat(ac[0][name]), flat(ac[1][name])])
-    f = torch.cat([flat(f32[0][name]), flat(f32[1][name])])
-    print(f"{name:46s} {str(ac[0][name].dtype)[6:]:10s} {mc.rel(v, a):10.2e} {mc.rel(v, f):10.2e} {mc.rel(a, f):10.2e}")
-a = torch.cat([ac[0]["eps"], ac[1]["eps"]]).float()
-f = torch.cat([f32[0]["eps"], f32[1]["eps"]]).float()
-print(f"{'eps':46s} {'':10s} {mc.rel(out, a):10.2e} {mc.rel(out, f):10.2e} {mc.rel(a, f):10.2e}")
+    if name == "eps":
+        v = v.float().permute(0, 2, 3, 1).reshape(-1, v.shape[1])
+    a, f, w, ap = both(ac, name), both(f32, name), both(w16, name), both(acp, name)
+    print(f"{name:46s} {str(ac[0][name].dtype)[6:]:10s} {mc.rel(v, a):10.2e} {mc.rel(ap, a):10.2e} {mc.rel(v, f):10.2e} {mc.rel(a, f):10.2e} "
+          f"{mc.rel(v, w):10.2e} {mc.rel(a, w):10.2e} {mc.rel(w, f):10.2e}")
