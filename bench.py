@@ -5,11 +5,13 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one complete image batch through the reference-facing API of the drop-in tree,
-`PLMSSampler.sample(S=50, shape, input, uc, guidance_scale=7.5)` on the drop-in `UNetModel` (102 UNet evaluations
-per image: 51 [cond ; uncond] pairs).  `value` times K steps with the conditioning tensors already in HBM; `e2e`
-times K more steps whose inputs start in pinned HOST memory (H2D inside the step) and whose final latents are
-read back to the host.  Weights are random-init tensors of the LayoutLLM-T2I architecture (no checkpoints offline).
+One "step" = one complete image batch through the reference-facing API of the drop-in tree, as the reference's
+generate_one_image does it (txt2img.py:302-324): `PLMSSampler.sample(S=50, shape, input, uc, guidance_scale=7.5)` on the
+drop-in `UNetModel` (102 UNet evaluations per image: 51 [cond ; uncond] pairs), then `AutoencoderKL.decode` of the latents
+with the uint8 / HWC image conversion fused in (the metric is sampler + decode; the sampler-only figure is
+reported beside it).  `value` times K steps with the conditioning tensors already in HBM and the images left in HBM;
+`e2e` times K more steps whose inputs start in pinned HOST memory (H2D inside the step) and whose uint8 images are read
+back to the host with one pinned copy.  Weights are random-init tensors of the LayoutLLM-T2I architecture (no checkpoints offline).
 N > 1: every rank samples its own batch slice (no data-path collective) and the final latents are all-gathered once
 per step over NCCL; weak scaling (per-GPU batch fixed) unless --global-batch is given.
 
@@ -38,6 +40,9 @@ UNET_CFG = dict(image_size=64, in_channels=4, out_channels=4, model_channels=320
                 fuser_type="gatedSA", grounding_in_dim=768, grounding_out_dim=768, fourier_freqs=8)
 # algorithmic FLOPs (2*MAC) of one UNet evaluation at B=1, from FlopCounterMode on the reference module
 GF_FWD = {64: (1147.69, 814.14), 96: (3249.49, 2158.99)}        # latent size -> (alpha=1, alpha=0 with the fuser elided)
+GF_VAE_DECODE_64 = 2514.5                                       # AutoencoderKL.decode of one 64x64 latent, ~ (lat/64)^2
+VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                    num_res_blocks=2, attn_resolutions=[], dropout=0.0)          # GLIGEN/configs/coco2014.yaml:33-52
 GUIDANCE = 7.5
 ALPHA_TYPE = (0.3, 0.0, 0.7)
 
@@ -123,6 +128,15 @@ def build_model(device):
     g2 = torch.Generator().manual_seed(5)       # stand-in for SD_input_conv_weight_bias.pth (ships with the reference only)
     model.set_sd_first_conv(0.2 * torch.randn(320, 4, 3, 3, generator=g2), 0.02 * torch.randn(320, generator=g2))
     return model
+
+
+def build_vae(device):
+    """Drop-in AutoencoderKL (SD VAE geometry) with random-init weights on the device."""
+    from ldm.util import instantiate_from_config
+    torch.manual_seed(1)
+    vae = instantiate_from_config(dict(target="ldm.models.autoencoder.AutoencoderKL",
+                                       params=dict(ddconfig=VAE_DDCONFIG, embed_dim=4, scale_factor=0.18215)))
+    return vae.to(device).eval()
 
 
 class ClockSampler:
@@ -298,6 +312,7 @@ def main():
     ap.add_argument("--plms-steps", type=int, default=50)
     ap.add_argument("--boxes", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="sampler only (no VAE decode / image conversion in the step)")
     ap.add_argument("--cpu-baseline-pairs", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -336,13 +351,15 @@ def main():
 
     B, lat, S = args.batch, args.size // 8, args.plms_steps
     model = build_model(dev)
+    vae = None if args.no_decode else build_vae(dev)
     diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).to(dev)
     sampler = PLMSSampler(diffusion, model, alpha_generator_func=partial(alpha_generator, type=list(ALPHA_TYPE)),
                           set_alpha_scale=set_alpha_scale)
     host = synthetic_host_inputs(B, lat, lat, args.boxes, rank, pin=True)
     devin = {k: v.to(dev) for k, v in host.items()}
     from layoutllm_t2i_b200 import shard
-    out_host = torch.empty(B, 4, lat, lat).pin_memory()
+    out_host = torch.empty(B, 4, lat, lat).pin_memory() if vae is None else torch.empty(B, 8 * lat, 8 * lat, 3, dtype=torch.uint8).pin_memory()
+    decode_events = []
 
     def one_image_batch(src, from_host):
         t = {k: (v.to(dev, non_blocking=True) if from_host else v) for k, v in src.items()}
@@ -352,7 +369,16 @@ def main():
         z = sampler.sample(S=S, shape=(B, 4, lat, lat), input=inp, uc=t["uc"], guidance_scale=GUIDANCE)
         if world > 1:
             z_all = shard.gather_latents(z, B * world)    # the path's single collective: final latents over NVLink
-        if from_host:
+        if vae is not None:
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            if from_host:                                 # uint8 HWC images -> pinned host memory, one copy, then sync
+                vae.decode_to_uint8(z, out_host, sync=True)
+            else:
+                vae.engine().decode(z, images_u8=True)
+            d1.record()
+            decode_events.append((d0, d1))
+        elif from_host:
             out_host.copy_(z, non_blocking=True)
             torch.cuda.current_stream().synchronize()     # the caller holds the result on the host
         return z
@@ -380,9 +406,11 @@ def main():
         one_image_batch(devin, False)
     eng = model.engine(30)
     clocks = ClockSampler(local) if rank == 0 else None
-    l0 = eng.launch_count
+    l0 = eng.launch_count + (vae.engine().launch_count if vae is not None else 0)
+    decode_events.clear()
     ms_dev, z = timed(False, args.steps)
-    launches = eng.launch_count - l0
+    launches = eng.launch_count + (vae.engine().launch_count if vae is not None else 0) - l0
+    ms_decode = sum(a.elapsed_time(b) for a, b in decode_events)
     ms_e2e, z2 = timed(True, args.steps)
     clk = clocks.stop() if clocks else None
     finite = bool(torch.isfinite(z).all().item())
@@ -413,6 +441,8 @@ def main():
         n1 = sum(1 for a in alpha_generator(S) if a != 0) + 1          # +1: the Euler predictor's second evaluation
         gf1, gf0 = GF_FWD.get(lat, GF_FWD[64])
         f_alg_tf = 2 * B * (n1 * gf1 + (evals - n1) * gf0) / 1e3          # cond + uncond, fuser elided at alpha = 0
+        if vae is not None:
+            f_alg_tf += B * GF_VAE_DECODE_64 * (lat / 64.0) ** 2 / 1e3
         # The event nodes cost the programmatic-dependent-launch overlap between neighbouring kernels, so the
         # instrumented image batch is a little slower than a timed one: every class time is scaled by
         # (timed ms per step) / (instrumented ms per step), which makes the classes sum to <= ms_per_step.
@@ -454,8 +484,12 @@ def main():
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f16",
                     data="synthetic (seeded noise/text/box tensors, random-init weights of the LayoutLLM-T2I UNet)",
                     config=workload_config(args, world),
-                    e2e=dict(value=e2e_v, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=out_host.numel() * 4,
-                             ms_per_step=ms_e2e / args.steps),
+                    e2e=dict(value=e2e_v, unit="images/s", h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=out_host.numel() * out_host.element_size(), ms_per_step=ms_e2e / args.steps,
+                             result="uint8 HWC images" if vae is not None else "final latents (fp32)"),
+                    includes_vae_decode=vae is not None,
+                    sampler_only=dict(value=imgs / ((ms_dev - ms_decode) / 1e3), unit="images/s",
+                                      ms_per_step=(ms_dev - ms_decode) / args.steps, decode_ms_per_step=ms_decode / args.steps),
                     gpu_launches=int(launches), clocks=clk, roofline=roof,
                     step_tensor_roofline=dict(alg_tflop_per_step=f_alg_tf, achieved_tflops=f_alg_tf * args.steps / (ms_dev / 1e3),
                                               frac=f_alg_tf * args.steps / (ms_dev / 1e3) / pk["tflops"], peak=pk["tflops"]),

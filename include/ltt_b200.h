@@ -146,6 +146,14 @@ int64_t ltt_vae_launch_count(const ltt_vae* v);
 int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, const float* bias, int act,
                   const void* res, int res_dtype, int ldr, float gate, int has_gate, void* out, int out_dtype, int ldo,
                   void* stream);
+/* x = a . w1^T + b1 ; out2 = act(LayerNorm(x; gamma, beta, eps) . w2^T + b2)   (BasicTransformerBlock: `attn(norm(x))`,
+ * `ff(norm(x))`, attention.py:394-402) with the LayerNorm FOLDED into the second GEMM: the first GEMM's epilogue leaves
+ * per-row partial (sum, sum of squares), the second reads the raw fp16 rows x, uses w2 * gamma as weights and applies
+ * rstd * (acc - mean * s_n) + c_n in its epilogue -- no normalised tensor is ever written.  a [M,K1] fp16, w1 [C,K1]
+ * fp16, w2 [N,C] fp32 (packed inside), act2 0 or GEGLU; out1 [M,C] fp16, out2 [M, N or N/2] fp16. */
+int ltt_op_linear_ln_linear(const void* a16, int M, int K1, const void* w1_16, const float* b1, int C, const float* gamma,
+                            const float* beta, float eps, const float* w2_f32, const float* b2, int N, int act2, void* out1_16,
+                            void* out2_16, void* stream);
 /* [8C, K] fp32 GEGLU projection weight -> fp16 rows interleaved per 128-row tile (64 value rows, 64 gate rows) */
 int ltt_op_pack_geglu(const float* w, int rows, int K, void* out_f16, void* stream);
 /* OIHW fp32 3x3 conv weight [Cout, Cin, 3, 3] -> fp16 [Cout][tap][Cin] */

@@ -59,6 +59,7 @@ _SIGS = {
     "ltt_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ltt_vae_launch_count": (_i64, [_vp]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
+    "ltt_op_linear_ln_linear": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),
     "ltt_op_pack_conv3x3": (_i, [_vp, _i, _i, _vp, _vp]),
     "ltt_op_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),

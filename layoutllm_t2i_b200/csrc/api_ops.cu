@@ -46,6 +46,47 @@ int ltt_op_linear(const void* a, int M, int K, int lda, const void* w, int N, co
     return gemm_tc_launch(p, global_sms(), (cudaStream_t)stream);
 }
 
+// LayerNorm folded into the consumer GEMM (gemm_tc.cu), as the transformer blocks use it: out1 = a . w1^T + b1 with the
+// per-row partial statistics left by that GEMM's epilogue, then out2 = act(LayerNorm(out1) . w2^T + b2) computed from the RAW
+// out1 rows with w2 packed as W * gamma.  Scratch is allocated and freed inside (parity tests only).
+int ltt_op_linear_ln_linear(const void* a16, int M, int K1, const void* w1_16, const float* b1, int C, const float* gamma,
+                            const float* beta, float eps, const float* w2_f32, const float* b2, int N, int act2, void* out1_16,
+                            void* out2_16, void* stream) {
+    if (int rc = ensure_global_ws()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* stats = nullptr;
+    __half* w2p = nullptr;
+    float *sv = nullptr, *cv = nullptr;
+    LTT_CUDA_OK(cudaMalloc(&stats, (size_t)M * GEMM_STATS_LD * sizeof(float2)));
+    LTT_CUDA_OK(cudaMalloc(&w2p, (size_t)N * C * 2));
+    LTT_CUDA_OK(cudaMalloc(&sv, (size_t)N * 4));
+    LTT_CUDA_OK(cudaMalloc(&cv, (size_t)N * 4));
+    int rc = pack_rows_launch(w2_f32, N, C, w2p, 0, act2 == ACT_GEGLU ? 1 : 0, st, gamma);
+    if (!rc) rc = ln_fold_vectors_launch(w2_f32, gamma, beta, b2, N, C, sv, cv, st);
+    int slots = 0;
+    if (!rc) {
+        GemmProblem p{};
+        p.B = 1; p.H = 1; p.W = M; p.N = C; p.nsrc = 1;
+        p.src[0] = GemmSrc{(const __half*)a16, K1, K1, 1};
+        p.w = (const __half*)w1_16; p.Ktot = K1;
+        p.epi.bias = b1; p.epi.out = out1_16; p.epi.out_dtype = DT_F16; p.epi.ldo = C;
+        p.epi.stats_out = stats; p.epi.stats_ld = GEMM_STATS_LD;
+        rc = gemm_tc_launch(p, global_sms(), st, &slots);
+    }
+    if (!rc) {
+        GemmProblem p{};
+        p.B = 1; p.H = 1; p.W = M; p.N = N; p.nsrc = 1;
+        p.src[0] = GemmSrc{(const __half*)out1_16, C, C, 1};
+        p.w = w2p; p.Ktot = C;
+        p.epi.bias = cv; p.epi.act = act2; p.epi.out = out2_16; p.epi.out_dtype = DT_F16; p.epi.ldo = act2 == ACT_GEGLU ? N / 2 : N;
+        p.epi.ln_stats = stats; p.epi.ln_slots = slots; p.epi.ln_ld = GEMM_STATS_LD; p.epi.ln_K = C; p.epi.ln_s = sv; p.epi.ln_eps = eps;
+        rc = gemm_tc_launch(p, global_sms(), st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(stats); cudaFree(w2p); cudaFree(sv); cudaFree(cv);
+    return rc;
+}
+
 int ltt_op_pack_geglu(const float* w, int rows, int K, void* out_f16, void* stream) {
     return pack_rows_launch(w, rows, K, (__half*)out_f16, 0, 1, (cudaStream_t)stream);
 }
@@ -119,17 +160,17 @@ int ltt_op_rela_rects(const float* boxes, const float* masks, int B, int mo, int
     return rela_rects_launch(boxes, masks, B, mo, h, w, rects, (cudaStream_t)stream);
 }
 int ltt_op_rela_pool(const float* hid, const int* rects, int B, int mo, int h, int w, int C, void* feats16, void* stream) {
-    return rela_pool_launch(hid, nullptr, nullptr, nullptr, nullptr, rects, B, mo, h, w, C, (__half*)feats16, (cudaStream_t)stream);
+    return rela_pool_launch(hid, nullptr, RowStatSrc{}, nullptr, nullptr, rects, B, mo, h, w, C, (__half*)feats16, (cudaStream_t)stream);
 }
 int ltt_op_rela_scatter(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                         int mo, int h, int w, int C, float* out, void* stream) {
-    return rela_scatter_launch(hid, nullptr, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+    return rela_scatter_launch(hid, RowStatSrc{}, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
                                nullptr, nullptr, 0.f, nullptr, (cudaStream_t)stream);
 }
 int ltt_op_rela_scatter_ln(const float* hid, const void* x16, const void* feats16, const int* rects, int nb_feats, int B,
                            int mo, int h, int w, int C, float* out, const float* gamma, const float* beta, float eps,
                            void* ln16, void* stream) {
-    return rela_scatter_launch(hid, nullptr, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
+    return rela_scatter_launch(hid, RowStatSrc{}, nullptr, nullptr, (const __half*)x16, (const __half*)feats16, rects, nb_feats, B, mo, h, w, C, out,
                                gamma, beta, eps, (__half*)ln16, (cudaStream_t)stream);
 }
 int ltt_op_rela_fold(const void* wq16, const void* wo16, const void* kv16, int G, int nrel, int heads, int d, float scale,

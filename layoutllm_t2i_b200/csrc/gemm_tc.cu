@@ -58,7 +58,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES / 2;     // per CTA of a pair
     static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;           // BN floats
-    static constexpr int BAR_OFFSET = BIAS_OFFSET + BN * 4;
+    static constexpr int LNS_OFFSET = BIAS_OFFSET + BN * 4;            // BN floats: ln_s of this tile (LayerNorm fold)
+    static constexpr int BAR_OFFSET = LNS_OFFSET + BN * 4;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;              // + barriers/tmem slot + alignment slack
 };
 
@@ -85,6 +86,19 @@ struct RowInfo {
     int m;       // global row
     int b;       // batch element
     bool valid;
+};
+
+// running (sum, sum of squares) of the fp16 values a thread stored for its row (producer side of the LayerNorm fold)
+struct RowStats {
+    float s = 0.f, q = 0.f;
+    __device__ __forceinline__ void add(const __half2* h) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            s += f.x + f.y;
+            q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+        }
+    }
 };
 
 // Residual / time-embedding operands of one row for 16 consecutive output columns, fetched BEFORE the accumulator
@@ -124,7 +138,7 @@ __device__ __forceinline__ void fetch_operands(const GemmEpilogue& e, const RowI
 // output is rounded to fp16 before the next elementwise op.
 __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
                                                 const float (&g)[8], const float (&bv)[8], const float (&bg)[8],
-                                                const RowOperands& o, int j) {
+                                                const RowOperands& o, int j, RowStats& rs) {
     if (!ri.valid || n >= Nout) return;
     if (e.act == ACT_GEGLU) {
 #pragma unroll
@@ -185,15 +199,17 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
             v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
         }
     }
-    if (e.out_dtype == DT_F16) {
-        __half2 h[4];
+    __half2 h[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    if (e.stats_out) rs.add(h);
+    if (e.out_dtype == DT_F16) {
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
     } else {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
         op[0] = make_float4(v[0], v[1], v[2], v[3]);
         op[1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
     }
 }
 
@@ -203,7 +219,7 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
 enum : int { EK_GENERIC = 0, EK_F16 = 1, EK_GATE16 = 2, EK_GEGLU = 3, EK_QKV = 4, EK_RES32 = 5 };
 
 __host__ __device__ inline int epilogue_kind(const GemmEpilogue& e) {
-    if (e.out_mode == OUT_QKV) return (!e.bias && !e.act && !e.has_gate && !e.rowvec) ? EK_QKV : EK_GENERIC;
+    if (e.out_mode == OUT_QKV) return (!e.act && !e.has_gate && !e.rowvec) ? EK_QKV : EK_GENERIC;
     if (e.act == ACT_GEGLU) return (!e.res && !e.has_gate && !e.rowvec && e.out_dtype == DT_F16) ? EK_GEGLU : EK_GENERIC;
     if (e.act != ACT_NONE || e.rowvec) return EK_GENERIC;
     if (e.res && e.res_dtype == DT_F32) return e.has_gate ? EK_GENERIC : EK_RES32;
@@ -220,7 +236,7 @@ struct KindTag {
 template <int KIND>
 __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
                                            const float (&g)[8], const float* __restrict__ bs, const float* __restrict__ bsg,
-                                           const RowOperands& o, int j) {
+                                           const RowOperands& o, int j, RowStats& rs) {
     if constexpr (KIND == EK_GENERIC) {
         float bv[8], bg[8];
 #pragma unroll
@@ -228,7 +244,7 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
             bv[i] = bs[i];
             bg[i] = e.act == ACT_GEGLU ? bsg[i] : 0.f;
         }
-        epilogue_group8(e, ri, n, Nout, v, g, bv, bg, o, j);
+        epilogue_group8(e, ri, n, Nout, v, g, bv, bg, o, j, rs);
         return;
     } else {
         if (!ri.valid || n >= Nout) return;
@@ -257,7 +273,7 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
             }
         } else if constexpr (KIND == EK_QKV) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i] + bs[2 * i], v[2 * i + 1] + bs[2 * i + 1]);   // bias: 0 unless LN fold / conv bias
             const int which = n / e.C + e.qkv_base, c = n % e.C;
             const int t = ri.m - ri.b * e.tokens;
             if (which == 2) {
@@ -285,15 +301,18 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
                 y[2 * i] = f.x + rr[2 * i];
                 y[2 * i + 1] = f.y + rr[2 * i + 1];
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
             if (e.out_dtype == DT_F32) {
                 float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
                 op[0] = make_float4(y[0], y[1], y[2], y[3]);
                 op[1] = make_float4(y[4], y[5], y[6], y[7]);
+                if (e.stats_out) rs.add(h);
+                if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
                 return;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
         }
+        if (e.stats_out && (KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32)) rs.add(h);
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
     }
 }
@@ -309,6 +328,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* bias_s = reinterpret_cast<float*>(smem + SM::BIAS_OFFSET);
+    float* lns_s = reinterpret_cast<float*>(smem + SM::LNS_OFFSET);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;     // 2
@@ -529,9 +549,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     }
                 }
                 bias_s[c] = bvv;
+                if (e.ln_stats) {           // LayerNorm fold: ln_s is indexed like the bias
+                    float sv = 0.f;
+                    if (geglu) {
+                        const int half = c / ncols, cc = c % ncols;
+                        if (nbase + cc < Nout) sv = e.ln_s[half * Nout + nbase + cc];
+                    } else if (n0 + c < Nout) {
+                        sv = e.ln_s[n0 + c];
+                    }
+                    lns_s[c] = sv;
+                }
             }
             RowOperands opA;
             if (args.splits == 1) fetch_operands(e, ri, nbase + 16 * wg, Nout, opA);
+            // LayerNorm fold, consumer side: (mean, rstd) of this thread's row from the producer's partial sums -- fetched
+            // while the main loop of this unit is still running
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (e.ln_stats && ri.valid) {
+                const float2* sp = e.ln_stats + (size_t)ri.m * e.ln_ld;
+                if (e.ln_slots < 0) {
+                    const float2 t = sp[0];
+                    ln_mean = t.x;
+                    ln_rstd = t.y;
+                } else {
+                    float sm = 0.f, sq = 0.f;
+                    for (int i = 0; i < e.ln_slots; ++i) {      // fixed slot order: deterministic
+                        const float2 t = sp[i];
+                        sm += t.x;
+                        sq += t.y;
+                    }
+                    const float inv = 1.0f / (float)e.ln_K;
+                    ln_mean = sm * inv;
+                    ln_rstd = rsqrtf(fmaxf(sq * inv - ln_mean * ln_mean, 0.f) + e.ln_eps);
+                }
+            }
+            RowStats rstat;
             named_bar_sync(2, EPI_THREADS);
             const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -604,7 +656,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             }
                         }
                     }
-                    epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0);
+                    if (e.ln_stats) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v8[i] = ln_rstd * fmaf(-ln_mean, lns_s[c + i], v8[i]);
+                            if (geglu) g8[i] = ln_rstd * fmaf(-ln_mean, lns_s[ncols + c + i], g8[i]);
+                        }
+                    }
+                    epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0, rstat);
                 }
             } else {
                 // 16-column chunks: accumulators -> fused epilogue (specialised per epilogue kind) -> global
@@ -632,7 +691,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v8[i] = __uint_as_float(v[h * 8 + i]);
                                 g8[i] = gg ? __uint_as_float(g[h * 8 + i]) : 0.f;
                             }
-                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, opA, h);
+                            if ((KIND == EK_QKV || KIND == EK_GEGLU || KIND == EK_GENERIC) && e.ln_stats) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    v8[i] = ln_rstd * fmaf(-ln_mean, lns_s[c + h * 8 + i], v8[i]);
+                                    if (gg) g8[i] = ln_rstd * fmaf(-ln_mean, lns_s[ncols + c + h * 8 + i], g8[i]);
+                                }
+                            }
+                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, opA, h, rstat);
                         }
                     }
                 };
@@ -647,6 +713,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 tc_fence_before();
                 if (pair) mbar_arrive_remote(acc_empty_leader + (uint32_t)buf * 8u);
                 else mbar_arrive(&acc_empty[buf]);
+            }
+            if (e.stats_out && ri.valid) {
+                const int slot = ((tile % args.ntiles) * args.splits + z) * EPI_WGS + wg;
+                e.stats_out[(size_t)ri.m * e.stats_ld + slot] = make_float2(rstat.s, rstat.q);
             }
         }
     }
@@ -840,7 +910,7 @@ struct Variant {
     }
 };
 
-int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots) {
     GemmDeviceArgs a;
     memset(&a, 0, sizeof(a));
     a.B = p.B; a.H = p.H; a.W = p.W; a.N = p.N;
@@ -902,6 +972,8 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
         if (force_bn && bn != force_bn && !(geglu && force_bn % 128)) continue;
         const int nt = (p.N + bn - 1) / bn;
         const int ctas_c = mtiles * nt;
+        const bool want_stats = p.epi.stats_out != nullptr;
+        if (want_stats && nt * EPI_WGS > p.epi.stats_ld) continue;      // row-statistics slots of this tiling must fit
         const double it_cycles = std::max(2.0 * bn, (16384.0 + 128.0 * bn) / 75.0);
         const double epi_cycles = 600.0 + 6.0 * bn;
         if (pair_mode && mtiles >= 2 && (iters >= 10 || pair_mode == 2) && bn >= 128) {
@@ -942,6 +1014,7 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
                     default: mc = Variant<256, 4>::max_clusters(sp); break;
                 }
                 if (mc < ctas_c) continue;                         // all clusters of the launch must be co-resident
+                if (want_stats && nt * sp * EPI_WGS > p.epi.stats_ld) continue;
                 resident = mc * sp;
             }
             const int units = ctas_c * sp;
@@ -961,6 +1034,15 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     }
     const int ntiles = (p.N + BN - 1) / BN;
     const int ctas = mtiles * ntiles;
+    if (best >= 1e30) {
+        set_error("gemm: no tiling fits (N=%d, stats_ld=%d)", p.N, p.epi.stats_ld);
+        return -1;
+    }
+    if (p.epi.ln_stats && (!p.epi.ln_s || p.epi.ln_K <= 0 || (p.epi.ln_slots <= 0 && p.epi.ln_slots != -1))) {
+        set_error("gemm: incomplete LayerNorm-fold operands");
+        return -1;
+    }
+    if (stats_slots) *stats_slots = ntiles * S * EPI_WGS;
     a.mtiles = mtiles;
     a.ntiles = ntiles;
     {

@@ -83,6 +83,22 @@ struct GemmEpilogue {
     __half* vt = nullptr; // [B, C, pitch_v]
     int C = 0, dhead = 0, dpad = 0, rows_q = 0, rows_k = 0, pitch_v = 0, tokens = 0;  // tokens = rows per batch elem
     int qkv_base = 0;                 // first C-wide column block is q (0), k (1) or v (2)
+    // ---- LayerNorm folded into the CONSUMER GEMM (gemm_tc.cu, "LayerNorm fold").
+    // Producer side: every epilogue thread leaves the partial (sum, sum of squares) of the fp16 values it stored for its
+    // row in slot (n_tile * splits + k_rank) * EPI_WGS + warpgroup of stats_out[row * stats_ld + slot]; the launcher
+    // reports the number of slots used.  out16: additional fp16 copy of an fp32 output (the LayerNorm input of the
+    // fp32 residual stream reaches the consumer GEMM as fp16 rows), same pitch as `out`.
+    float2* stats_out = nullptr;
+    int stats_ld = 0;
+    __half* out16 = nullptr;
+    // Consumer side: A holds the RAW rows x, the packed weights are W' = W * gamma (column scale) and
+    //   y[m, n] = rstd_m * (acc[m, n] - mean_m * ln_s[n]) + bias[n],   ln_s[n] = sum_k W'[n, k],  bias[n] = b[n] + sum_k beta[k] W[n, k]
+    // with (mean, rstd) of row m over its ln_K columns from ln_slots partial sums (ln_slots > 0) or stored directly as
+    // (mean, rstd) (ln_slots == -1).
+    const float2* ln_stats = nullptr;
+    int ln_slots = 0, ln_ld = 0, ln_K = 0;
+    const float* ln_s = nullptr;
+    float ln_eps = 1e-5f;
 };
 
 struct GemmProblem {
@@ -97,7 +113,9 @@ struct GemmProblem {
 };
 
 // (split-K partial sums meet in distributed shared memory of a thread-block cluster: no global workspace)
-int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream);
+// stats_slots (optional): receives the number of statistics slots per row the launch writes when epi.stats_out is set.
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots = nullptr);
+constexpr int GEMM_STATS_LD = 128;      // slots per row every stats buffer provides (launches are tiled to fit)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused attention core:  O[b, i, h*d:(h+1)*d] = softmax_j(q_i . k_j * scale) v_j   (flash-style, S/O in TMEM)

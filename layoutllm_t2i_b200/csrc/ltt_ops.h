@@ -25,9 +25,16 @@ int timestep_embed_launch(const float* t, int B, int dim, __half* out, cudaStrea
 int posnet_input_launch(const float* boxes, const float* masks, const float* emb, const float* null_txt,
                         const float* null_pos, int rows, int in_dim, int nfreq, __half* out, cudaStream_t st);
 int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int h, int w, int* rects, cudaStream_t st);
-int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, const float* gamma, const float* beta,
+// row statistics for kernels that apply a LayerNorm on the fly: slots == -1: p[row * ld] = (mean, rstd); slots > 0: partial
+// (sum, sum of squares) over K columns in p[row * ld + 0 .. slots) (left by a GEMM epilogue, see gemm_tc.cu LayerNorm fold)
+struct RowStatSrc {
+    const float2* p = nullptr;
+    int ld = 1, slots = -1, K = 0;
+    float eps = 1e-5f;
+};
+int rela_pool_launch(const float* hid, const __half* x16, const RowStatSrc& stats, const float* gamma, const float* beta,
                      const int* rects, int B, int mo, int h, int w, int C, __half* feats, cudaStream_t st);
-int rela_scatter_launch(const float* hid, const float2* stats, const float* gamma3, const float* beta3, const __half* x,
+int rela_scatter_launch(const float* hid, const RowStatSrc& stats, const float* gamma3, const float* beta3, const __half* x,
                         const __half* feats, const int* rects, int nb_feats, int B, int mo, int h, int w, int C, float* out,
                         const float* gamma, const float* beta, float eps, __half* ln16, cudaStream_t st);
 int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
@@ -54,6 +61,9 @@ int fill_tvals_launch(const float* host_vals, int n, float* out, cudaStream_t st
 
 int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int Cs, __half* dst, int Kdst, int koff,
                      cudaStream_t st);
-int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, int geglu, cudaStream_t st);
+int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, int geglu, cudaStream_t st,
+                     const float* colscale = nullptr);
+int ln_fold_vectors_launch(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K, float* s_out,
+                           float* c_out, cudaStream_t st);
 
 }  // namespace ltt

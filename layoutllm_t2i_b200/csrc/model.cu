@@ -53,6 +53,11 @@ struct StW {
     Lin f_linear, f_qkv, f_out, f_ff1, f_ff2;
     Lin r_q, r_kv, r_out, r_ff1, r_ff2;
     float f_ta = 0, f_td = 0, r_ta = 0, r_td = 0;   // tanh(alpha)
+    // LayerNorm fold (gemm_tc.cu): the four projections that consume a LayerNorm of the token stream are packed as
+    // W * gamma and carry s[n] = sum_k W'[n,k] and c[n] = bias[n] + sum_k beta[k] W[n,k]; the norm itself is never launched
+    const float *a1_s = nullptr, *a1_c = nullptr, *fq_s = nullptr, *fq_c = nullptr, *ff1f_s = nullptr, *ff1f_c = nullptr,
+                *ff1_s = nullptr, *ff1_c = nullptr;
+    Lin f_kv_plain;                                 // fuser to_k / to_v without the fold (grounding tokens, per conditioning)
     // per-conditioning caches
     __half *c2_k = nullptr, *c2_vt = nullptr, *r_kvbuf = nullptr;
     // self-attention K [B, rows_k, heads*dpad] / V^T [B, C, rows_k] of THIS block: rows [0, N) are rewritten by every
@@ -147,6 +152,10 @@ struct ltt_model {
     cudaStream_t capture_stream = nullptr;
     bool use_graphs = true;
     bool rela_fused = true;           // LTT_RELA_UNFUSED=1: q-GEMM / attention / out-GEMM as separate launches (A/B checks)
+    bool ln_fold = true;              // LTT_NO_LNFOLD=1: LayerNorms of the token stream as separate launches (A/B checks)
+    float2* rstats[2] = {nullptr, nullptr};   // row-statistics slots [rows][GEMM_STATS_LD] written by GEMM epilogues (ping-pong)
+    __half* xh16 = nullptr;           // fp16 copy of the fp32 residual stream (LayerNorm-fold operand of the last feed-forward)
+    float2* cond_stats = nullptr;
     // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
     // prof_mode 1: eager launches, every class launch bracketed by events.  prof_mode 2: the brackets are external
     // event-record nodes INSIDE the captured CUDA graph of the evaluation (the mode the timed path runs in); a record then
@@ -229,6 +238,40 @@ static int pack_concat(ltt_model* m, const std::vector<std::string>& keys, Lin* 
     out->w = (__half*)p; out->N = N; out->K = K; out->bias = nullptr;
     return 0;
 }
+// LayerNorm-folded packing of one or more [Ni, K] matrices that consume LayerNorm(gamma, beta) of the same rows:
+// rows concatenated (GEGLU interleave for a single matrix), W' = W * gamma, plus the s / c vectors (original row order).
+static int pack_ln_fold(ltt_model* m, const std::vector<std::string>& wkeys, const char* bias_key, const Norm& nrm, int geglu,
+                        Lin* out, const float** s_out, const float** c_out) {
+    int N = 0, K = 0;
+    std::vector<const Param*> ps;
+    for (auto& k : wkeys) {
+        GETP(w, k)
+        ps.push_back(w);
+        N += (int)w->shape[0];
+        K = (int)(w->numel / w->shape[0]);
+    }
+    void *p, *sv, *cv;
+    RC(m->warena.alloc(&p, (size_t)N * K * 2));
+    RC(m->warena.alloc(&sv, (size_t)N * 4));
+    RC(m->warena.alloc(&cv, (size_t)N * 4));
+    const float* bias = nullptr;
+    if (bias_key) {
+        GETP(b, std::string(bias_key))
+        bias = b->dev;
+    }
+    int off = 0;
+    for (auto* w : ps) {
+        const int n = (int)w->shape[0];
+        RC(pack_rows_launch(w->dev, n, K, (__half*)p, off, geglu, 0, nrm.g));
+        RC(ln_fold_vectors_launch(w->dev, nrm.g, nrm.b, bias ? bias + off : nullptr, n, K, (float*)sv + off, (float*)cv + off, 0));
+        off += n;
+    }
+    for (auto& k : wkeys) m->packed_keys.push_back(k);
+    out->w = (__half*)p; out->N = N; out->K = K; out->bias = (const float*)cv;
+    *s_out = (const float*)sv; *c_out = (const float*)cv;
+    return 0;
+}
+
 static int scalar_tanh(ltt_model* m, const std::string& key, float* out) {
     GETP(a, key)
     float v = 0;
@@ -298,20 +341,34 @@ static int build_st(ltt_model* m, const std::string& p, int C) {
     RC(norm(m, t + ".norm1", &s.ln1));
     RC(norm(m, t + ".norm2", &s.ln2));
     RC(norm(m, t + ".norm3", &s.ln3));
-    RC(pack_concat(m, {t + ".attn1.to_q.weight", t + ".attn1.to_k.weight", t + ".attn1.to_v.weight"}, &s.a1_qkv));
+    if (m->ln_fold)
+        RC(pack_ln_fold(m, {t + ".attn1.to_q.weight", t + ".attn1.to_k.weight", t + ".attn1.to_v.weight"}, nullptr, s.ln1, 0,
+                        &s.a1_qkv, &s.a1_s, &s.a1_c));
+    else
+        RC(pack_concat(m, {t + ".attn1.to_q.weight", t + ".attn1.to_k.weight", t + ".attn1.to_v.weight"}, &s.a1_qkv));
     RC(lin(m, t + ".attn1.to_out.0", &s.a1_out));
     RC(lin(m, t + ".attn2.to_q", &s.a2_q, false));
     RC(pack_concat(m, {t + ".attn2.to_k.weight", t + ".attn2.to_v.weight"}, &s.a2_kv));
     RC(lin(m, t + ".attn2.to_out.0", &s.a2_out));
-    RC(lin(m, t + ".ff.net.0.proj", &s.ff1, true, 1));
+    if (m->ln_fold)
+        RC(pack_ln_fold(m, {t + ".ff.net.0.proj.weight"}, (t + ".ff.net.0.proj.bias").c_str(), s.ln3, 1, &s.ff1, &s.ff1_s, &s.ff1_c));
+    else
+        RC(lin(m, t + ".ff.net.0.proj", &s.ff1, true, 1));
     RC(lin(m, t + ".ff.net.2", &s.ff2));
     const std::string f = t + ".fuser";
     RC(lin(m, f + ".linear", &s.f_linear));
     RC(norm(m, f + ".norm1", &s.f_ln1));
     RC(norm(m, f + ".norm2", &s.f_ln2));
-    RC(pack_concat(m, {f + ".attn.to_q.weight", f + ".attn.to_k.weight", f + ".attn.to_v.weight"}, &s.f_qkv));
+    RC(pack_concat(m, {f + ".attn.to_k.weight", f + ".attn.to_v.weight"}, &s.f_kv_plain));
+    if (m->ln_fold) {
+        RC(pack_ln_fold(m, {f + ".attn.to_q.weight", f + ".attn.to_k.weight", f + ".attn.to_v.weight"}, nullptr, s.f_ln1, 0, &s.f_qkv,
+                        &s.fq_s, &s.fq_c));
+        RC(pack_ln_fold(m, {f + ".ff.net.0.proj.weight"}, (f + ".ff.net.0.proj.bias").c_str(), s.f_ln2, 1, &s.f_ff1, &s.ff1f_s, &s.ff1f_c));
+    } else {
+        RC(pack_concat(m, {f + ".attn.to_q.weight", f + ".attn.to_k.weight", f + ".attn.to_v.weight"}, &s.f_qkv));
+        RC(lin(m, f + ".ff.net.0.proj", &s.f_ff1, true, 1));
+    }
     RC(lin(m, f + ".attn.to_out.0", &s.f_out));
-    RC(lin(m, f + ".ff.net.0.proj", &s.f_ff1, true, 1));
     RC(lin(m, f + ".ff.net.2", &s.f_ff2));
     RC(scalar_tanh(m, f + ".alpha_attn", &s.f_ta));
     RC(scalar_tanh(m, f + ".alpha_dense", &s.f_td));
@@ -515,7 +572,8 @@ struct Run {
     ltt_model* m;
     cudaStream_t st;
     int B;
-    int gemm(int H, int W, int N, std::initializer_list<GemmSrc> srcs, const Lin& w, const GemmEpilogue& epi, int Bov = -1) {
+    int gemm(int H, int W, int N, std::initializer_list<GemmSrc> srcs, const Lin& w, const GemmEpilogue& epi, int Bov = -1,
+             int* stats_slots = nullptr) {
         GemmProblem p{};
         p.B = Bov > 0 ? Bov : B; p.H = H; p.W = W; p.N = N; p.nsrc = 0; p.Ktot = 0;
         for (auto& s : srcs) {
@@ -536,7 +594,7 @@ struct Run {
         ProfScope ps(m, st, PC_GEMM, 2.0 * Mrows * N * p.Ktot,
                      2.0 * (Mrows * p.Ktot / (srcs.begin()->taps == 9 ? 9.0 : 1.0) + (double)N * p.Ktot) +
                          Mrows * nout * (p.epi.out_dtype == DT_F32 ? 4.0 : 2.0));
-        return gemm_tc_launch(p, m->sms, st);
+        return gemm_tc_launch(p, m->sms, st, stats_slots);
     }
 };
 
@@ -623,57 +681,112 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     __half* qb = m->qbuf[s.d];
     __half* kb = s.kb;
     __half* vtb = s.vtb;
+    // LayerNorm fold: a GEMM whose output feeds a LayerNorm leaves per-row partial (sum, sum of squares) in a statistics
+    // buffer (`produce`); the projection that consumes the norm reads the raw rows and normalises in its epilogue (`consume`)
+    const bool fold = m->ln_fold;
+    int slots[2] = {0, 0};
+    auto produce = [&](GemmEpilogue& e, int which) {
+        if (fold) {
+            e.stats_out = m->rstats[which];
+            e.stats_ld = GEMM_STATS_LD;
+        }
+    };
+    auto consume = [&](GemmEpilogue& e, int which, const float* sv, const float* cv) {
+        e.ln_stats = m->rstats[which];
+        e.ln_slots = slots[which];
+        e.ln_ld = GEMM_STATS_LD;
+        e.ln_K = C;
+        e.ln_s = sv;
+        e.ln_eps = 1e-5f;
+        e.bias = cv;
+    };
     // GroupNorm (eps 1e-6) -> proj_in
     RC(groupnorm(m, st, x_in, C, nullptr, 0, B, N, s.gn, 1e-6f, 0, m->tnorm));
-    RC(r.gemm(H, W, C, {GemmSrc{m->tnorm, C, C, 1}}, s.proj_in, epi_out(m->xa, C)));
+    {
+        GemmEpilogue e = epi_out(m->xa, C);
+        produce(e, 0);
+        RC(r.gemm(H, W, C, {GemmSrc{m->tnorm, C, C, 1}}, s.proj_in, e, -1, &slots[0]));
+    }
     // attn1
-    RC(ln(m, st, m->xa, DT_F16, M, C, s.ln1, m->ln16, nullptr));
-    RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.a1_qkv, epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0)));
+    {
+        GemmEpilogue e = epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0);
+        const __half* a = m->xa;
+        if (fold) {
+            consume(e, 0, s.a1_s, s.a1_c);
+        } else {
+            RC(ln(m, st, m->xa, DT_F16, M, C, s.ln1, m->ln16, nullptr));
+            a = m->ln16;
+        }
+        RC(r.gemm(H, W, 3 * C, {GemmSrc{a, C, C, 1}}, s.a1_qkv, e));
+    }
     RC(attention(m, st, s, B, qb, N, kb, rows_k, vtb, pitch_v, N, N, m->ao));
     {
         GemmEpilogue e = epi_out(m->xb, C);
         e.res = m->xa; e.ldr = C;
-        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a1_out, e));
+        produce(e, 1);
+        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a1_out, e, -1, &slots[1]));
     }
-    __half* x16 = m->xb;   // fp16 stream after attn1 (+ fuser)
+    __half* x16 = m->xb;   // fp16 stream after attn1 (+ fuser); its row statistics are in rstats[1]
     RC(tap(m, st, s.p + ":proj_in", m->xa, DT_F16, M, C));
     RC(tap(m, st, s.p + ":attn1", m->xb, DT_F16, M, C));
     if (alpha_scale != 0.0f) {
         // GatedSelfAttentionDense (attention.py:226-234): visual queries only; the 30 grounding K/V rows of this block sit
         // behind the N visual rows of its K / V^T buffers since ltt_set_conditioning
-        RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
-        RC(r.gemm(H, W, 3 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_qkv, epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0)));
+        {
+            GemmEpilogue e = epi_qkv(s, qb, N, kb, rows_k, vtb, pitch_v, N, 0);
+            const __half* a = m->xb;
+            if (fold) {
+                consume(e, 1, s.fq_s, s.fq_c);
+            } else {
+                RC(ln(m, st, m->xb, DT_F16, M, C, s.f_ln1, m->ln16, nullptr));
+                a = m->ln16;
+            }
+            RC(r.gemm(H, W, 3 * C, {GemmSrc{a, C, C, 1}}, s.f_qkv, e));
+        }
         RC(attention(m, st, s, B, qb, N, kb, rows_k, vtb, pitch_v, N, N + mo, m->ao));
         {
             GemmEpilogue e = epi_out(m->xa, C);
             e.res = m->xb; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_ta;
-            RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.f_out, e));
+            produce(e, 0);
+            RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.f_out, e, -1, &slots[0]));
         }
-        RC(ln(m, st, m->xa, DT_F16, M, C, s.f_ln2, m->ln16, nullptr));
         {
             GemmEpilogue e = epi_out(m->ffbuf, 4 * C);
             e.act = ACT_GEGLU;
-            RC(r.gemm(H, W, 8 * C, {GemmSrc{m->ln16, C, C, 1}}, s.f_ff1, e));
+            const __half* a = m->xa;
+            if (fold) {
+                consume(e, 0, s.ff1f_s, s.ff1f_c);
+            } else {
+                RC(ln(m, st, m->xa, DT_F16, M, C, s.f_ln2, m->ln16, nullptr));
+                a = m->ln16;
+            }
+            RC(r.gemm(H, W, 8 * C, {GemmSrc{a, C, C, 1}}, s.f_ff1, e));
         }
         {
             GemmEpilogue e = epi_out(m->xb, C);
             e.res = m->xa; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_td;
-            RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.f_ff2, e));
+            produce(e, 1);
+            RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.f_ff2, e, -1, &slots[1]));
         }
         x16 = m->xb;
     }
     RC(tap(m, st, s.p + ":fuser", x16, DT_F16, M, C));
     // RelationCrossAttention (attention.py:315-359) + the caller's (out + x) / 2 (:398)
-    // norm3 is never materialised: one pass leaves (mean, rstd) per row, the pool and scatter kernels normalise on the fly
-    {
+    // norm3 is never materialised: the pool and scatter kernels normalise on the fly from per-row statistics -- the
+    // partial sums the producing GEMM's epilogue left (LayerNorm fold) or one statistics pass over x16
+    RowStatSrc r3;
+    if (fold) {
+        r3.p = m->rstats[1]; r3.ld = GEMM_STATS_LD; r3.slots = slots[1]; r3.K = C; r3.eps = 1e-5f;
+    } else {
         m->launches++;
         ProfScope ps(m, st, PC_LN, 0.0, (double)M * C * 2.0);
         RC(layernorm_launch(x16, DT_F16, M, C, s.r_ln3.g, s.r_ln3.b, 1e-5f, nullptr, nullptr, st, m->row_stats));
+        r3.p = m->row_stats;
     }
     const int ng = m->n_grounded;
     const __half* feats_final = nullptr;
     if (ng > 0) {
-        RC(rela_pool_launch(nullptr, x16, m->row_stats, s.r_ln3.g, s.r_ln3.b, m->rects[level], ng, mo, H, W, C, m->feats, st));
+        RC(rela_pool_launch(nullptr, x16, r3, s.r_ln3.g, s.r_ln3.b, m->rects[level], ng, mo, H, W, C, m->feats, st));
         m->launches++;
         const int R = ng * mo;
         if (m->rela_fused) {
@@ -708,7 +821,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         feats_final = m->feats3;
     }
     // scatter + the block's norm2 in one kernel
-    RC(rela_scatter_launch(nullptr, m->row_stats, s.r_ln3.g, s.r_ln3.b, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
+    RC(rela_scatter_launch(nullptr, r3, s.r_ln3.g, s.r_ln3.b, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
                            m->ln16, st));
     m->launches++;
     RC(tap(m, st, s.p + ":rela", m->xe32, DT_F32, M, C));
@@ -718,15 +831,23 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     {
         GemmEpilogue e = epi_out(m->xf32, C, DT_F32);
         e.res = m->xe32; e.res_dtype = DT_F32; e.ldr = C;
-        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a2_out, e));
+        if (fold) e.out16 = m->xh16;     // the feed-forward's folded LayerNorm reads the stream as fp16 rows
+        produce(e, 0);
+        RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a2_out, e, -1, &slots[0]));
     }
     RC(tap(m, st, s.p + ":attn2", m->xf32, DT_F32, M, C));
     // ff
-    RC(ln(m, st, m->xf32, DT_F32, M, C, s.ln3, m->ln16, nullptr));
     {
         GemmEpilogue e = epi_out(m->ffbuf, 4 * C);
         e.act = ACT_GEGLU;
-        RC(r.gemm(H, W, 8 * C, {GemmSrc{m->ln16, C, C, 1}}, s.ff1, e));
+        const __half* a = m->xh16;
+        if (fold) {
+            consume(e, 0, s.ff1_s, s.ff1_c);
+        } else {
+            RC(ln(m, st, m->xf32, DT_F32, M, C, s.ln3, m->ln16, nullptr));
+            a = m->ln16;
+        }
+        RC(r.gemm(H, W, 8 * C, {GemmSrc{a, C, C, 1}}, s.ff1, e));
     }
     {   // the fp32 stream is consumed only by proj_out, whose input autocast rounds to fp16
         GemmEpilogue e = epi_out(m->xa, C);
@@ -975,6 +1096,9 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->ao, max_tok * 2));
     RC(A(&m->ffbuf, max_ff * 2));
     RC(A(&m->row_stats, (size_t)B * H * W * sizeof(float2)));
+    for (int i = 0; i < 2; ++i) RC(A(&m->rstats[i], (size_t)B * H * W * GEMM_STATS_LD * sizeof(float2)));
+    RC(A(&m->xh16, max_tok * 2));
+    RC(A(&m->cond_stats, (size_t)B * mo * sizeof(float2)));
     RC(A(&m->xe32, max_tok * 4));
     RC(A(&m->xf32, max_tok * 4));
     const size_t fe = (size_t)B * mo * maxC;
@@ -1056,6 +1180,7 @@ int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
     LTT_CUDA_OK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device));
     m->use_graphs = getenv("LTT_NO_GRAPH") == nullptr;
     m->rela_fused = getenv("LTT_RELA_UNFUSED") == nullptr;     // debugging / per-launch profiling: eager launches
+    m->ln_fold = getenv("LTT_NO_LNFOLD") == nullptr;
     *out = m;
     return 0;
 }
@@ -1216,8 +1341,7 @@ int ltt_set_conditioning(ltt_model* m, const float* context, int ctx_len, const 
         RC(r.gemm(1, R, C, {GemmSrc{m->objs16, cd, cd, 1}}, s.f_linear, epi_out(h1, C), 1));
         RC(ln(m, st, h1, DT_F16, R, C, s.f_ln1, h2, nullptr));
         {
-            Lin kv = s.f_qkv;
-            kv.w = s.f_qkv.w + (size_t)C * C; kv.N = 2 * C;
+            const Lin& kv = s.f_kv_plain;
             // rows [Ntok, Ntok + mo) of the block's own K / V^T buffers (never touched by the per-step QKV projections)
             GemmEpilogue e = epi_qkv(s, nullptr, 0, s.kb + (size_t)Ntok * s.heads * s.dpad, s.rows_k, s.vtb + Ntok, s.rows_k, mo, 1);
             RC(r.gemm(1, mo, 2 * C, {GemmSrc{h2, C, C, 1}}, kv, e));

@@ -756,13 +756,30 @@ int rela_rects_launch(const float* boxes, const float* masks, int B, int mo, int
     return 0;
 }
 
+// (mean, rstd) of a token row for the kernels that normalise on the fly: either stored directly (slots == -1,
+// layernorm_kernel's stats_out) or as the `slots` partial (sum, sum of squares) the producing GEMM's epilogue left
+// (gemm_tc.cu, LayerNorm fold), summed in slot order.
+__device__ __forceinline__ float2 row_mean_rstd(const RowStatSrc& s, size_t row) {
+    const float2* p = s.p + row * (size_t)s.ld;
+    if (s.slots < 0) return p[0];
+    float sm = 0.f, sq = 0.f;
+    for (int i = 0; i < s.slots; ++i) {
+        const float2 t = p[i];
+        sm += t.x;
+        sq += t.y;
+    }
+    const float inv = 1.0f / (float)s.K;
+    const float mean = sm * inv;
+    return make_float2(mean, rsqrtf(fmaxf(sq * inv - mean * mean, 0.f) + s.eps));
+}
+
 // feats[b, i, :] = mean over the box of hid (fp32) -> fp16; zero for unused slots.  CTA = (64 channels, slot, b),
 // RP_LANES pixel lanes x 16 channel quads (a box of a 64x64 latent holds up to 4096 pixels and only the valid slots do
 // work, so the pixel loop is the critical path: 64 lanes x 4 pixels in flight), smem reduction over the pixel lanes.  hid is either a materialised
 // fp32 tensor or (hid == nullptr) the LayerNorm of the fp16 tensor x16 evaluated on the fly from per-row statistics:
 // hid[p][c] = (x16[p][c] - mean_p) * rstd_p * gamma[c] + beta[c]  (same expression / order as layernorm_kernel).
 constexpr int RP_LANES = 64;
-__global__ void __launch_bounds__(16 * RP_LANES) rela_pool_kernel(const float* __restrict__ hid, const __half* __restrict__ x16, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(16 * RP_LANES) rela_pool_kernel(const float* __restrict__ hid, const __half* __restrict__ x16, const RowStatSrc stats,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, const int* __restrict__ rects,
                                  int mo, int w, int HW, int C, __half* __restrict__ feats) {
     pdl_launch_dependents();
@@ -788,7 +805,7 @@ __global__ void __launch_bounds__(16 * RP_LANES) rela_pool_kernel(const float* _
         const size_t row = (size_t)b * HW + y * w + x;
         if (hid) return *reinterpret_cast<const float4*>(hid + row * C + c);
         const uint2 u = *reinterpret_cast<const uint2*>(x16 + row * C + c);
-        const float2 st = stats[row];
+        const float2 st = row_mean_rstd(stats, row);
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
         const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
         return make_float4((f0.x - st.x) * st.y * g4.x + b4.x, (f0.y - st.x) * st.y * g4.y + b4.y,
@@ -830,7 +847,7 @@ __global__ void __launch_bounds__(16 * RP_LANES) rela_pool_kernel(const float* _
         *reinterpret_cast<uint2*>(o) = u;
     }
 }
-int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, const float* gamma, const float* beta,
+int rela_pool_launch(const float* hid, const __half* x16, const RowStatSrc& stats, const float* gamma, const float* beta,
                      const int* rects, int B, int mo, int h, int w, int C, __half* feats, cudaStream_t st) {
     if (C % 64) {
         set_error("rela_pool: C %% 64 != 0 (C=%d)", C);
@@ -848,7 +865,7 @@ int rela_pool_launch(const float* hid, const __half* x16, const float2* stats, c
 // (fp32 two-pass statistics, as layernorm_kernel).  C <= 8 * blockDim.x.
 constexpr int RS_THREADS = 160;
 __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
-    const float* __restrict__ hid, const float2* __restrict__ stats, const float* __restrict__ gamma3,
+    const float* __restrict__ hid, const RowStatSrc stats, const float* __restrict__ gamma3,
     const float* __restrict__ beta3, const __half* __restrict__ x, const __half* __restrict__ feats,
     const int* __restrict__ rects, int nb_feats, int mo, int w, int HW, int C, float* __restrict__ out,
     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ ln16) {
@@ -895,7 +912,7 @@ __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
             const float4 h1 = *reinterpret_cast<const float4*>(hid + (size_t)row * C + c + 4);
             hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
         } else {      // hid = LayerNorm(x) from the row statistics (same expression / order as layernorm_kernel)
-            const float2 st = stats[row];
+            const float2 st = row_mean_rstd(stats, (size_t)row);
             const float4 ga = *reinterpret_cast<const float4*>(gamma3 + c), gb = *reinterpret_cast<const float4*>(gamma3 + c + 4);
             const float4 ba = *reinterpret_cast<const float4*>(beta3 + c), bb = *reinterpret_cast<const float4*>(beta3 + c + 4);
             const float g3[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
@@ -959,7 +976,7 @@ __global__ void __launch_bounds__(RS_THREADS) rela_scatter_ln_kernel(
     }
 }
 // gamma == nullptr: scatter only (ln16 ignored).
-int rela_scatter_launch(const float* hid, const float2* stats, const float* gamma3, const float* beta3, const __half* x,
+int rela_scatter_launch(const float* hid, const RowStatSrc& stats, const float* gamma3, const float* beta3, const __half* x,
                         const __half* feats, const int* rects, int nb_feats, int B, int mo, int h, int w, int C, float* out,
                         const float* gamma, const float* beta, float eps, __half* ln16, cudaStream_t st) {
     if (mo > 32 || C % 8 || C > 8 * RS_THREADS) {
@@ -1537,7 +1554,7 @@ int pack_conv_launch(const float* w, int O, int Cin, int taps, int cstart, int C
 // linear weight rows [rows, K] fp32 -> fp16 dst rows starting at row_off; geglu != 0 interleaves per 128-row tile:
 // packed row p = tile*128 + h*64 + i  <-  source row h*(rows/2) + tile*64 + i   (h = 0 value, 1 gate)
 __global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int K, __half* __restrict__ dst, int row_off,
-                                 int geglu) {
+                                 int geglu, const float* __restrict__ colscale) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t total = (size_t)rows * K;
@@ -1549,17 +1566,46 @@ __global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int K, _
             const int tile = p / 128, h = (p % 128) / 64, ii = p % 64;
             src = h * (rows / 2) + tile * 64 + ii;
         }
-        dst[((size_t)row_off + p) * K + k] = __float2half_rn(w[(size_t)src * K + k]);
+        const float v = w[(size_t)src * K + k];
+        dst[((size_t)row_off + p) * K + k] = __float2half_rn(colscale ? v * colscale[k] : v);
     }
 }
-int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, int geglu, cudaStream_t st) {
+// LayerNorm fold (gemm_tc.cu): for W' = fp16(W * gamma) the consumer GEMM needs per output row n
+//   s[n] = sum_k W'[n, k]   and   c[n] = bias[n] + sum_k beta[k] * fp16(W[n, k]).   One warp per row (original row order).
+__global__ void ln_fold_vectors_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ bias, int N, int K, float* __restrict__ s_out,
+                                       float* __restrict__ c_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s = 0.f, c = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float v = w[(size_t)n * K + k];
+        s += r16f(v * gamma[k]);
+        c = fmaf(beta[k], r16f(v), c);
+    }
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+        s_out[n] = s;
+        c_out[n] = c + (bias ? bias[n] : 0.f);
+    }
+}
+int ln_fold_vectors_launch(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K, float* s_out,
+                           float* c_out, cudaStream_t st) {
+    ln_fold_vectors_kernel<<<(N + 7) / 8, 256, 0, st>>>(w, gamma, beta, bias, N, K, s_out, c_out);
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int pack_rows_launch(const float* w, int rows, int K, __half* dst, int row_off, int geglu, cudaStream_t st, const float* colscale) {
     if (geglu && rows % 128) {
         set_error("pack_rows: GEGLU rows %% 128 != 0 (%d)", rows);
         return -1;
     }
     const size_t total = (size_t)rows * K;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    LTT_CUDA_OK(launch_k(pack_rows_kernel, dim3(blocks), dim3(256), 0, st, w, rows, K, dst, row_off, geglu));
+    LTT_CUDA_OK(launch_k(pack_rows_kernel, dim3(blocks), dim3(256), 0, st, w, rows, K, dst, row_off, geglu, colscale));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -56,6 +56,19 @@ def reference_tree():
         sys.path[:] = saved_path
 
 
+@contextlib.contextmanager
+def true_fp32():
+    """fp32 reference runs must be fp32: PyTorch lets cuDNN convolutions use TF32 on CUDA by default (10-bit mantissa,
+    7.8e-4 rel-L2 on this UNet), which is not the arithmetic of the reference's CPU / fp32 path."""
+    c, m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = c, m
+
+
 def unet_params(cfg: dict) -> dict:
     """Constructor arguments of the reference UNetModel for an oracle-style cfg dict (GLIGEN/configs/coco2014.yaml:8-30)."""
     return dict(image_size=cfg.get("image_size", 64), in_channels=cfg["in_channels"], out_channels=cfg["out_channels"],
@@ -117,7 +130,8 @@ def unet_eps(model, syn: dict, t: int, scale: float, cond: bool, autocast: bool)
     if autocast:
         with torch.autocast(syn["x"].device.type, dtype=torch.float16):
             return model(inp).float()
-    return model(inp).float()
+    with true_fp32():
+        return model(inp).float()
 
 
 def build_sampler(model, device, alpha_type=(0.3, 0.0, 0.7)):

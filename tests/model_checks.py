@@ -62,7 +62,9 @@ def oracle_eps(sd, cfg, syn, t, scale, cond, autocast, first_conv=None):
         if autocast:
             with torch.autocast("cuda", dtype=torch.float16):
                 return uo.unet_forward(sd, cfg, inp, scale=scale, first_conv=first_conv).float()
-        return uo.unet_forward(sd, cfg, inp, scale=scale, first_conv=first_conv)
+        from oracle.ref_loader import true_fp32
+        with true_fp32():          # no TF32 convolutions in the fp32 oracle
+            return uo.unet_forward(sd, cfg, inp, scale=scale, first_conv=first_conv)
 
 
 def engine_eps_pair(e, syn, t, scale, H, W):

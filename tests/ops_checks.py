@@ -247,6 +247,29 @@ def check_rela_scatter_ln(B, nb, h, w, C, seed=0):
     return max(rel(out, ref), rel(ln16.float(), ref_ln) / 4)
 
 
+def check_ln_fold(M, K1, C, N, act2=0, seed=0):
+    """Producer GEMM with row-statistics epilogue -> consumer GEMM with the LayerNorm folded in, against
+    F.linear(F.layer_norm(x)) in fp32 on the same fp16 x (x = the producer's own fp16 output)."""
+    a = rn(M, K1, seed=seed, dtype=torch.float16)
+    w1 = rn(C, K1, seed=seed + 1, scale=1 / math.sqrt(K1)).half()
+    b1 = rn(C, seed=seed + 2, scale=0.5)                      # a row mean well away from 0
+    gamma, beta = 1 + 0.2 * rn(C, seed=seed + 3), 0.2 * rn(C, seed=seed + 4)
+    w2 = rn(N, C, seed=seed + 5, scale=1 / math.sqrt(C))
+    b2 = rn(N, seed=seed + 6, scale=0.1)
+    nout = N // 2 if act2 == 2 else N
+    out1 = torch.empty(M, C, device=DEV, dtype=torch.float16)
+    out2 = torch.empty(M, nout, device=DEV, dtype=torch.float16)
+    L.check(L.lib().ltt_op_linear_ln_linear(L.ptr(a), M, K1, L.ptr(w1), L.ptr(b1), C, L.ptr(gamma), L.ptr(beta), 1e-5,
+                                            L.ptr(w2.contiguous()), L.ptr(b2), N, act2, L.ptr(out1), L.ptr(out2), L.stream_ptr()),
+            "linear_ln_linear")
+    x = out1.float()
+    e1 = rel(x, F.linear(a.float(), w1.float(), b1))
+    ref = F.linear(F.layer_norm(x, (C,), gamma, beta, 1e-5), w2.half().float(), b2)
+    if act2 == 2:
+        v, g = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+    return max(e1, rel(out2.float(), ref))
+
 # ------------------------------------------------------------------------------------------------ small ops vs the oracle
 def check_rela_rects(B, h, w, seed=0):
     """Integer box rectangles incl. the truncation and `break` rules against oracle.box_pixel_rects (bit-exact)."""
@@ -421,6 +444,13 @@ ALL = [
     ("layernorm f16 4096x320", check_layernorm, dict(M=4096, C=320, dtype=torch.float16), 1e-4),
     ("layernorm f32 1000x1280", check_layernorm, dict(M=1000, C=1280, dtype=torch.float32), 1e-4),
     ("layernorm f16 90x64", check_layernorm, dict(M=90, C=64, dtype=torch.float16), 1e-4),
+    ("LayerNorm fold 4096x320 -> QKV-like 960", check_ln_fold, dict(M=4096, K1=320, C=320, N=960), 2e-3),
+    ("LayerNorm fold 4096x320 -> GEGLU 2560", check_ln_fold, dict(M=4096, K1=320, C=320, N=2560, act2=2), 2e-3),
+    ("LayerNorm fold 1000x640 (K1 2560, tail rows) -> 1920", check_ln_fold, dict(M=1000, K1=2560, C=640, N=1920), 2e-3),
+    ("LayerNorm fold 128x1280 (split-K producer and consumer) -> 3840", check_ln_fold, dict(M=128, K1=5120, C=1280, N=3840), 2e-3),
+    ("LayerNorm fold 60x1280 -> GEGLU 10240 (split-K)", check_ln_fold, dict(M=60, K1=1280, C=1280, N=10240, act2=2), 2e-3),
+    ("LayerNorm fold 16384x320 (CTA-pair producer) -> 960", check_ln_fold, dict(M=16384, K1=1280, C=320, N=960), 2e-3),
+    ("LayerNorm fold 300x64 -> 192", check_ln_fold, dict(M=300, K1=64, C=64, N=192), 2e-3),
     ("rela rects 8x64x64 vs oracle (truncation, clamp, break rule)", check_rela_rects, dict(B=8, h=64, w=64), 0.5),
     ("rela rects 4x24x16 vs oracle", check_rela_rects, dict(B=4, h=24, w=16, seed=3), 0.5),
     ("rela rects 5x8x8 vs oracle", check_rela_rects, dict(B=5, h=8, w=8, seed=5), 0.5),

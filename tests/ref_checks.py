@@ -112,9 +112,11 @@ def reference_noise(cfg, seed, H, W, n_boxes, t, scale):
     return out
 
 
-def check_engine_within_reference_noise(cfg, seed, H, W, n_boxes, t, scale, factor=1.35):
-    """err(engine, reference fp16) / (factor * noise floor): < 1 passes.  Noise floor = the reference against itself
-    when the sample is merely batched with another one."""
+def check_engine_within_reference_noise(cfg, seed, H, W, n_boxes, t, scale, factor=1.2):
+    """err(engine, reference fp16) / (factor * noise floor): < 1 passes.  Noise floor = the reference's fp16 output
+    against ITSELF when the sample is merely batched with another one, or when its latent is perturbed far below fp16
+    resolution (measured on B200: 1.5e-3 / 1.7e-3 -- north_star's 1e-3 is below what the reference reproduces of itself;
+    the engine sits at 1.85e-3, and closer to the fp32 reference than the reference's own fp16 run is)."""
     noise = reference_noise(cfg, seed, H, W, n_boxes, t, scale)
     err = check_engine_vs_reference(cfg=cfg, seed=seed, B=1, H=H, W=W, n_boxes=n_boxes, t=t, scale=scale)
     floor = max(noise["batched_with_another_sample"], noise["latent_perturbed_below_fp16_resolution"])
@@ -132,7 +134,7 @@ def reference_trace(cfg, seed, B, H, W, n_boxes, S=50, guidance=7.5, autocast=Tr
     inp = rl.model_inputs(ref, syn, 0, True)
     inp["x"], inp["timesteps"] = syn["x"].clone(), None
     gliv = {k: v.detach().clone() for k, v in ref.input_blocks[0][0].state_dict().items()}
-    ctx = torch.autocast("cuda", dtype=torch.float16) if autocast else torch.autocast("cuda", enabled=False)
+    ctx = torch.autocast("cuda", dtype=torch.float16) if autocast else rl.true_fp32()
     with ctx:
         out = sampler.sample(S=S, shape=tuple(syn["x"].shape), input=inp, uc=syn["uc"], guidance_scale=guidance)
     sdw = {k: v.detach().clone() for k, v in ref.input_blocks[0][0].state_dict().items()}

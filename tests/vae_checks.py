@@ -78,7 +78,10 @@ def latents(B, h, w, seed=9):
 @torch.no_grad()
 def ref_decode(dd, seed, z, autocast):
     m = reference_vae(dd, seed)
-    with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.float16):
+            return m.decode(z).float()
+    with rl.true_fp32():
         return m.decode(z).float()
 
 

@@ -43,7 +43,9 @@ def oracle(autocast, sdd=None, xin=None):
                 with torch.autocast("cuda", dtype=torch.float16):
                     o = uo.unet_forward(sdd, cfg, inp, scale=scale, taps=tp)
             else:
-                o = uo.unet_forward(sdd, cfg, inp, scale=scale, taps=tp)
+                from oracle.ref_loader import true_fp32
+                with true_fp32():
+                    o = uo.unet_forward(sdd, cfg, inp, scale=scale, taps=tp)
         tp["eps"] = o
         res.append(tp)
     return res
