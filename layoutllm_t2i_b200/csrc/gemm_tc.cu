@@ -136,6 +136,7 @@ __device__ __forceinline__ void fetch_operands(const GemmEpilogue& e, const RowI
 // g = gate half), bv / bg = the matching bias values (already in registers), j = index of the group inside the
 // 16-column chunk whose operands are in `o`.  Rounding points follow the fp16-autocast reference: each Linear/Conv
 // output is rounded to fp16 before the next elementwise op.
+template <bool LNF>
 __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
                                                 const float (&g)[8], const float (&bv)[8], const float (&bg)[8],
                                                 const RowOperands& o, int j, RowStats& rs) {
@@ -202,14 +203,18 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
     __half2 h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    if (e.stats_out) rs.add(h);
+    if constexpr (LNF) {
+        if (e.stats_out) rs.add(h);
+    }
     if (e.out_dtype == DT_F16) {
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
     } else {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
         op[0] = make_float4(v[0], v[1], v[2], v[3]);
         op[1] = make_float4(v[4], v[5], v[6], v[7]);
-        if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+        if constexpr (LNF) {
+            if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+        }
     }
 }
 
@@ -233,7 +238,7 @@ struct KindTag {
     static constexpr int value = K;
 };
 
-template <int KIND>
+template <int KIND, bool LNF>
 __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo& ri, int n, int Nout, float (&v)[8],
                                            const float (&g)[8], const float* __restrict__ bs, const float* __restrict__ bsg,
                                            const RowOperands& o, int j, RowStats& rs) {
@@ -244,7 +249,7 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
             bv[i] = bs[i];
             bg[i] = e.act == ACT_GEGLU ? bsg[i] : 0.f;
         }
-        epilogue_group8(e, ri, n, Nout, v, g, bv, bg, o, j, rs);
+        epilogue_group8<LNF>(e, ri, n, Nout, v, g, bv, bg, o, j, rs);
         return;
     } else {
         if (!ri.valid || n >= Nout) return;
@@ -307,12 +312,16 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
                 float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)ri.m * e.ldo + n);
                 op[0] = make_float4(y[0], y[1], y[2], y[3]);
                 op[1] = make_float4(y[4], y[5], y[6], y[7]);
-                if (e.stats_out) rs.add(h);
-                if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+                if constexpr (LNF) {
+                    if (e.stats_out) rs.add(h);
+                    if (e.out16) *reinterpret_cast<uint4*>(e.out16 + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
+                }
                 return;
             }
         }
-        if (e.stats_out && (KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32)) rs.add(h);
+        if constexpr (LNF && (KIND == EK_F16 || KIND == EK_GATE16 || KIND == EK_RES32)) {
+            if (e.stats_out) rs.add(h);
+        }
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + (size_t)ri.m * e.ldo + n) = *reinterpret_cast<uint4*>(h);
     }
 }
@@ -321,7 +330,9 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
 // blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA issuer run ahead of the epilogue warps by up
 // to one unit because the fp32 accumulator is double buffered in TMEM (2 x BN columns): the epilogue of unit u
 // overlaps the main loop of unit u + 1.
-template <int BN, int STAGES, bool PAIR>
+// LNF: the LayerNorm-fold features (row statistics out, fp16 copy of an fp32 output, folded-LayerNorm consumer); the plain
+// variant carries none of that code.
+template <int BN, int STAGES, bool PAIR, bool LNF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
     using SM = GemmSmem<BN, STAGES>;
     constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     }
                 }
                 bias_s[c] = bvv;
-                if (e.ln_stats) {           // LayerNorm fold: ln_s is indexed like the bias
+                if (LNF && e.ln_stats) {    // LayerNorm fold: ln_s is indexed like the bias
                     float sv = 0.f;
                     if (geglu) {
                         const int half = c / ncols, cc = c % ncols;
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             // LayerNorm fold, consumer side: (mean, rstd) of this thread's row from the producer's partial sums -- fetched
             // while the main loop of this unit is still running
             float ln_mean = 0.f, ln_rstd = 1.f;
-            if (e.ln_stats && ri.valid) {
+            if (LNF && e.ln_stats && ri.valid) {
                 const float2* sp = e.ln_stats + (size_t)ri.m * e.ln_ld;
                 if (e.ln_slots < 0) {
                     const float2 t = sp[0];
@@ -583,6 +594,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     ln_rstd = rsqrtf(fmaxf(sq * inv - ln_mean * ln_mean, 0.f) + e.ln_eps);
                 }
             }
+            const float ln_nmr = -ln_mean * ln_rstd;       // y = rstd * acc + (-mean * rstd) * s_n + c_n
             RowStats rstat;
             named_bar_sync(2, EPI_THREADS);
             const uint32_t trow = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -656,14 +668,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             }
                         }
                     }
-                    if (e.ln_stats) {
+                    if (LNF && e.ln_stats) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            v8[i] = ln_rstd * fmaf(-ln_mean, lns_s[c + i], v8[i]);
-                            if (geglu) g8[i] = ln_rstd * fmaf(-ln_mean, lns_s[ncols + c + i], g8[i]);
+                            v8[i] = fmaf(v8[i], ln_rstd, ln_nmr * lns_s[c + i]);
+                            if (geglu) g8[i] = fmaf(g8[i], ln_rstd, ln_nmr * lns_s[ncols + c + i]);
                         }
                     }
-                    epilogue_group8(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0, rstat);
+                    epilogue_group8<LNF>(e, ri, nbase + c, Nout, v8, g8, bv, bg, o, 0, rstat);
                 }
             } else {
                 // 16-column chunks: accumulators -> fused epilogue (specialised per epilogue kind) -> global
@@ -691,14 +703,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v8[i] = __uint_as_float(v[h * 8 + i]);
                                 g8[i] = gg ? __uint_as_float(g[h * 8 + i]) : 0.f;
                             }
-                            if ((KIND == EK_QKV || KIND == EK_GEGLU || KIND == EK_GENERIC) && e.ln_stats) {
+                            if (LNF && e.ln_stats) {
+                                const float4* s4 = reinterpret_cast<const float4*>(lns_s + c + h * 8);
+                                const float4 sa = s4[0], sb = s4[1];
+                                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    v8[i] = ln_rstd * fmaf(-ln_mean, lns_s[c + h * 8 + i], v8[i]);
-                                    if (gg) g8[i] = ln_rstd * fmaf(-ln_mean, lns_s[ncols + c + h * 8 + i], g8[i]);
+                                for (int i = 0; i < 8; ++i) v8[i] = fmaf(v8[i], ln_rstd, ln_nmr * sv[i]);
+                                if (gg) {
+                                    const float4* g4 = reinterpret_cast<const float4*>(lns_s + ncols + c + h * 8);
+                                    const float4 ga = g4[0], gb = g4[1];
+                                    const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) g8[i] = fmaf(g8[i], ln_rstd, ln_nmr * gv[i]);
                                 }
                             }
-                            epi_group8<KIND>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, opA, h, rstat);
+                            epi_group8<KIND, LNF>(e, ri, nbase + c + h * 8, Nout, v8, g8, bias_s + c + h * 8, bias_s + ncols + c + h * 8, opA, h, rstat);
                         }
                     }
                 };
@@ -714,7 +733,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 if (pair) mbar_arrive_remote(acc_empty_leader + (uint32_t)buf * 8u);
                 else mbar_arrive(&acc_empty[buf]);
             }
-            if (e.stats_out && ri.valid) {
+            if (LNF && e.stats_out && ri.valid) {
                 const int slot = ((tile % args.ntiles) * args.splits + z) * EPI_WGS + wg;
                 e.stats_out[(size_t)ri.m * e.stats_ld + slot] = make_float2(rstat.s, rstat.q);
             }
@@ -818,11 +837,14 @@ static void pick_tile(int B, int H, int W, int* tw, int* th) {
 template <int BN, int STAGES>
 struct Variant {
     using SM = GemmSmem<BN, STAGES>;
+    static bool lnf(const GemmDeviceArgs& a) { return a.epi.stats_out || a.epi.ln_stats || a.epi.out16; }
     static int configure() {
         static bool configured = false;
         if (!configured) {
-            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+            LTT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
             configured = true;
         }
         return 0;
@@ -845,7 +867,7 @@ struct Variant {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES, false>, &cfg) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES, false, true>, &cfg) != cudaSuccess) {
             cudaGetLastError();
             n = -1;
         }
@@ -877,7 +899,8 @@ struct Variant {
         at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true>, a));
+        if (lnf(a)) LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true, true>, a));
+        else LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, true, false>, a));
         LTT_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -886,7 +909,8 @@ struct Variant {
         a.splits = S;
         if (S == 1) {
             const int grid = ctas < num_sms ? ctas : num_sms;
-            LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
+            if (lnf(a)) LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false, true>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
+            else LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false, false>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
@@ -903,7 +927,8 @@ struct Variant {
             at[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at;
             cfg.numAttrs = pdl_enabled() ? 2 : 1;
-            LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false>, a));
+            if (lnf(a)) LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false, true>, a));
+            else LTT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, false, false>, a));
         }
         LTT_CUDA_OK(cudaGetLastError());
         return 0;
@@ -966,17 +991,19 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
     bool use_pair = false;
     double best = 1e30;
     static const int force_bn = getenv("LTT_GEMM_BN") ? atoi(getenv("LTT_GEMM_BN")) : 0;     // experiments only
+    const bool forced = p.force_bn != 0;           // autotuner: exactly this tiling or GEMM_ILLEGAL_TILING
     for (int bi = 0; bi < 4; ++bi) {
         const int bn = kBN[bi];
         if (geglu && bn % 128) continue;
-        if (force_bn && bn != force_bn && !(geglu && force_bn % 128)) continue;
+        if (forced && bn != p.force_bn) continue;
+        if (!forced && force_bn && bn != force_bn && !(geglu && force_bn % 128)) continue;
         const int nt = (p.N + bn - 1) / bn;
         const int ctas_c = mtiles * nt;
         const bool want_stats = p.epi.stats_out != nullptr;
         if (want_stats && nt * EPI_WGS > p.epi.stats_ld) continue;      // row-statistics slots of this tiling must fit
         const double it_cycles = std::max(2.0 * bn, (16384.0 + 128.0 * bn) / 75.0);
         const double epi_cycles = 600.0 + 6.0 * bn;
-        if (pair_mode && mtiles >= 2 && (iters >= 10 || pair_mode == 2) && bn >= 128) {
+        if (forced ? (p.force_pair && mtiles >= 2 && bn >= 128) : (pair_mode && mtiles >= 2 && (iters >= 10 || pair_mode == 2) && bn >= 128)) {
             int mc = 0;
             switch (bn) {
                 case 128: mc = Variant<128, 6>::max_clusters(2); break;
@@ -985,14 +1012,14 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
             }
             const int cu = ((mtiles + 1) / 2) * nt;
             // measured: the pair only pays once every CTA walks several tiles (cluster sync + remote barriers cost ~1.5 us)
-            if (mc > 0 && (cu >= 2 * mc || pair_mode == 2)) {
+            if (mc > 0 && (cu >= 2 * mc || pair_mode == 2 || forced)) {
                 const int waves = (cu + mc - 1) / mc;
                 const double it_pair = 1.1 * std::max(2.0 * bn, 256.0 + bn);
                 const double per_unit = iters * it_pair;
                 const double t = 3500.0 + (waves > 1 ? waves * std::max(per_unit, epi_cycles) + std::min(per_unit, epi_cycles)
                                                      : per_unit + epi_cycles);
-                if (t < best || (pair_mode == 2 && !use_pair)) {
-                    best = pair_mode == 2 ? 0.0 : t;      // 2: force pair mode wherever it is legal (experiments)
+                if (t < best || (pair_mode == 2 && !use_pair) || forced) {
+                    best = (pair_mode == 2 || forced) ? 0.0 : t;      // 2: force pair mode wherever it is legal (experiments)
                     BN = bn;
                     S = 1;
                     use_pair = true;
@@ -1001,6 +1028,7 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
         }
         static const int max_split = getenv("LTT_GEMM_MAXSPLIT") ? atoi(getenv("LTT_GEMM_MAXSPLIT")) : 8;     // experiments only
         for (int sp = 1; sp <= max_split; ++sp) {
+            if (forced && (p.force_pair || sp != p.force_splits)) continue;
             int resident = num_sms;
             if (sp > 1) {
                 if (sp * 2 > iters) break;
@@ -1035,6 +1063,7 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
     const int ntiles = (p.N + BN - 1) / BN;
     const int ctas = mtiles * ntiles;
     if (best >= 1e30) {
+        if (forced) return GEMM_ILLEGAL_TILING;
         set_error("gemm: no tiling fits (N=%d, stats_ld=%d)", p.N, p.epi.stats_ld);
         return -1;
     }

@@ -110,7 +110,11 @@ struct GemmProblem {
     int Ktot;             // = sum taps*channels
     int w_static;         // 1: `w` is never written by a kernel still in flight on the stream (model weights)
     GemmEpilogue epi;
+    // host only: tiling forced by the autotuner (model.cu); force_bn == 0 -> the launcher's cycle model picks.
+    // An illegal forced tiling returns GEMM_ILLEGAL_TILING without launching.
+    int force_bn = 0, force_splits = 1, force_pair = 0;
 };
+constexpr int GEMM_ILLEGAL_TILING = -9;
 
 // (split-K partial sums meet in distributed shared memory of a thread-block cluster: no global workspace)
 // stats_slots (optional): receives the number of statistics slots per row the launch writes when epi.stats_out is set.

@@ -10,6 +10,7 @@
 // stream switches to fp32 after the relation fusion exactly where CUDA autocast does in the reference; weights are
 // repacked once (ltt_finalize) to K-major fp16 [N, K] matrices in the K order the TMA gather walks.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -152,7 +153,12 @@ struct ltt_model {
     cudaStream_t capture_stream = nullptr;
     bool use_graphs = true;
     bool rela_fused = true;           // LTT_RELA_UNFUSED=1: q-GEMM / attention / out-GEMM as separate launches (A/B checks)
-    bool ln_fold = true;              // LTT_NO_LNFOLD=1: LayerNorms of the token stream as separate launches (A/B checks)
+    bool ln_fold = false;             // LTT_LNFOLD=1: LayerNorms of the token stream folded into the consumer GEMMs (see ltt_create)
+    // GEMM tiling autotuner: the first (eager) evaluation of a geometry times every legal (tile width, split-K cluster,
+    // CTA-pair) choice of each distinct GEMM shape on the device and keeps the fastest; LTT_NO_AUTOTUNE=1: cycle model only
+    bool autotune = true, tuning = false;
+    void* tune_flush = nullptr;       // 256 MB written between timed launches (L2 flush)
+    void* tune_touch = nullptr;
     float2* rstats[2] = {nullptr, nullptr};   // row-statistics slots [rows][GEMM_STATS_LD] written by GEMM epilogues (ping-pong)
     __half* xh16 = nullptr;           // fp16 copy of the fp32 residual stream (LayerNorm-fold operand of the last feed-forward)
     float2* cond_stats = nullptr;
@@ -567,6 +573,79 @@ static int tap(ltt_model* m, cudaStream_t st, const std::string& name, const voi
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------ GEMM autotuner
+// Process-wide so that every handle of a process runs a given GEMM shape with the same tiling (bit-identical results
+// between handles); like cuDNN's benchmark mode -- which the reference's callers switch on (txt2img.py:57) -- the choice
+// may differ between processes, and with it the fp32 summation order.
+struct TuneCfg { int bn, splits, pair; };
+static std::map<std::string, TuneCfg>& tuned_table() {
+    static std::map<std::string, TuneCfg> t;
+    return t;
+}
+static std::string tune_key(const GemmProblem& p) {
+    char buf[160];
+    const GemmEpilogue& e = p.epi;
+    snprintf(buf, sizeof(buf), "%d,%d,%d,%d,%d,%d,%d,%d|%d,%d,%d,%d,%d,%d,%d,%d,%d", p.B, p.H, p.W, p.N, p.Ktot, p.nsrc, p.src[0].taps,
+             p.src[0].channels, e.act, e.out_mode, e.out_dtype, e.res ? 1 + e.res_dtype : 0, e.has_gate, e.rowvec ? 1 : 0, e.bias ? 1 : 0,
+             e.stats_out ? 1 : 0, e.ln_stats ? 1 : 0);
+    return buf;
+}
+static const size_t TUNE_FLUSH_BYTES = (size_t)256 << 20;
+static int tune_gemm(ltt_model* m, GemmProblem& p, const std::string& key, cudaStream_t st) {
+    if (!m->tune_flush) {
+        LTT_CUDA_OK(cudaMalloc(&m->tune_flush, TUNE_FLUSH_BYTES));
+        LTT_CUDA_OK(cudaMalloc(&m->tune_touch, (size_t)64 << 20));
+    }
+    cudaEvent_t e0, e1;
+    LTT_CUDA_OK(cudaEventCreate(&e0));
+    LTT_CUDA_OK(cudaEventCreate(&e1));
+    static const int kBN[4] = {64, 128, 160, 256};
+    TuneCfg best{0, 1, 0};
+    float best_t = 1e30f;
+    int rc_final = 0;
+    for (int bi = 0; bi < 4 && !rc_final; ++bi) {
+        for (int mode = 0; mode <= 8 && !rc_final; ++mode) {      // 0: CTA pair, 1..8: split-K cluster size
+            p.force_bn = kBN[bi];
+            p.force_pair = mode == 0;
+            p.force_splits = mode == 0 ? 1 : mode;
+            int rc = gemm_tc_launch(p, m->sms, st);            // validates the tiling and warms the kernel
+            if (rc == GEMM_ILLEGAL_TILING) continue;
+            if (rc) { rc_final = rc; break; }
+            float tmin = 1e30f;
+            for (int rep = 0; rep < 3; ++rep) {
+                // weights stream from HBM in the real sequence (2.5 GB per evaluation against 126 MB of L2) while the
+                // activations were just written by the previous kernel: flush L2, then touch the A sources
+                cudaMemsetAsync(m->tune_flush, rep, TUNE_FLUSH_BYTES, st);
+                for (int si = 0; si < p.nsrc; ++si) {
+                    const size_t bytes = (size_t)p.B * p.H * p.W * p.src[si].ld * 2;
+                    if (bytes <= ((size_t)64 << 20)) cudaMemcpyAsync(m->tune_touch, p.src[si].ptr, bytes, cudaMemcpyDeviceToDevice, st);
+                }
+                cudaEventRecord(e0, st);
+                rc = gemm_tc_launch(p, m->sms, st);
+                cudaEventRecord(e1, st);
+                if (rc || cudaEventSynchronize(e1) != cudaSuccess) { rc_final = rc ? rc : -2; break; }
+                float t = 0.f;
+                cudaEventElapsedTime(&t, e0, e1);
+                tmin = std::min(tmin, t);
+            }
+            if (tmin < best_t) {
+                best_t = tmin;
+                best = TuneCfg{p.force_bn, p.force_splits, p.force_pair};
+            }
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc_final) return rc_final;
+    if (best.bn == 0) {
+        p.force_bn = 0;
+        return 0;          // nothing legal was timed: leave the choice to the cycle model
+    }
+    tuned_table()[key] = best;
+    if (getenv("LTT_VERBOSE")) fprintf(stderr, "[ltt] tuned %s -> BN %d splits %d pair %d (%.1f us)\n", key.c_str(), best.bn, best.splits, best.pair, best_t * 1e3f);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------ launch helpers
 struct Run {
     ltt_model* m;
@@ -588,6 +667,19 @@ struct Run {
         p.w_static = 1;      // packed model weights: written once at ltt_finalize
         p.epi = epi;
         if (!p.epi.bias) p.epi.bias = w.bias;
+        if (m->autotune) {
+            const std::string key = tune_key(p);
+            auto it = tuned_table().find(key);
+            if (it == tuned_table().end() && m->tuning && !m->capturing) {
+                RC(tune_gemm(m, p, key, st));
+                it = tuned_table().find(key);
+            }
+            if (it != tuned_table().end()) {
+                p.force_bn = it->second.bn; p.force_splits = it->second.splits; p.force_pair = it->second.pair;
+            } else {
+                p.force_bn = 0;
+            }
+        }
         m->launches++;
         const double Mrows = (double)p.B * p.H * p.W;
         const double nout = p.epi.act == ACT_GEGLU ? N / 2 : N;
@@ -996,7 +1088,12 @@ static int forward_cached(ltt_model* m, float alpha_scale, cudaStream_t st, bool
                          ((uint64_t)(skip_temb ? 1 : 0) << 62) | ((uint64_t)(m->prof_mode == 2 ? 1 : 0) << 61);
     auto it = m->graphs.find(key);
     if (it == m->graphs.end()) {
-        if (m->graph_seen[key]++ == 0) return forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
+        if (m->graph_seen[key]++ == 0) {
+            m->tuning = m->autotune;      // the eager first evaluation doubles as the tiling autotuner's measuring pass
+            const int rc = forward_impl(m, m->x_in, m->t_in, alpha_scale, m->eps_buf, st, skip_temb);
+            m->tuning = false;
+            return rc;
+        }
         if (!m->capture_stream) LTT_CUDA_OK(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
         const int64_t l0 = m->launches;
         LTT_CUDA_OK(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
@@ -1180,7 +1277,13 @@ int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
     LTT_CUDA_OK(cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device));
     m->use_graphs = getenv("LTT_NO_GRAPH") == nullptr;
     m->rela_fused = getenv("LTT_RELA_UNFUSED") == nullptr;     // debugging / per-launch profiling: eager launches
-    m->ln_fold = getenv("LTT_NO_LNFOLD") == nullptr;
+    // Measured on B200 (profiles/r02_lnfold_ab.txt): folding the LayerNorms into the consumer GEMMs removes 3-5 launches per
+    // transformer block but LOSES time (B=1: 305 vs 279 ms per image; B=8: 1370 vs 1335 ms): the folded epilogue costs
+    // two more FP32 operations per accumulator on GEMMs that are epilogue bound already, and the separate LayerNorm
+    // kernels were nearly free at B=1 because the next GEMM's prologue and weight prefetch overlap them (PDL).  Off by
+    // default; LTT_LNFOLD=1 switches it on (kept for larger hidden sizes, where the balance shifts).
+    m->ln_fold = getenv("LTT_LNFOLD") != nullptr;
+    m->autotune = getenv("LTT_NO_AUTOTUNE") == nullptr;
     *out = m;
     return 0;
 }
@@ -1196,6 +1299,8 @@ void ltt_destroy(ltt_model* m) {
     for (auto& kv : m->params) cudaFree(kv.second.dev);
     if (m->sd_conv_w) cudaFree(m->sd_conv_w);
     if (m->sd_conv_b) cudaFree(m->sd_conv_b);
+    if (m->tune_flush) cudaFree(m->tune_flush);
+    if (m->tune_touch) cudaFree(m->tune_touch);
     for (void* p : {(void*)m->ev_tab, (void*)m->tt_tab, (void*)m->tt_temb, (void*)m->tt_h, (void*)m->tt_s})
         if (p) cudaFree(p);
     delete m;

@@ -228,6 +228,25 @@ def check_dropin_sampler(cfg, seed, B, H, W, S, mode):
     return rel(out, ref)
 
 
+def check_unet_lnfold(cfg, seed, B, H, W, n_boxes, t, scale):
+    """The same forward with the LayerNorms folded into the consumer GEMMs (LTT_LNFOLD=1, read at ltt_create)."""
+    os.environ["LTT_LNFOLD"] = "1"
+    try:
+        e, sd = engine_for(cfg, seed, "lnfold")
+    finally:
+        del os.environ["LTT_LNFOLD"]
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    syn = to_dev(uo.synthetic_inputs(B=B, H=H, W=W, n_boxes=n_boxes, seed=4321))
+    l0 = e.launch_count
+    ec, eu = engine_eps_pair(e, syn, t, scale, H, W)
+    folded = e.launch_count - l0
+    e2, _ = engine_for(cfg, seed)
+    l0 = e2.launch_count
+    engine_eps_pair(e2, syn, t, scale, H, W)
+    assert folded < e2.launch_count - l0, (folded, e2.launch_count - l0)      # the LayerNorm launches are really gone
+    return max(rel(ec, oracle_eps(sd_dev, cfg, syn, t, scale, True, True)), rel(eu, oracle_eps(sd_dev, cfg, syn, t, scale, False, True)))
+
+
 FULL = uo.default_unet_config()
 
 ALL = [
@@ -236,6 +255,10 @@ ALL = [
      dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, degenerate=True), 3e-3),
     ("tiny UNet vs autocast oracle, alpha=0, 24x16 latent", check_unet_vs_oracle,
      dict(cfg=TINY, seed=7, B=3, H=24, W=16, n_boxes=5, t=401, scale=0.0), 3e-3),
+    ("tiny UNet with the LayerNorm fold on (LTT_LNFOLD=1), alpha=1", check_unet_lnfold,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0), 3e-3),
+    ("tiny UNet with the LayerNorm fold on, alpha=0", check_unet_lnfold,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=401, scale=0.0), 3e-3),
     ("tiny UNet cond-only / null-only batches", check_cond_only_batch, dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=30, t=21), 3e-3),
     ("tiny PLMS 5 steps, CFG 7.5", check_plms_vs_oracle, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5), 5e-3),
     ("drop-in UNetModel.forward(dict), cond + uncond, both gate values", check_dropin_forward,
