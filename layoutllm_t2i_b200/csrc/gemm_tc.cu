@@ -935,7 +935,7 @@ struct Variant {
     }
 };
 
-int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots) {
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots, int* chosen) {
     GemmDeviceArgs a;
     memset(&a, 0, sizeof(a));
     a.B = p.B; a.H = p.H; a.W = p.W; a.N = p.N;
@@ -1072,6 +1072,9 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
         return -1;
     }
     if (stats_slots) *stats_slots = ntiles * S * EPI_WGS;
+    if (chosen) {
+        chosen[0] = BN; chosen[1] = S; chosen[2] = use_pair ? 1 : 0;
+    }
     a.mtiles = mtiles;
     a.ntiles = ntiles;
     {

@@ -118,7 +118,8 @@ constexpr int GEMM_ILLEGAL_TILING = -9;
 
 // (split-K partial sums meet in distributed shared memory of a thread-block cluster: no global workspace)
 // stats_slots (optional): receives the number of statistics slots per row the launch writes when epi.stats_out is set.
-int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots = nullptr);
+// chosen (optional): receives {tile width BN, split-K cluster size, CTA-pair flag} of the tiling that was launched.
+int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* stats_slots = nullptr, int* chosen = nullptr);
 constexpr int GEMM_STATS_LD = 128;      // slots per row every stats buffer provides (launches are tiled to fit)
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -287,7 +287,8 @@ def check_rela_rects(B, h, w, seed=0):
         if n >= 7:
             boxes[b, 3] = torch.tensor([0.5, 0.2, 0.5 + 1e-4, 0.9])   # degenerate (l == r): ends the scan for this sample
     rects = torch.zeros(B, mo, 5, device=DEV, dtype=torch.int32)
-    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes.to(DEV)), L.ptr(masks.to(DEV)), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
+    boxes_d, masks_d = boxes.to(DEV), masks.to(DEV)        # named: the device copies must outlive the asynchronous launch
+    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes_d), L.ptr(masks_d), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
     torch.cuda.synchronize()
     ref = uo.box_pixel_rects(boxes, masks, h, w)
     got = rects.cpu()
@@ -316,7 +317,8 @@ def check_rela_pool(B, h, w, C, seed=0):
         boxes[b, :n] = torch.cat([xy, (xy + wh).clamp(max=1.0)], dim=-1)
         masks[b, :n] = 1
     rects = torch.zeros(B, mo, 5, device=DEV, dtype=torch.int32)
-    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes.to(DEV)), L.ptr(masks.to(DEV)), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
+    boxes_d, masks_d = boxes.to(DEV), masks.to(DEV)        # named: the device copies must outlive the asynchronous launch
+    L.check(L.lib().ltt_op_rela_rects(L.ptr(boxes_d), L.ptr(masks_d), B, mo, h, w, L.ptr(rects), L.stream_ptr()), "rects")
     hid = rn(B, h * w, C, seed=seed + 1) * 2 + 0.3
     feats = torch.full((B, mo, C), 9.0, device=DEV, dtype=torch.float16)
     L.check(L.lib().ltt_op_rela_pool(L.ptr(hid), L.ptr(rects), B, mo, h, w, C, L.ptr(feats), L.stream_ptr()), "rela_pool")
