@@ -61,6 +61,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial on [-0.5, 0.5], relative error
+// 7.5e-5 -- a sixth of an fp16 ulp, P is rounded to fp16 anyway): the MUFU unit delivers 16 ex2 per clock per SM
+// (measured: tools/ubench/tmem_mufu.cu, 15.3-15.5), i.e. 1024+ cycles for a 128 x 128 score tile against ~400 cycles of
+// tensor-core work at d = 40, so the softmax is MUFU bound; evaluating every POLY-th exponential here instead moves that
+// share of the load onto pipes that are otherwise ~35 % busy (the idea of FlashAttention-4's software exp2).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);                        // masked (-inf) scores -> 2^-126 ~ 0
+    const float t = x + 12582912.0f;              // 1.5 * 2^23: the integer nearest to x lands in the low mantissa bits
+    const float n = t - 12582912.0f;
+    const float f = x - n;
+    float p = fmaf(0.055171624f, f, 0.24261113f);
+    p = fmaf(p, f, 0.69326097f);
+    p = fmaf(p, f, 0.99992806f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));      // * 2^n through the exponent field
+}
+
 // SBUF = number of S accumulators in TMEM: 2 lets QK^T of tile j+1 overlap the softmax of tile j inside one CTA;
 // 1 (with MINB = 2 CTAs per SM, 256 TMEM columns each) gets the same overlap from the co-resident CTA and doubles
 // the number of softmax warps per SM -- the d=40 level is bound by the softmax warps' issue rate, not by the tensor pipe.
@@ -68,7 +84,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // core -- S(j+1) was produced while tile j was exponentiated and P(j+1) goes to the other buffer while PV(j) runs.
 // NWG = softmax warpgroups: with 2 the columns of a score tile are split between two threads per query row (half the
 // serial TMEM-load -> exp -> store chain per tile); the pair agrees on the running reference through shared memory.
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG>
+// POLY = k > 0: every k-th exponential of a row goes through ex2_poly instead of MUFU.EX2.
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG, int POLY>
 __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     extern __shared__ uint8_t smem_raw[];
@@ -228,8 +245,10 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                             __half2 h[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const float p0 = ex2_approx(fmaf(f[c8 * 8 + 2 * i], sc, nm));
-                                const float p1 = ex2_approx(fmaf(f[c8 * 8 + 2 * i + 1], sc, nm));
+                                const int e0 = c8 * 8 + 2 * i;         // compile-time after unrolling
+                                const float a0 = fmaf(f[e0], sc, nm), a1 = fmaf(f[e0 + 1], sc, nm);
+                                const float p0 = (POLY > 0 && e0 % POLY == 0) ? ex2_poly(a0) : ex2_approx(a0);
+                                const float p1 = (POLY > 0 && (e0 + 1) % POLY == 0) ? ex2_poly(a1) : ex2_approx(a1);
                                 rs += p0 + p1;
                                 h[i] = __floats2half2_rn(p0, p1);
                             }
@@ -338,20 +357,20 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
     }
 }
 
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1, int POLY = 0>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
         if (getenv("LTT_VERBOSE")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, att_threads(NWG), C::TOTAL);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, att_threads(NWG), C::TOTAL);
             fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, PBUF, MINB, C::TOTAL, nb);
         }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -411,6 +430,11 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
         // short key sets (the
         // 77-token text context) use 64-key tiles with S and P double buffered
         if (bkv == 64) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
+        static const int poly = getenv("LTT_ATTN_POLY") ? atoi(getenv("LTT_ATTN_POLY")) : 0;     // software-exp2 share (A/B)
+        if (poly == 2) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 2>(a, grid, stream);
+        if (poly == 3) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 3>(a, grid, stream);
+        if (poly == 4) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 4>(a, grid, stream);
+        if (poly == 8) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 8>(a, grid, stream);
         return attn_launch_variant<64, 48, 128, 1, 1, 2, 2>(a, grid, stream);
     }
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)
