@@ -90,10 +90,13 @@ int ltt_plms_sample(ltt_model* m, float* x_inout, int Bimg, int S, const int* ti
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t ltt_launch_count(const ltt_model* m);
 
-/* Per-kernel-class device timing for bench.py's roofline: while enabled, every launch of a class is bracketed by CUDA
- * events on the launch stream.  ltt_profile_report synchronises and returns, for class cls (0 = tcgen05 GEMM/implicit
- * conv, 1 = tcgen05 attention, 2 = GroupNorm, 3 = LayerNorm, 4 = whole UNet forward), the summed event time [ms], the
- * algorithmic FLOPs (2*M*N*K; 4*nq*nk*d per head) and bytes, and the launch count since ltt_profile_enable(m, 1). */
+/* Per-kernel-class device timing for bench.py's roofline.  on = 1: eager launches, every launch of a class bracketed by
+ * CUDA events on the launch stream.  on = 2: the brackets are external event-record nodes INSIDE the captured CUDA graphs
+ * of the evaluation (the mode the timed path runs in); a bracket then holds the times of its graph's last replay and
+ * ltt_profile_report weights it by the graph's replay count (calling ltt_profile_enable(m, 2) again restarts the
+ * counts).  on = 0: off.  ltt_profile_report synchronises and returns, for class cls (0 = tcgen05 GEMM / implicit conv,
+ * 1 = tcgen05 attention, 2 = GroupNorm, 3 = LayerNorm, 4 = whole UNet forward), the summed event time [ms], the
+ * algorithmic FLOPs (2*M*N*K; 4*nq*nk*d per head) and bytes, and the launch count since it was enabled. */
 int ltt_profile_enable(ltt_model* m, int on);
 int ltt_profile_report(ltt_model* m, int cls, double* ms, double* flops, double* bytes, int64_t* launches);
 
