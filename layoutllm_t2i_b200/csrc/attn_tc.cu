@@ -381,7 +381,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     const int rowlen = p.heads * p.dpad;
     int bkv, dv;
     static const int v40 = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;      // d = 40 variant (experiments)
-    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
+    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || v40 == 8 || v40 == 9 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
@@ -425,16 +425,24 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
         if (v40 == 1) return attn_launch_variant<64, 48, 64, 1, 1, 3>(a, grid, stream);
         if (v40 == 2) return attn_launch_variant<64, 48, 64, 2, 2, 2>(a, grid, stream);
         if (v40 == 7) return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
+        if (v40 == 8) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);        // 64-key tiles, S and P double buffered, 2 warpgroups
+        if (v40 == 9) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2, 8>(a, grid, stream);     // ... + 1/8 software exp2
         // default: two softmax warpgroups per CTA, two CTAs per SM (16 softmax warps per SM; measured alternatives at
         // 4096 x 4126 keys: 1 warpgroup 114 us, 2 warpgroups 103 us, 4 warpgroups 111 us, any 1-CTA/SM layout >= 129 us);
         // short key sets (the
         // 77-token text context) use 64-key tiles with S and P double buffered
         if (bkv == 64) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
-        static const int poly = getenv("LTT_ATTN_POLY") ? atoi(getenv("LTT_ATTN_POLY")) : 0;     // software-exp2 share (A/B)
+        // software-exp2 share: every 8th exponential on the FMA / ALU pipes is the measured optimum (4096 x 4126 keys, B=2:
+        // none 106.2 us, 1/16 105.5, 1/12 101.8, 1/8 97.6, 1/6 99.8, 1/4 101.5, 1/3 114.6, 1/2 122.6 -- beyond 1/8 the extra
+        // nine instructions per element make the softmax warps issue bound); LTT_ATTN_POLY=0 switches it off (A/B)
+        static const int poly = getenv("LTT_ATTN_POLY") ? atoi(getenv("LTT_ATTN_POLY")) : 8;
         if (poly == 2) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 2>(a, grid, stream);
         if (poly == 3) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 3>(a, grid, stream);
         if (poly == 4) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 4>(a, grid, stream);
+        if (poly == 6) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 6>(a, grid, stream);
         if (poly == 8) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 8>(a, grid, stream);
+        if (poly == 12) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 12>(a, grid, stream);
+        if (poly == 16) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 16>(a, grid, stream);
         return attn_launch_variant<64, 48, 128, 1, 1, 2, 2>(a, grid, stream);
     }
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Small end-to-end workload for `compute-sanitizer` (tests/test_sanitizer_gpu.py): a tiny UNet [cond ; uncond] forward at
+both gate values, a 3-step fused PLMS loop (CUDA-graph replay included) and a small VAE decode, all through the C-ABI.
+Prints one line per stage; any kernel fault surfaces as a sanitizer error."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import model_checks as mc  # noqa: E402
+from layoutllm_t2i_b200.vae import VaeDecoder  # noqa: E402
+from oracle import plms_oracle as po  # noqa: E402
+from oracle import unet_oracle as uo  # noqa: E402
+
+e, sd = mc.engine_for(mc.TINY, 7)
+syn = mc.to_dev(uo.synthetic_inputs(B=2, H=16, W=16, n_boxes=3, seed=4321))
+syn["grounding"]["boxes"][1, 1] = torch.tensor([0.30, 0.2, 0.3001, 0.9], device="cuda")
+for scale in (1.0, 0.0):
+    ec, eu = mc.engine_eps_pair(e, syn, 981, scale, 16, 16)
+    torch.cuda.synchronize()
+    print(f"forward gate {scale}: finite={bool(torch.isfinite(ec).all() and torch.isfinite(eu).all())}", flush=True)
+ts, a_t, a_prev, s1m = po.plms_tables(3, po.alphas_cumprod())
+ctx, relations = mc.cfg_batch(syn, 2)
+e.set_conditioning(ctx, relations, syn["grounding"], 16, 16)
+for _ in range(2):          # second call replays the captured graphs
+    out = e.plms_sample(syn["x"], ts, a_t, a_prev, s1m, [1, 1, 0], 7.5, None)
+torch.cuda.synchronize()
+print(f"plms 3 steps x2: finite={bool(torch.isfinite(out).all())}", flush=True)
+g = torch.Generator().manual_seed(0)
+dec = VaeDecoder(dict(ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=4, embed_dim=4, scale_factor=0.18215), 0)
+vsd = {}
+def conv(p, co, ci, k):
+    vsd[p + ".weight"] = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    vsd[p + ".bias"] = 0.02 * torch.randn(co, generator=g)
+def norm(p, c):
+    vsd[p + ".weight"] = 1 + 0.1 * torch.randn(c, generator=g)
+    vsd[p + ".bias"] = 0.1 * torch.randn(c, generator=g)
+def res(p, ci, co):
+    norm(p + ".norm1", ci); conv(p + ".conv1", co, ci, 3); norm(p + ".norm2", co); conv(p + ".conv2", co, co, 3)
+    if ci != co:
+        conv(p + ".nin_shortcut", co, ci, 1)
+conv("post_quant_conv", 4, 4, 1); conv("decoder.conv_in", 128, 4, 3)
+res("decoder.mid.block_1", 128, 128); res("decoder.mid.block_2", 128, 128)
+norm("decoder.mid.attn_1.norm", 128)
+for n in ("q", "k", "v", "proj_out"):
+    conv("decoder.mid.attn_1." + n, 128, 128, 1)
+res("decoder.up.1.block.0", 128, 128); res("decoder.up.1.block.1", 128, 128); conv("decoder.up.1.upsample.conv", 128, 128, 3)
+res("decoder.up.0.block.0", 128, 64); res("decoder.up.0.block.1", 64, 64)
+norm("decoder.norm_out", 64); conv("decoder.conv_out", 3, 64, 3)
+dec.load_state_dict(vsd)
+img, u8 = dec.decode(torch.randn(2, 4, 16, 16, generator=g).cuda(), images_u8=True)
+torch.cuda.synchronize()
+print(f"vae decode: {tuple(img.shape)} finite={bool(torch.isfinite(img).all())} u8={tuple(u8.shape)}", flush=True)
+print("SANITIZE_SMOKE_DONE", flush=True)
