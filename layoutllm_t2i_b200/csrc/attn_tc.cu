@@ -30,7 +30,10 @@ struct AttnDeviceArgs {
     float scale_log2;
 };
 
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF>
+// PTM: the probabilities P live in tensor memory (tcgen05.st by the softmax threads, A-from-TMEM operand of the PV MMA)
+// instead of a swizzled shared-memory tile: per 128 x 128 score tile that takes 64 KB of shared-memory traffic (32 KB of
+// st.shared + 32 KB of MMA operand reads, half of the tile's total) off the 128 B/clk shared-memory port.
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, bool PTM = false>
 struct AttnCfg {
     static constexpr int NKC = DPAD / 64;           // 64-column chunks of Q / K rows
     static constexpr int KSTEPS = DV / 16;          // k16 steps of QK^T (d rounded up to 16)
@@ -42,11 +45,12 @@ struct AttnCfg {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
     static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
-    static constexpr int OFF_BAR = OFF_P + PBUF * P_BYTES;
+    static constexpr int OFF_BAR = OFF_P + (PTM ? 0 : PBUF * P_BYTES);
     static constexpr int OFF_XCH = OFF_BAR + 256;                 // [4][128] floats: row max / row sum exchange between warpgroups
     static constexpr int TOTAL = OFF_XCH + 2048 + 1024;
-    static constexpr int TM_S = 0, TM_O = SBUF * BKV;
-    static constexpr int TM_USED = SBUF * BKV + DV;
+    static constexpr int TM_S = 0, TM_P = SBUF * BKV;                       // P: BKV / 2 packed columns per buffer
+    static constexpr int TM_O = TM_P + (PTM ? PBUF * BKV / 2 : 0);
+    static constexpr int TM_USED = TM_O + DV;
     static constexpr int TM_COLS = TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
 };
 
@@ -85,9 +89,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // NWG = softmax warpgroups: with 2 the columns of a score tile are split between two threads per query row (half the
 // serial TMEM-load -> exp -> store chain per tile); the pair agrees on the running reference through shared memory.
 // POLY = k > 0: every k-th exponential of a row goes through ex2_poly instead of MUFU.EX2.
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG, int POLY>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG, int POLY, bool PTM>
 __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
-    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
+    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF, PTM>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -182,11 +186,17 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
             mbar_wait(&v_full[st], (j >> 1) & 1);
             mbar_wait(&p_full[pb], (j / PBUF) & 1);
             tc_fence_after();
+            // (issuing QK(j+1) ahead of PV(j) here was measured: 91 -> 104 us at 4096 x 4126 keys -- PV(j) then completes later,
+            // and with it the release of the V stage and of the P buffer the next softmax needs)
 #pragma unroll
             for (int kk = 0; kk < BKV / 16; ++kk) {
-                const uint64_t ad = umma_desc_sw128(sp + pb * C::P_BYTES + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
                 const uint64_t bd = umma_desc_sw128(sv + st * C::V_BYTES + (kk >> 2) * (DV * 128)) + 2 * (kk & 3);
-                umma_f16_elect(tmem_base + C::TM_O, ad, bd, idesc_pv, (j | kk) != 0);
+                if constexpr (PTM) {       // 16 keys = 8 packed columns of the P buffer
+                    umma_f16_ts_elect(tmem_base + C::TM_O, tmem_base + C::TM_P + pb * (BKV / 2) + kk * 8, bd, idesc_pv, (j | kk) != 0);
+                } else {
+                    const uint64_t ad = umma_desc_sw128(sp + pb * C::P_BYTES + (kk >> 2) * (128 * 128)) + 2 * (kk & 3);
+                    umma_f16_elect(tmem_base + C::TM_O, ad, bd, idesc_pv, (j | kk) != 0);
+                }
             }
             umma_commit_elect(bar_base + 8 * (7 + st));      // v_empty[st]
             umma_commit_elect(bar_base + 8 * (15 + pb));     // pv_done[pb]
@@ -216,6 +226,7 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
             const uint32_t ts = trow + C::TM_S + sb * BKV;
             mbar_wait(&s_full[sb], (j / SBUF) & 1);
             tc_fence_after();
+            // (deferring this wait to the first P store of the tile was measured slower: 91 -> 103 us)
             if (j >= PBUF) {
                 mbar_wait(&pv_done[pb], ((j / PBUF) - 1) & 1);      // P[pb] is free again (PBUF == 1: and O is up to date)
                 tc_fence_after();
@@ -239,6 +250,7 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                         if (TAIL && cb + c + i >= kvalid) f[i] = -INFINITY;
                         if (!store) tmax = fmaxf(tmax, f[i]);
                     }
+                    [[maybe_unused]] uint32_t pk[16];      // PTM: the chunk's 32 probabilities as 16 packed half2
                     if (store) {
 #pragma unroll
                         for (int c8 = 0; c8 < 4; ++c8) {
@@ -247,16 +259,23 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                             for (int i = 0; i < 4; ++i) {
                                 const int e0 = c8 * 8 + 2 * i;         // compile-time after unrolling
                                 const float a0 = fmaf(f[e0], sc, nm), a1 = fmaf(f[e0 + 1], sc, nm);
-                                const float p0 = (POLY > 0 && e0 % POLY == 0) ? ex2_poly(a0) : ex2_approx(a0);
-                                const float p1 = (POLY > 0 && (e0 + 1) % POLY == 0) ? ex2_poly(a1) : ex2_approx(a1);
+                                constexpr int PD = POLY > 0 ? POLY : 1;
+                                const float p0 = (POLY > 0 && e0 % PD == 0) ? ex2_poly(a0) : ex2_approx(a0);
+                                const float p1 = (POLY > 0 && (e0 + 1) % PD == 0) ? ex2_poly(a1) : ex2_approx(a1);
                                 rs += p0 + p1;
                                 h[i] = __floats2half2_rn(p0, p1);
                             }
-                            const int g8 = ((cb + c) >> 3) + c8;       // 8-column group inside the tile
-                            const int kc = g8 >> 3, u = g8 & 7;
-                            *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
-                                *reinterpret_cast<uint4*>(h);
+                            if constexpr (PTM) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) pk[c8 * 4 + i] = *reinterpret_cast<uint32_t*>(&h[i]);
+                            } else {
+                                const int g8 = ((cb + c) >> 3) + c8;       // 8-column group inside the tile
+                                const int kc = g8 >> 3, u = g8 & 7;
+                                *reinterpret_cast<uint4*>(sP + kc * (128 * 128) + r * 128 + ((u ^ (r & 7)) << 4)) =
+                                    *reinterpret_cast<uint4*>(h);
+                            }
                         }
+                        if constexpr (PTM) tmem_st16(trow + C::TM_P + pb * (BKV / 2) + ((cb + c) >> 1), pk);
                     }
                 }
                 return rs;
@@ -312,9 +331,10 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                 rs = exp_pass(m_used);
             }
             l += rs;
+            if constexpr (PTM) tmem_st_wait();      // this thread's P columns are in tensor memory
             tc_fence_before();
             mbar_arrive(&s_empty[sb]);
-            fence_async_smem();
+            if constexpr (!PTM) fence_async_smem();
             mbar_arrive(&p_full[pb]);
         }
         mbar_wait(&pv_done[(nt - 1) % PBUF], ((nt - 1) / PBUF) & 1);
@@ -357,20 +377,20 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
     }
 }
 
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1, int POLY = 0>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1, int POLY = 0, bool PTM = false>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
-    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF>;
+    using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF, PTM>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
         if (getenv("LTT_VERBOSE")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, att_threads(NWG), C::TOTAL);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, att_threads(NWG), C::TOTAL);
             fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, PBUF, MINB, C::TOTAL, nb);
         }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -381,7 +401,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     const int rowlen = p.heads * p.dpad;
     int bkv, dv;
     static const int v40 = getenv("LTT_ATTN40") ? atoi(getenv("LTT_ATTN40")) : 0;      // d = 40 variant (experiments)
-    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || v40 == 8 || v40 == 9 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
+    if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || v40 == 8 || v40 == 9 || v40 == 10 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
@@ -427,15 +447,21 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
         if (v40 == 7) return attn_launch_variant<64, 48, 128, 1, 1, 2>(a, grid, stream);
         if (v40 == 8) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);        // 64-key tiles, S and P double buffered, 2 warpgroups
         if (v40 == 9) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2, 8>(a, grid, stream);     // ... + 1/8 software exp2
+        if (v40 == 10) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2, 8, true>(a, grid, stream);    // ... + P in tensor memory
         // default: two softmax warpgroups per CTA, two CTAs per SM (16 softmax warps per SM; measured alternatives at
         // 4096 x 4126 keys: 1 warpgroup 114 us, 2 warpgroups 103 us, 4 warpgroups 111 us, any 1-CTA/SM layout >= 129 us);
         // short key sets (the
         // 77-token text context) use 64-key tiles with S and P double buffered
-        if (bkv == 64) return attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
+        // P in tensor memory (PTM): 4096 x 4126 keys 97.3 -> 91.2 us, 77 keys 9.1 -> 8.1 us; LTT_ATTN_PTM=0: shared-memory P (A/B)
+        static const int ptm = getenv("LTT_ATTN_PTM") ? atoi(getenv("LTT_ATTN_PTM")) : 1;
+        if (bkv == 64) return ptm ? attn_launch_variant<64, 48, 64, 2, 2, 2, 2, 8, true>(a, grid, stream)
+                                  : attn_launch_variant<64, 48, 64, 2, 2, 2, 2>(a, grid, stream);
         // software-exp2 share: every 8th exponential on the FMA / ALU pipes is the measured optimum (4096 x 4126 keys, B=2:
         // none 106.2 us, 1/16 105.5, 1/12 101.8, 1/8 97.6, 1/6 99.8, 1/4 101.5, 1/3 114.6, 1/2 122.6 -- beyond 1/8 the extra
         // nine instructions per element make the softmax warps issue bound); LTT_ATTN_POLY=0 switches it off (A/B)
         static const int poly = getenv("LTT_ATTN_POLY") ? atoi(getenv("LTT_ATTN_POLY")) : 8;
+        if (ptm && poly == 8) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 8, true>(a, grid, stream);
+        if (ptm) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 0, true>(a, grid, stream);
         if (poly == 2) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 2>(a, grid, stream);
         if (poly == 3) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 3>(a, grid, stream);
         if (poly == 4) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 4>(a, grid, stream);
@@ -445,6 +471,10 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
         if (poly == 16) return attn_launch_variant<64, 48, 128, 1, 1, 2, 2, 16>(a, grid, stream);
         return attn_launch_variant<64, 48, 128, 1, 1, 2, 2>(a, grid, stream);
     }
+    // P in tensor memory for the wider heads too: d = 80 13.1 -> 12.3 us (1024 x 1054 keys), d = 160 7.3 -> 6.9 us
+    static const int ptm_all = getenv("LTT_ATTN_PTM") ? atoi(getenv("LTT_ATTN_PTM")) : 1;
+    if (dv == 80 && ptm_all) return attn_launch_variant<128, 80, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
+    if (dv == 160 && ptm_all) return attn_launch_variant<192, 160, 64, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)
                                   : attn_launch_variant<128, 80, 128, 2, 2, 1>(a, grid, stream);
     if (dv == 160) return vwg == 2 ? attn_launch_variant<192, 160, 64, 2, 2, 1, 2>(a, grid, stream)
