@@ -37,8 +37,6 @@ int rela_pool_launch(const float* hid, const __half* x16, const RowStatSrc& stat
 int rela_scatter_launch(const float* hid, const RowStatSrc& stats, const float* gamma3, const float* beta3, const __half* x,
                         const __half* feats, const int* rects, int nb_feats, int B, int mo, int h, int w, int C, float* out,
                         const float* gamma, const float* beta, float eps, __half* ln16, cudaStream_t st);
-int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
-                          int pitch_v, int B, int mo, int C, cudaStream_t st);
 int rela_fold_launch(const __half* wq, const __half* wo, const __half* kv, int G, int nrel, int heads, int d, float scale,
                      __half* A, __half* Bm, cudaStream_t st);
 int rela_attn_fused_launch(const __half* feats, int G, int rows_per_g, int C, int heads, int nrel, const __half* A,

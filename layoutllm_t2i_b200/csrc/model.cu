@@ -161,7 +161,6 @@ struct ltt_model {
     void* tune_touch = nullptr;
     float2* rstats[2] = {nullptr, nullptr};   // row-statistics slots [rows][GEMM_STATS_LD] written by GEMM epilogues (ping-pong)
     __half* xh16 = nullptr;           // fp16 copy of the fp32 residual stream (LayerNorm-fold operand of the last feed-forward)
-    float2* cond_stats = nullptr;
     // per-kernel-class CUDA-event profile (ltt_profile_enable / ltt_profile_report)
     // prof_mode 1: eager launches, every class launch bracketed by events.  prof_mode 2: the brackets are external
     // event-record nodes INSIDE the captured CUDA graph of the evaluation (the mode the timed path runs in); a record then
@@ -1153,15 +1152,13 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     {
         int h = H, w = W, ch = mc;
         std::vector<int> sch;
-        auto visit = [&](const std::vector<Layer>& ls, int extra) {
-            int cin_extra = extra;
+        auto visit = [&](const std::vector<Layer>& ls) {
             for (auto& L : ls) {
                 if (L.kind == L_CONV_IN) ch = mc;
                 else if (L.kind == L_RES) {
                     const ResW& r = m->res[L.idx];
                     max_norm = std::max(max_norm, (size_t)B * h * w * std::max(r.cin, r.cout));
                     ch = r.cout;
-                    cin_extra = 0;
                 } else if (L.kind == L_ST) {
                     StW& s = m->st[L.idx];
                     s.rows_k = (h * w + mo + 63) / 64 * 64;
@@ -1179,16 +1176,15 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
                 }
                 max_act = std::max(max_act, (size_t)B * h * w * ch);
             }
-            (void)cin_extra;
         };
         for (auto& ls : m->in_blocks) {
-            visit(ls, 0);
+            visit(ls);
             __half* s;
             RC(A(&s, (size_t)B * h * w * ch * 2));
             m->skips.push_back(s);
         }
-        visit(m->mid, 0);
-        for (auto& ls : m->out_blocks) visit(ls, 0);
+        visit(m->mid);
+        for (auto& ls : m->out_blocks) visit(ls);
     }
     RC(A(&m->act0, max_act * 2));
     RC(A(&m->act1, max_act * 2));
@@ -1202,7 +1198,6 @@ static int setup_workspace(ltt_model* m, int B, int H, int W, int ctx_len, int n
     RC(A(&m->row_stats, (size_t)B * H * W * sizeof(float2)));
     for (int i = 0; i < 2; ++i) RC(A(&m->rstats[i], (size_t)B * H * W * GEMM_STATS_LD * sizeof(float2)));
     RC(A(&m->xh16, max_tok * 2));
-    RC(A(&m->cond_stats, (size_t)B * mo * sizeof(float2)));
     RC(A(&m->xe32, max_tok * 4));
     RC(A(&m->xf32, max_tok * 4));
     const size_t fe = (size_t)B * mo * maxC;

@@ -147,7 +147,6 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 // statistics buffer, no memset node between the producer GEMM and the consumer (the PDL chain stays intact).
 constexpr int GN_S = 8;          // CTAs per cluster (pixel split)
 constexpr int GN_MAXG = 4;       // groups per cluster
-constexpr int GN_MAXTHREADS = 512;
 
 template <int GN_THREADS>
 __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
@@ -1381,49 +1380,6 @@ __global__ void copy2d_kernel(const __half* __restrict__ src, size_t sb, int sld
         dst[b * db + (size_t)r * dld + c] = src[b * sb + (size_t)r * sld + c];
     }
 }
-// Both strided copies of one gated self-attention layer in ONE launch: the cached grounding-token K rows
-// [B][mo][rowlen] go behind the visual keys of the K buffer and the cached V^T columns [B][C][32] behind the visual
-// columns of the V^T buffer.  blockIdx.y selects the copy.
-__global__ void ground_kv_copy_kernel(const __half* __restrict__ ksrc, __half* __restrict__ kdst, size_t kdb, int rowlen,
-                                      const __half* __restrict__ vsrc, __half* __restrict__ vdst, size_t vdb, int pitch_v,
-                                      int B, int mo, int C) {
-    pdl_launch_dependents();
-    pdl_wait();
-    if (blockIdx.y == 0) {
-        const int vec = rowlen >> 3;                       // 16-byte vectors per K row
-        const size_t total = (size_t)B * mo * vec;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const int cv = (int)(i % vec);
-            const size_t r = i / vec;
-            const int rr = (int)(r % mo);
-            const size_t b = r / mo;
-            reinterpret_cast<uint4*>(kdst + b * kdb + (size_t)rr * rowlen)[cv] =
-                reinterpret_cast<const uint4*>(ksrc + (b * mo + rr) * (size_t)rowlen)[cv];
-        }
-    } else {
-        const size_t total = (size_t)B * C * mo;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            const int c = (int)(i % mo);
-            const size_t r = i / mo;
-            const int rr = (int)(r % C);
-            const size_t b = r / C;
-            vdst[b * vdb + (size_t)rr * pitch_v + c] = vsrc[(b * C + rr) * 32 + c];
-        }
-    }
-}
-int ground_kv_copy_launch(const __half* ksrc, __half* kdst, size_t kdb, int rowlen, const __half* vsrc, __half* vdst, size_t vdb,
-                          int pitch_v, int B, int mo, int C, cudaStream_t st) {
-    if (rowlen % 8 || mo > 32) {
-        set_error("ground_kv_copy: unsupported rowlen=%d mo=%d", rowlen, mo);
-        return -1;
-    }
-    const size_t total = (size_t)B * C * mo;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 4);
-    LTT_CUDA_OK(launch_k(ground_kv_copy_kernel, dim3(blocks, 2), dim3(256), 0, st, ksrc, kdst, kdb, rowlen, vsrc, vdst, vdb, pitch_v, B, mo, C));
-    LTT_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 int copy2d_launch(const __half* src, size_t sb, int sld, __half* dst, size_t db, int dld, int B, int rows, int cols,
                   cudaStream_t st) {
     const size_t total = (size_t)B * rows * cols;
