@@ -32,6 +32,13 @@ constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 #define LTT_EPI_WGS 3
 #endif
 constexpr int EPI_WGS = LTT_EPI_WGS;                          // epilogue warpgroups (the epilogue is latency bound: more warps)
+// Experiment build (-DLTT_LITE=1 -DLTT_EPI_WGS=1): CTAs small enough for TWO per SM (192 threads, <= 96 KB of shared memory,
+// 256 TMEM columns), so that consecutive GEMM launches overlap under PDL; tile widths 64 / 128 only.
+#ifndef LTT_LITE
+#define LTT_LITE 0
+#endif
+constexpr int GEMM_MINB = LTT_LITE ? 2 : 1;
+constexpr int ST64 = LTT_LITE ? 3 : 6, ST128 = LTT_LITE ? 3 : 6, ST160 = LTT_LITE ? 2 : 5, ST256 = LTT_LITE ? 2 : 4;
 constexpr int EPI_THREADS = 128 * EPI_WGS;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;      // TMA warp, MMA warp, epilogue warpgroups
 
@@ -333,7 +340,7 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
 // LNF: the LayerNorm-fold features (row statistics out, fp16 copy of an fp32 output, folded-LayerNorm consumer); the plain
 // variant carries none of that code.
 template <int BN, int STAGES, bool PAIR, bool LNF>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_MINB) gemm_tc_kernel(const __grid_constant__ GemmDeviceArgs args) {
     using SM = GemmSmem<BN, STAGES>;
     constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
@@ -908,7 +915,7 @@ struct Variant {
         if (int rc = configure()) return rc;
         a.splits = S;
         if (S == 1) {
-            const int grid = ctas < num_sms ? ctas : num_sms;
+            const int grid = ctas < num_sms * GEMM_MINB ? ctas : num_sms * GEMM_MINB;
             if (lnf(a)) LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false, true>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
             else LTT_CUDA_OK(launch_k(gemm_tc_kernel<BN, STAGES, false, false>, dim3(grid), dim3(GEMM_THREADS), SM::TOTAL, stream, a));
         } else {
@@ -995,6 +1002,7 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
     for (int bi = 0; bi < 4; ++bi) {
         const int bn = kBN[bi];
         if (geglu && bn % 128) continue;
+        if (LTT_LITE && bn > 128) continue;
         if (forced && bn != p.force_bn) continue;
         if (!forced && force_bn && bn != force_bn && !(geglu && force_bn % 128)) continue;
         const int nt = (p.N + bn - 1) / bn;
@@ -1006,9 +1014,9 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
         if (forced ? (p.force_pair && mtiles >= 2 && bn >= 128) : (pair_mode && mtiles >= 2 && (iters >= 10 || pair_mode == 2) && bn >= 128)) {
             int mc = 0;
             switch (bn) {
-                case 128: mc = Variant<128, 6>::max_clusters(2); break;
-                case 160: mc = Variant<160, 5>::max_clusters(2); break;
-                default: mc = Variant<256, 4>::max_clusters(2); break;
+                case 128: mc = Variant<128, ST128>::max_clusters(2); break;
+                case 160: mc = Variant<160, ST160>::max_clusters(2); break;
+                default: mc = Variant<256, ST256>::max_clusters(2); break;
             }
             const int cu = ((mtiles + 1) / 2) * nt;
             // measured: the pair only pays once every CTA walks several tiles (cluster sync + remote barriers cost ~1.5 us)
@@ -1036,10 +1044,10 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
                 if ((iters + per - 1) / per != sp) continue;      // every rank must own at least one iteration
                 int mc = 0;
                 switch (bn) {
-                    case 64: mc = Variant<64, 6>::max_clusters(sp); break;
-                    case 128: mc = Variant<128, 6>::max_clusters(sp); break;
-                    case 160: mc = Variant<160, 5>::max_clusters(sp); break;
-                    default: mc = Variant<256, 4>::max_clusters(sp); break;
+                    case 64: mc = Variant<64, ST64>::max_clusters(sp); break;
+                    case 128: mc = Variant<128, ST128>::max_clusters(sp); break;
+                    case 160: mc = Variant<160, ST160>::max_clusters(sp); break;
+                    default: mc = Variant<256, ST256>::max_clusters(sp); break;
                 }
                 if (mc < ctas_c) continue;                         // all clusters of the launch must be co-resident
                 if (want_stats && nt * sp * EPI_WGS > p.epi.stats_ld) continue;
@@ -1087,16 +1095,16 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
     if (use_pair) {
         const int cu = ((mtiles + 1) / 2) * ntiles;
         switch (BN) {
-            case 128: return Variant<128, 6>::launch_pair(a, cu, stream);
-            case 160: return Variant<160, 5>::launch_pair(a, cu, stream);
-            default: return Variant<256, 4>::launch_pair(a, cu, stream);
+            case 128: return Variant<128, ST128>::launch_pair(a, cu, stream);
+            case 160: return Variant<160, ST160>::launch_pair(a, cu, stream);
+            default: return Variant<256, ST256>::launch_pair(a, cu, stream);
         }
     }
     switch (BN) {
-        case 64: return Variant<64, 6>::launch(a, ctas, S, num_sms, stream);
-        case 128: return Variant<128, 6>::launch(a, ctas, S, num_sms, stream);
-        case 160: return Variant<160, 5>::launch(a, ctas, S, num_sms, stream);
-        case 256: return Variant<256, 4>::launch(a, ctas, S, num_sms, stream);
+        case 64: return Variant<64, ST64>::launch(a, ctas, S, num_sms, stream);
+        case 128: return Variant<128, ST128>::launch(a, ctas, S, num_sms, stream);
+        case 160: return Variant<160, ST160>::launch(a, ctas, S, num_sms, stream);
+        case 256: return Variant<256, ST256>::launch(a, ctas, S, num_sms, stream);
     }
     set_error("gemm: no kernel variant for BN=%d", BN);
     return -1;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small end-to-end workload for `compute-sanitizer` (tests/test_sanitizer_gpu.py): a tiny UNet [cond ; uncond] forward at
-both gate values, a 3-step fused PLMS loop (CUDA-graph replay included) and a small VAE decode, all through the C-ABI.
+both gate values, a 5-step fused PLMS loop (CUDA-graph replay included) and a small VAE decode, all through the C-ABI.
 Prints one line per stage; any kernel fault surfaces as a sanitizer error."""
 import os
 import sys
@@ -22,13 +22,13 @@ for scale in (1.0, 0.0):
     ec, eu = mc.engine_eps_pair(e, syn, 981, scale, 16, 16)
     torch.cuda.synchronize()
     print(f"forward gate {scale}: finite={bool(torch.isfinite(ec).all() and torch.isfinite(eu).all())}", flush=True)
-ts, a_t, a_prev, s1m = po.plms_tables(3, po.alphas_cumprod())
+ts, a_t, a_prev, s1m = po.plms_tables(5, po.alphas_cumprod())
 ctx, relations = mc.cfg_batch(syn, 2)
 e.set_conditioning(ctx, relations, syn["grounding"], 16, 16)
 for _ in range(2):          # second call replays the captured graphs
-    out = e.plms_sample(syn["x"], ts, a_t, a_prev, s1m, [1, 1, 0], 7.5, None)
+    out = e.plms_sample(syn["x"], ts, a_t, a_prev, s1m, [1, 1, 0, 0, 0], 7.5, None)
 torch.cuda.synchronize()
-print(f"plms 3 steps x2: finite={bool(torch.isfinite(out).all())}", flush=True)
+print(f"plms 5 steps x2: finite={bool(torch.isfinite(out).all())}", flush=True)
 g = torch.Generator().manual_seed(0)
 dec = VaeDecoder(dict(ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=4, embed_dim=4, scale_factor=0.18215), 0)
 vsd = {}
