@@ -145,7 +145,8 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 // pixel column, then double across threads, then double across the cluster through distributed shared memory in fixed
 // rank order (deterministic).  Pass 2 normalises from the staged copy.  One read + one write of the tensor, no
 // statistics buffer, no memset node between the producer GEMM and the consumer (the PDL chain stays intact).
-constexpr int GN_S = 8;          // CTAs per cluster (pixel split)
+constexpr int GN_S = 8;          // CTAs per cluster (pixel split); 16 (non-portable cluster size) for small batches, see the launcher
+constexpr int GN_SMAX = 16;
 constexpr int GN_MAXG = 4;       // groups per cluster
 
 template <int GN_THREADS>
@@ -153,13 +154,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     const __half* __restrict__ x0, int c0, int ld0, const __half* __restrict__ x1, int ld1, int C, int HW, int cpg, int G,
     int V, int R, int px_per_cta, int stage, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
     int silu, __half* __restrict__ out) {
+    const int S = gridDim.x;                           // CTAs of this cluster (8 or 16)
     pdl_launch_dependents();
     extern __shared__ uint4 gn_slab[];                 // [px_per_cta][V] when stage
     __shared__ float part[GN_THREADS * 8];             // per-thread (sum, sumsq) of its 4 channel pairs
     __shared__ float2 sub2[GN_THREADS];                // second-level partial sums
     __shared__ double colsum[GN_THREADS * 2];          // [V*4 pair columns][2]  (V <= GN_THREADS/4 by host check)
     __shared__ double cta_stats[2 * GN_MAXG];          // this CTA's (sum, sumsq) per group -- read by the whole cluster
-    __shared__ double all_stats[2 * GN_MAXG * GN_S];   // every rank's cta_stats, gathered through DSMEM
+    __shared__ double all_stats[2 * GN_MAXG * GN_SMAX];   // every rank's cta_stats, gathered through DSMEM
     __shared__ float2 mr[GN_MAXG];
     const int tid = threadIdx.x;
     const int rank = blockIdx.x;                       // cluster dims (GN_S,1,1), gridDim.x == GN_S
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
         cta_stats[tid] = a;
     }
     cluster_sync_all();                                // every CTA's cta_stats is complete and visible
-    if (tid < 2 * GN_MAXG * GN_S) {                    // one remote load per thread, all in flight together
+    if (tid < 2 * GN_MAXG * S) {                       // one remote load per thread, all in flight together
         const int rk = tid / (2 * GN_MAXG), e = tid % (2 * GN_MAXG);
         all_stats[tid] = e < 2 * G ? dsmem_ld_f64(dsmem_map(smem_u32(&cta_stats[e]), rk)) : 0.0;
     }
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
     __syncthreads();
     if (tid < G) {
         double sm = 0.0, sq = 0.0;
-        for (int rk = 0; rk < GN_S; ++rk) {            // fixed rank order: deterministic
+        for (int rk = 0; rk < S; ++rk) {               // fixed rank order: deterministic
             sm += all_stats[rk * 2 * GN_MAXG + 2 * tid];
             sq += all_stats[rk * 2 * GN_MAXG + 2 * tid + 1];
         }
@@ -328,7 +330,12 @@ int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, 
         if ((g * cpg) % 8 == 0 && (G == 0 || GN_S * B * (32 / g) >= 128)) G = g;
     if (G == 0) return 1;
     const int V = G * cpg / 8;
-    const int px = (HW + GN_S - 1) / GN_S;
+    // 16 CTAs per cluster (non-portable size) halve both passes over the slab, but the wider cluster barrier / gang launch
+    // costs more than that saves: measured at B = 2 (one image): 4096 x 320: 9.9 -> 11.8 us, 1024 x 640: 6.7 -> 9.6 us, only
+    // the 960-channel concat gains (23.2 -> 19.0 us); 270.9 -> 273.6 ms per image.  Off by default (LTT_GN_S16=1: A/B).
+    static const int s16 = getenv("LTT_GN_S16") ? atoi(getenv("LTT_GN_S16")) : 0;
+    const int S = (s16 && HW >= 1024 && 16 * B * (32 / G) <= 296) ? 16 : GN_S;
+    const int px = (HW + S - 1) / S;
     const size_t slab = (size_t)px * V * 16;
     // big slabs (level-0 concat inputs) own their SM anyway: 16 warps hide the load / MUFU latency better than 8
     const int threads = slab > 96 * 1024 ? 512 : 256;
@@ -339,17 +346,19 @@ int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, 
     if (!configured) {
         LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        LTT_CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel<512>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(GN_S, 32 / G, B);
+    cfg.gridDim = dim3(S, 32 / G, B);
     cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = stage ? slab : 0;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = GN_S;
+    at[0].val.clusterDim.x = S;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -114,6 +114,13 @@ if only == "small":
     bench_ln(8192, 320, torch.float32)
     for d in (40, 80, 160):
         bench_small_attn(1, d)
+if only == "norms":      # memory-bound kernels across batch sizes (B = 2 is one image's [cond ; uncond] pair)
+    for B in (2, 16, 128):
+        for HW, c0, c1 in ((4096, 320, 0), (4096, 640, 320), (1024, 640, 0), (256, 1280, 0)):
+            bench_gn(B, HW, c0, c1)
+        for N, C in ((4096, 320), (1024, 640), (256, 1280)):
+            bench_ln(B * N, C)
+        bench_ln(B * 4096, 320, torch.float32)
 if not only or only == "linear":
     for M, C in ((8192, 320), (2048, 640), (512, 1280), (128, 1280)):
         bench_linear(M, C, C)                 # proj / to_out
