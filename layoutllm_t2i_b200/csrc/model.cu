@@ -676,7 +676,9 @@ struct Run {
         if (m->autotune) {
             const std::string key = tune_key(p);
             auto it = tuned_table().find(key);
-            if (it == tuned_table().end() && m->tuning && !m->capturing) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (m->tuning && cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+            if (it == tuned_table().end() && m->tuning && !m->capturing && cap == cudaStreamCaptureStatusNone) {
                 RC(tune_gemm(m, p, key, st));
                 it = tuned_table().find(key);
             }
