@@ -595,18 +595,22 @@ static int tune_gemm(ltt_model* m, GemmProblem& p, const std::string& key, cudaS
         LTT_CUDA_OK(cudaMalloc(&m->tune_flush, TUNE_FLUSH_BYTES));
         LTT_CUDA_OK(cudaMalloc(&m->tune_touch, (size_t)64 << 20));
     }
-    cudaEvent_t e0, e1;
-    LTT_CUDA_OK(cudaEventCreate(&e0));
-    LTT_CUDA_OK(cudaEventCreate(&e1));
-    static const int kBN[4] = {64, 128, 160, 256};
-    TuneCfg best{0, 1, 0};
-    float best_t = 1e30f, model_t = 1e30f;
-    int rc_final = 0;
     // the cycle model's own choice: kept unless a measured alternative is clearly (> 4 %, well above the ~0.5 us event
     // resolution on these 10-50 us launches) faster
     int model_cfg[3] = {0, 1, 0};
     p.force_bn = 0;
     if (int rc = gemm_tc_launch(p, m->sms, st, nullptr, model_cfg)) return rc;
+    cudaEvent_t e0, e1;
+    LTT_CUDA_OK(cudaEventCreate(&e0));
+    if (cudaEventCreate(&e1) != cudaSuccess) {
+        cudaEventDestroy(e0);
+        set_error("autotune: cudaEventCreate failed");
+        return -2;
+    }
+    static const int kBN[4] = {64, 128, 160, 256};
+    TuneCfg best{0, 1, 0};
+    float best_t = 1e30f, model_t = 1e30f;
+    int rc_final = 0;
     for (int bi = 0; bi < 4 && !rc_final; ++bi) {
         for (int mode = 0; mode <= 8 && !rc_final; ++mode) {      // 0: CTA pair, 1..8: split-K cluster size
             p.force_bn = kBN[bi];
