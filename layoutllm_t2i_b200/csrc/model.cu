@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -581,6 +582,17 @@ static std::map<std::string, TuneCfg>& tuned_table() {
     static std::map<std::string, TuneCfg> t;
     return t;
 }
+static std::mutex& tuned_mutex() {       // handles are single-threaded, the table is shared by all handles of the process
+    static std::mutex mu;
+    return mu;
+}
+static bool tuned_lookup(const std::string& key, TuneCfg* out) {
+    std::lock_guard<std::mutex> lk(tuned_mutex());
+    auto it = tuned_table().find(key);
+    if (it == tuned_table().end()) return false;
+    *out = it->second;
+    return true;
+}
 static std::string tune_key(const GemmProblem& p) {
     char buf[160];
     const GemmEpilogue& e = p.epi;
@@ -651,7 +663,10 @@ static int tune_gemm(ltt_model* m, GemmProblem& p, const std::string& key, cudaS
         return 0;          // nothing legal was timed: leave the choice to the cycle model
     }
     if (model_t < 1e30f && best_t > 0.96f * model_t) best = TuneCfg{model_cfg[0], model_cfg[1], model_cfg[2]};
-    tuned_table()[key] = best;
+    {
+        std::lock_guard<std::mutex> lk(tuned_mutex());
+        tuned_table()[key] = best;
+    }
     if (getenv("LTT_VERBOSE")) fprintf(stderr, "[ltt] tuned %s -> BN %d splits %d pair %d (%.1f us)\n", key.c_str(), best.bn, best.splits, best.pair, best_t * 1e3f);
     return 0;
 }
@@ -679,15 +694,16 @@ struct Run {
         if (!p.epi.bias) p.epi.bias = w.bias;
         if (m->autotune) {
             const std::string key = tune_key(p);
-            auto it = tuned_table().find(key);
+            TuneCfg tc{0, 1, 0};
+            bool have = tuned_lookup(key, &tc);
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
             if (m->tuning && cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
-            if (it == tuned_table().end() && m->tuning && !m->capturing && cap == cudaStreamCaptureStatusNone) {
+            if (!have && m->tuning && !m->capturing && cap == cudaStreamCaptureStatusNone) {
                 RC(tune_gemm(m, p, key, st));
-                it = tuned_table().find(key);
+                have = tuned_lookup(key, &tc);
             }
-            if (it != tuned_table().end()) {
-                p.force_bn = it->second.bn; p.force_splits = it->second.splits; p.force_pair = it->second.pair;
+            if (have) {
+                p.force_bn = tc.bn; p.force_splits = tc.splits; p.force_pair = tc.pair;
             } else {
                 p.force_bn = 0;
             }
