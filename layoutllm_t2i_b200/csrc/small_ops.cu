@@ -147,7 +147,7 @@ int gn_apply_launch(const __half* x0, int c0, int ld0, const __half* x1, int c1,
 // statistics buffer, no memset node between the producer GEMM and the consumer (the PDL chain stays intact).
 constexpr int GN_S = 8;          // CTAs per cluster (pixel split); 16 (non-portable cluster size) for small batches, see the launcher
 constexpr int GN_SMAX = 16;
-constexpr int GN_MAXG = 4;       // groups per cluster
+constexpr int GN_MAXG = 32;      // groups per cluster the kernel supports (the launcher picks <= its own limit)
 
 template <int GN_THREADS>
 __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
@@ -247,9 +247,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_fused_kernel(
         cta_stats[tid] = a;
     }
     cluster_sync_all();                                // every CTA's cta_stats is complete and visible
-    if (tid < 2 * GN_MAXG * S) {                       // one remote load per thread, all in flight together
-        const int rk = tid / (2 * GN_MAXG), e = tid % (2 * GN_MAXG);
-        all_stats[tid] = e < 2 * G ? dsmem_ld_f64(dsmem_map(smem_u32(&cta_stats[e]), rk)) : 0.0;
+    for (int i = tid; i < 2 * G * S; i += GN_THREADS) {     // remote loads, all in flight together
+        const int rk = i / (2 * G), e = i % (2 * G);
+        all_stats[rk * 2 * GN_MAXG + e] = dsmem_ld_f64(dsmem_map(smem_u32(&cta_stats[e]), rk));
     }
     cluster_arrive();                                  // done reading peers; matching wait at the end
     __syncthreads();
@@ -326,8 +326,12 @@ int groupnorm_fused_launch(const __half* x0, int c0, int ld0, const __half* x1, 
     if ((cpg & 1) || c0 % 8 || ld0 % 8 || (c1 && ld1 % 8)) return 1;
     // groups per cluster: the slab must be whole 16-byte vectors; fewer groups per cluster = more CTAs for small batches
     int G = 0;
-    for (int g = 1; g <= GN_MAXG; g *= 2)
-        if ((g * cpg) % 8 == 0 && (G == 0 || GN_S * B * (32 / g) >= 128)) G = g;
+    // groups per cluster: more groups = wider contiguous row segments per CTA (cpg * G channels), fewer clusters.  The
+    // limit only matters once there are >= 128 CTAs anyway (B >= 16 per launch): measured 4 -> 8: 16x4096x320 40.2 -> 36.3 us,
+    // 16x256x1280 20.0 -> 13.3 us, 128x1024x640 215 -> 159 us, unchanged at B = 2; 16 / 32 are mixed (profiles/r02_gn_ab.txt)
+    static const int maxg = getenv("LTT_GN_MAXG") ? atoi(getenv("LTT_GN_MAXG")) : 8;
+    for (int g = 1; g <= std::min(maxg, GN_MAXG); g *= 2)
+        if ((g * cpg) % 8 == 0 && g * cpg / 8 <= 64 && (G == 0 || GN_S * B * (32 / g) >= 128)) G = g;
     if (G == 0) return 1;
     const int V = G * cpg / 8;
     // 16 CTAs per cluster (non-portable size) halve both passes over the slab, but the wider cluster barrier / gang launch
