@@ -470,11 +470,160 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int M, int C, const fl
     }
 }
 
+// Many rows (batch >= 8 images): the one-row-per-warp kernel re-reads gamma / beta (64 B of L1 traffic per 16 B of data) for
+// every row and keeps one row per warp in flight; here a warp holds its lanes' gamma / beta in registers and walks rows with a
+// grid stride, D rows ahead of the one being reduced held as RAW 16-byte vectors (fp16 rows are 640 B at C = 320: the bytes
+// in flight per SM, not the arithmetic, set the rate).  NV = vectors per lane (C <= 256*NV).
+template <typename T>
+struct LnRaw;
+template <>
+struct LnRaw<__half> {
+    uint4 a;
+    __device__ __forceinline__ void load(const __half* p) { a = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+};
+template <>
+struct LnRaw<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = *reinterpret_cast<const float4*>(p);
+        b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+template <typename T, int NV, int D>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const T* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, __half* __restrict__ out16,
+                                                              float* __restrict__ out32) {
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 3;
+    float g[NV][8], bt[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int j = i * 32 + lane;
+        if (j < nvec) {
+            ln_load8<float>(gamma + j * 8, g[i]);
+            ln_load8<float>(beta + j * 8, bt[i]);
+        }
+    }
+    pdl_wait();
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    const int row0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    LnRaw<T> ring[D][NV];
+    auto load_row = [&](int r, LnRaw<T> (&dst)[NV]) {
+        const T* xr = x + (size_t)r * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = i * 32 + lane;
+            if (j < nvec) dst[i].load(xr + j * 8);
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        if (row0 + d * wstride < M) load_row(row0 + d * wstride, ring[d]);
+    for (int base = row0; base < M; base += D * wstride) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int row = base + d * wstride;
+            if (row >= M) break;
+            float v[NV][8];
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i * 32 + lane < nvec) ring[d][i].unpack(v[i]);
+            if (row + D * wstride < M) load_row(row + D * wstride, ring[d]);      // in flight during D rows of arithmetic
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i * 32 + lane < nvec) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s += v[i][k];
+                }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s / C;
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i * 32 + lane < nvec) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dd = v[i][k] - mean;
+                        ss += dd * dd;
+                    }
+                }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float rstd = rsqrtf(ss / C + eps);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = i * 32 + lane;
+                if (j < nvec) {
+                    float y[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y[k] = (v[i][k] - mean) * rstd * g[i][k] + bt[i][k];     // same expression as layernorm_kernel
+                    if (out16) {
+                        __half2 h[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(y[2 * k], y[2 * k + 1]);
+                        *reinterpret_cast<uint4*>(out16 + (size_t)row * C + j * 8) = *reinterpret_cast<uint4*>(h);
+                    }
+                    if (out32) {
+                        float4* o = reinterpret_cast<float4*>(out32 + (size_t)row * C + j * 8);
+                        o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                        o[1] = make_float4(y[4], y[5], y[6], y[7]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int NV>
+static int layernorm_rows_go(const T* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out16, float* out32,
+                             cudaStream_t st) {
+    static int resident = 0;                   // CTAs per SM of this instantiation: the grid is exactly one resident wave
+    if (!resident) {
+        int n = 0;
+        LTT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_rows_kernel<T, NV, (sizeof(T) == 2 ? 4 : 2)>, 256, 0));
+        resident = n > 0 ? n : 1;
+    }
+    LTT_CUDA_OK(launch_k(layernorm_rows_kernel<T, NV, (sizeof(T) == 2 ? 4 : 2)>, dim3(148 * resident), dim3(256), 0, st, x, M, C, gamma, beta, eps, out16, out32));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int layernorm_rows_launch(const T* x, int M, int C, const float* gamma, const float* beta, float eps, __half* out16,
+                                 float* out32, cudaStream_t st) {
+    const int nvec = C >> 3;
+    if (nvec <= 32) return layernorm_rows_go<T, 1>(x, M, C, gamma, beta, eps, out16, out32, st);
+    if (nvec <= 64) return layernorm_rows_go<T, 2>(x, M, C, gamma, beta, eps, out16, out32, st);
+    return layernorm_rows_go<T, 3>(x, M, C, gamma, beta, eps, out16, out32, st);
+}
+
 int layernorm_launch(const void* x, int x_dtype, int M, int C, const float* gamma, const float* beta, float eps,
                      __half* out16, float* out32, cudaStream_t st, float2* stats_out) {
     if (C % 8 || C > 1280) {
         set_error("layernorm: unsupported C=%d", C);
         return -1;
+    }
+    // rows >> resident warps and C <= 768: the grid-stride variant (LTT_LN_ROWS=0: always one row per warp, A/B)
+    static const int rows_variant = getenv("LTT_LN_ROWS") ? atoi(getenv("LTT_LN_ROWS")) : 1;
+    if (rows_variant && !stats_out && C <= 768 && M >= 16384) {
+        if (x_dtype == DT_F16) return layernorm_rows_launch((const __half*)x, M, C, gamma, beta, eps, out16, out32, st);
+        return layernorm_rows_launch((const float*)x, M, C, gamma, beta, eps, out16, out32, st);
     }
     const int wpb = 8;
     const int blocks = (M + wpb - 1) / wpb;

@@ -446,6 +446,11 @@ ALL = [
     ("layernorm f16 4096x320", check_layernorm, dict(M=4096, C=320, dtype=torch.float16), 1e-4),
     ("layernorm f32 1000x1280", check_layernorm, dict(M=1000, C=1280, dtype=torch.float32), 1e-4),
     ("layernorm f16 90x64", check_layernorm, dict(M=90, C=64, dtype=torch.float16), 1e-4),
+    # M >= 16384 and C <= 768: the grid-stride variant (1, 2 and 3 vectors per lane; ragged last vector; odd row count)
+    ("layernorm rows f16 65536x320", check_layernorm, dict(M=65536, C=320, dtype=torch.float16), 1e-4),
+    ("layernorm rows f32 32771x320", check_layernorm, dict(M=32771, C=320, dtype=torch.float32), 1e-4),
+    ("layernorm rows f16 16384x640", check_layernorm, dict(M=16384, C=640, dtype=torch.float16), 1e-4),
+    ("layernorm rows f16 20001x64", check_layernorm, dict(M=20001, C=64, dtype=torch.float16), 1e-4),
     ("LayerNorm fold 4096x320 -> QKV-like 960", check_ln_fold, dict(M=4096, K1=320, C=320, N=960), 2e-3),
     ("LayerNorm fold 4096x320 -> GEGLU 2560", check_ln_fold, dict(M=4096, K1=320, C=320, N=2560, act2=2), 2e-3),
     ("LayerNorm fold 1000x640 (K1 2560, tail rows) -> 1920", check_ln_fold, dict(M=1000, K1=2560, C=640, N=1920), 2e-3),
