@@ -1,0 +1,69 @@
+"""oracle/clip_text_oracle.py against the third-party implementation the reference calls (fixtures made by
+tests/gen_golden_clip.py from the installed `transformers`), and the properties the batched conditioning pass rests on."""
+import os
+
+import pytest
+import torch
+
+from oracle import clip_text_oracle as co
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "clip_text.pt")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_eos"])
+def test_oracle_matches_transformers_fixture(name):
+    g = torch.load(GOLD)[name]
+    sd = co.random_state_dict(g["cfg"], seed=g["seed"], outliers=True)
+    for tag, c in g["cases"].items():
+        with torch.no_grad():
+            z, pooled = co.clip_text_forward(sd, g["cfg"], c["ids"], c["mask"])
+            emb = co.text_features(sd, g["cfg"], c["ids"], c["mask"])
+        assert rel(z, c["last_hidden_state"]) < 2e-6, tag
+        assert rel(pooled, c["pooler_output"]) < 2e-6, tag
+        assert rel(emb, c["text_embeds"]) < 2e-6, tag
+
+
+def test_oracle_matches_transformers_live():
+    pytest.importorskip("transformers")
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from gen_golden_clip import hf_text_model
+    cfg = co.tiny_clip_text_config()
+    sd = co.random_state_dict(cfg, seed=11)
+    m, _ = hf_text_model(cfg, sd)
+    ids = co.synthetic_ids(cfg, [4, 9, 0], seed=5)
+    with torch.no_grad():
+        o = m(input_ids=ids)
+        z, pooled = co.clip_text_forward(sd, cfg, ids)
+    assert rel(z, o.last_hidden_state) < 2e-6 and rel(pooled, o.pooler_output) < 2e-6
+
+
+def test_batched_padded_pass_equals_per_phrase_calls():
+    """Causal attention: rows up to the end-of-text token do not see the padding behind it, so ONE pass over phrases
+    padded to 77 tokens (no attention mask) returns the pooled vectors of the reference's per-phrase unpadded calls
+    (txt2img.py:147-156, modules.py:174-182) and of a masked padded batch (txt2img.py:454-457)."""
+    cfg = co.tiny_clip_text_config()
+    sd = co.random_state_dict(cfg, seed=2)
+    words = [1, 3, 8, 20, 75]
+    ids = co.synthetic_ids(cfg, words, seed=9)
+    with torch.no_grad():
+        _, pooled = co.clip_text_forward(sd, cfg, ids)
+        mask = torch.zeros_like(ids)
+        for r, n in enumerate(words):
+            mask[r, :n + 2] = 1
+        _, pooled_masked = co.clip_text_forward(sd, cfg, ids, mask)
+        for r, n in enumerate(words):
+            _, one = co.clip_text_forward(sd, cfg, ids[r:r + 1, :n + 2])
+            assert rel(pooled[r:r + 1], one) < 1e-5
+    assert rel(pooled, pooled_masked) < 1e-5
+
+
+def test_eos_position_rules():
+    ids = torch.tensor([[998, 5, 999, 999], [998, 999, 0, 0]])
+    assert co.eos_positions(ids, 2).tolist() == [2, 1]
+    assert co.eos_positions(ids, 999).tolist() == [2, 1]
+    assert co.eos_positions(torch.tensor([[998, 7, 3, 999]]), 999).tolist() == [3]
