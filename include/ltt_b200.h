@@ -140,6 +140,39 @@ int ltt_vae_decode(ltt_vae* v, const float* z, int B, int h, int w, float* img_f
 int64_t ltt_vae_launch_count(const ltt_vae* v);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Conditioning prep: the CLIP text tower  (replaces the per-string calls of
+ * ldm.modules.encoders.modules.FrozenCLIPEmbedder.forward / encode_one_token, modules.py:157-182 -- transformers
+ * CLIPTextModel -- and of txt2img.get_clip_feature / extract_text_feat, txt2img.py:147-156,454-457 -- transformers
+ * CLIPModel text tower -- by ONE batched pass over prompt, negative prompt, box phrases and relation phrases)
+ * -------------------------------------------------------------------------------------------------------------- */
+typedef struct ltt_clip ltt_clip;
+
+/* transformers CLIPTextConfig fields (openai/clip-vit-large-patch14: 49408, 77, 768, 12, 12, 3072, 1e-5, quick_gelu,
+ * projection 768, eos_token_id 2).  hidden / heads must be 64; hidden and ffn multiples of 64; act: 0 = quick_gelu. */
+typedef struct {
+    int vocab, max_pos, hidden, heads, layers, ffn;
+    float eps;
+    int act;
+    int proj_dim;       /* 0: no text_projection (CLIPTextModel); > 0: CLIPModel.text_projection rows */
+    int eos_token_id;   /* 2: pooled row = argmax(ids) (legacy config); otherwise first position holding this id */
+} ltt_clip_config;
+
+int ltt_clip_create(const ltt_clip_config* cfg, int device, ltt_clip** out);
+void ltt_clip_destroy(ltt_clip* c);
+/* state_dict keys of transformers CLIPTextModel ("text_model.embeddings.token_embedding.weight",
+ * "text_model.encoder.layers.3.self_attn.q_proj.bias", ..., "text_model.final_layer_norm.weight") and, for proj_dim > 0,
+ * CLIPModel's "text_projection.weight"; fp32 device or host pointers. */
+int ltt_clip_load_param(ltt_clip* c, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
+int ltt_clip_finalize(ltt_clip* c);
+/* ids [B, L] int32 on the device, L <= max_pos, rows laid out by CLIPTokenizer (<bos> ... <eos> padding); attention is
+ * causal with NO padding mask (what FrozenCLIPEmbedder does; rows up to <eos> -- hence the pooled vector -- are the
+ * same with one).  Outputs, fp32 device, each may be NULL: last_hidden [B, L, hidden] (= last_hidden_state, after
+ * final_layer_norm), pooled [B, hidden] (= pooler_output), text_embeds [B, proj_dim] (= get_text_features). */
+int ltt_clip_encode(ltt_clip* c, const int32_t* ids, int B, int L, float* last_hidden, float* pooled, float* text_embeds,
+                    void* stream);
+int64_t ltt_clip_launch_count(const ltt_clip* c);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Operator-level API (the same kernels, exposed one by one for parity tests and profiling)
  * -------------------------------------------------------------------------------------------------------------- */
 
@@ -171,6 +204,10 @@ int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int h
 /* softmax(q k^T scale) v  (attention.py:127-141,164-176), out [B, nq, heads*dhead] fp16 */
 int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
                      int heads, int dhead, int dpad, int nq, int nk, float scale, void* out, int ldo, void* stream);
+/* the same with a causal mask (key j visible to query i iff j <= i; n queries = n keys): CLIP text tower self-attention
+ * (transformers CLIPAttention with the causal mask of CLIPTextTransformer.forward) */
+int ltt_op_attention_causal(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
+                            int heads, int dhead, int dpad, int n, float scale, void* out, int ldo, void* stream);
 /* GroupNorm(32) [+ SiLU] on the channel concat of up to two NHWC fp16 tensors (util.py:211-229, attention.py:78) */
 int ltt_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* gamma,
                      const float* beta, float eps, int silu, void* out, void* stream);

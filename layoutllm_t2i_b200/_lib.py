@@ -30,6 +30,11 @@ class VaeConfig(C.Structure):
                 ("num_res_blocks", C.c_int), ("z_channels", C.c_int), ("embed_dim", C.c_int), ("scale_factor", C.c_float)]
 
 
+class ClipConfig(C.Structure):
+    _fields_ = [("vocab", C.c_int), ("max_pos", C.c_int), ("hidden", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+                ("ffn", C.c_int), ("eps", C.c_float), ("act", C.c_int), ("proj_dim", C.c_int), ("eos_token_id", C.c_int)]
+
+
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); mirrors include/ltt_b200.h one to one
@@ -58,6 +63,12 @@ _SIGS = {
     "ltt_vae_finalize": (_i, [_vp]),
     "ltt_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ltt_vae_launch_count": (_i64, [_vp]),
+    "ltt_clip_create": (_i, [C.POINTER(ClipConfig), _i, C.POINTER(_vp)]),
+    "ltt_clip_destroy": (None, [_vp]),
+    "ltt_clip_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "ltt_clip_finalize": (_i, [_vp]),
+    "ltt_clip_encode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ltt_clip_launch_count": (_i64, [_vp]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
     "ltt_op_linear_ln_linear": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -65,6 +76,7 @@ _SIGS = {
     "ltt_op_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "ltt_op_qkv": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "ltt_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "ltt_op_attention_causal": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
     "ltt_op_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
     "ltt_op_layernorm": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "ltt_op_rela_rects": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -131,6 +131,15 @@ int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const
     return attn_tc_launch(p, (cudaStream_t)stream);
 }
 
+int ltt_op_attention_causal(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
+                            int heads, int dhead, int dpad, int n, float scale, void* out, int ldo, void* stream) {
+    AttnProblem p{};
+    p.B = B; p.heads = heads; p.dhead = dhead; p.dpad = dpad; p.nq = n; p.nk = n;
+    p.q = (const __half*)q; p.rows_q = rows_q; p.k = (const __half*)k; p.rows_k = rows_k;
+    p.vt = (const __half*)vt; p.pitch_v = pitch_v; p.out = (__half*)out; p.ldo = ldo; p.scale = scale; p.causal = 1;
+    return attn_tc_launch(p, (cudaStream_t)stream);
+}
+
 int ltt_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* gamma,
                      const float* beta, float eps, int silu, void* out, void* stream) {
     static double* stats = nullptr;

@@ -28,6 +28,7 @@ struct AttnDeviceArgs {
     __half* out;
     int ldo;
     float scale_log2;
+    int causal;
 };
 
 // PTM: the probabilities P live in tensor memory (tcgen05.st by the softmax threads, A-from-TMEM operand of the PV MMA)
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
     // datapath (their TMA / tcgen05 operations are issued by one elected lane inside the "_elect" wrappers)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-    const int nt = (args.nk + BKV - 1) / BKV;
+    // causal: KV tiles entirely to the right of this CTA's last query row are never visited (all three roles agree on nt)
+    const int nt = args.causal ? min((args.nk + BKV - 1) / BKV, (q0 + 127) / BKV + 1) : (args.nk + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.qmap);
@@ -221,8 +223,9 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
         for (int j = 0; j < nt; ++j) {
             const int sb = j % SBUF, pb = j % PBUF;
             uint8_t* sP = smem + C::OFF_P + pb * C::P_BYTES;
-            const int kvalid = args.nk - j * BKV;   // >= 1
-            const bool tail = kvalid < BKV;
+            // columns of this tile visible to this row: the valid keys, under a causal mask only those up to the row's own index
+            const int kvalid = args.causal ? min(args.nk - j * BKV, q0 + r + 1 - j * BKV) : args.nk - j * BKV;   // non-causal: >= 1
+            const bool tail = args.causal || kvalid < BKV;
             const uint32_t ts = trow + C::TM_S + sb * BKV;
             mbar_wait(&s_full[sb], (j / SBUF) & 1);
             tc_fence_after();
@@ -404,10 +407,15 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     if (p.dhead == 40 && p.dpad == 64) { bkv = (v40 == 1 || v40 == 2 || v40 == 8 || v40 == 9 || v40 == 10 || (v40 == 0 && p.nk <= 128)) ? 64 : 128; dv = 48; }
     else if (p.dhead == 80 && p.dpad == 128) { bkv = 128; dv = 80; }
     else if (p.dhead == 160 && p.dpad == 192) { bkv = 64; dv = 160; }
+    else if (p.dhead == 64 && p.dpad == 64) { bkv = 128; dv = 64; }      // CLIP text tower (12 heads of 64)
     else if (p.dhead == 8 && p.dpad == 64) { bkv = 128; dv = 16; }     // tiny test / tiny-UNet heads
     else if (p.dhead == 16 && p.dpad == 64) { bkv = 128; dv = 16; }
     else {
         set_error("attention: unsupported head dim %d (dpad %d)", p.dhead, p.dpad);
+        return -1;
+    }
+    if (p.causal && p.nq != p.nk) {
+        set_error("attention: the causal mask needs nq == nk (%d, %d)", p.nq, p.nk);
         return -1;
     }
     if (p.nk < 1 || p.nq < 1 || p.pitch_v % 8 != 0) {
@@ -439,6 +447,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     a.nq = p.nq; a.nk = p.nk; a.dhead = p.dhead; a.dpad = p.dpad;
     a.out = p.out; a.ldo = p.ldo;
     a.scale_log2 = p.scale * 1.4426950408889634f;
+    a.causal = p.causal;
     dim3 grid((p.nq + 127) / 128, p.heads, p.B);
     static const int vwg = getenv("LTT_ATTN_WG") ? atoi(getenv("LTT_ATTN_WG")) : 2;     // softmax warpgroups for d = 80 / 160 (A/B)
     if (dv == 48) {
@@ -473,6 +482,7 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     }
     // P in tensor memory for the wider heads too: d = 80 13.1 -> 12.3 us (1024 x 1054 keys), d = 160 7.3 -> 6.9 us
     static const int ptm_all = getenv("LTT_ATTN_PTM") ? atoi(getenv("LTT_ATTN_PTM")) : 1;
+    if (dv == 64) return attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80 && ptm_all) return attn_launch_variant<128, 80, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 160 && ptm_all) return attn_launch_variant<192, 160, 64, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)

@@ -160,7 +160,8 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float y = v[i] + bv[i];
-            if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
+            if (e.act == ACT_QUICKGELU) y = y / (1.0f + __expf(-1.702f * y));      // fp32 through the activation (fp32 reference)
+            else if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
             if (e.rowvec) {
                 const float2 f = __half22float2(rvh[i >> 1]);
                 y = r16(y + ((i & 1) ? f.y : f.x));

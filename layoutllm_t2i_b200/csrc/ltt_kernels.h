@@ -52,7 +52,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 //   rows m = pixels (b, y, x) of an NHWC activation (or plain rows when H == 1),
 //   A is gathered from up to 3 sources; a source with taps == 9 contributes the 3x3 neighbourhood (zero padded,
 //   stride 1), one with taps == 1 its own pixel.  Wp is [N, Ktot] fp16, K ordered source-major, tap, channel.
-enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_QUICKGELU = 3 };   // QUICKGELU: x * sigmoid(1.702 x) (CLIP text MLP)
 enum : int { OUT_ROWMAJOR = 0, OUT_QKV = 1 };
 enum : int { DT_F16 = 0, DT_F32 = 1 };
 
@@ -136,6 +136,7 @@ struct AttnProblem {
     __half* out;              // [B, nq, ldo]
     int ldo;
     float scale;
+    int causal = 0;           // 1: key j is visible to query i only when j <= i (CLIP text tower); needs nq == nk
 };
 int attn_tc_launch(const AttnProblem& p, cudaStream_t stream);
 

@@ -50,3 +50,25 @@ class ClipModel:
     def __call__(self, input_ids=None, pixel_values=None, attention_mask=None, **kw):
         pooled = _vec("phrase:%d" % int(input_ids[0, 0]), 1).to(input_ids.device)
         return SimpleNamespace(text_model_output=SimpleNamespace(pooler_output=pooled))
+
+
+class HashTokenizer:
+    """CLIPTokenizer's call surface on a deterministic word hash: <bos> word ids <eos>, padded with <eos> (as the
+    clip-vit-large-patch14 tokenizer does) to `max_length` when padding == "max_length", else to the longest row."""
+
+    def __init__(self, vocab_size=49408):
+        self.vocab, self.bos, self.eos = vocab_size, vocab_size - 2, vocab_size - 1
+
+    def _row(self, text):
+        words = [int.from_bytes(hashlib.sha1(w.encode()).digest()[:4], "little") % (self.vocab - 3) + 1 for w in str(text).split()]
+        return [self.bos] + words + [self.eos]
+
+    def __call__(self, text=None, truncation=False, max_length=77, padding=False, return_tensors="pt", **kw):
+        texts = [text] if isinstance(text, str) else list(text)
+        rows = [self._row(t) for t in texts]
+        if truncation:
+            rows = [r[:max_length - 1] + [self.eos] if len(r) > max_length else r for r in rows]
+        width = max_length if padding == "max_length" else max(len(r) for r in rows)
+        ids = torch.tensor([r + [self.eos] * (width - len(r)) for r in rows])
+        mask = torch.tensor([[1] * len(r) + [0] * (width - len(r)) for r in rows])
+        return dict(input_ids=ids, attention_mask=mask)
