@@ -15,6 +15,7 @@ pointers are forwarded to the C-ABI.
 from __future__ import annotations
 
 import ctypes as C
+from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -111,6 +112,43 @@ class ClipTextEncoder:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class ClipModelAdapter:
+    """Stands where the reference's callers pass transformers' ``CLIPModel`` for its TEXT tower: ``model(**inputs)
+    .text_model_output.pooler_output`` (get_clip_feature, txt2img.py:147-156; GLIGEN/interface.py has the same function) and
+    ``model.get_text_features(**inputs)`` (extract_text_feat, txt2img.py:454-457).  The dummy ``pixel_values`` the callers
+    attach are ignored -- no vision pass is run -- and so is ``attention_mask``: under the causal mask the rows up to the
+    end-of-text token, which is where the pooled vector is read, do not see the padding.  Image inputs
+    (``get_clip_feature(..., is_image=True)`` with a real image) are outside the text-to-image path and raise."""
+
+    def __init__(self, encoder: ClipTextEncoder):
+        self.encoder = encoder
+
+    @property
+    def device(self):
+        return self.encoder.device
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def __call__(self, input_ids=None, attention_mask=None, pixel_values=None, **kw):
+        if input_ids is None:
+            raise L.LttError("ClipModelAdapter: the text tower needs input_ids")
+        if tuple(input_ids.shape) == (1, 4) and input_ids.flatten().tolist() == [0, 1, 2, 3]:     # the placeholder ids of the image branch (txt2img.py:139)
+            raise L.LttError("ClipModelAdapter: image features (CLIP vision tower) are not part of the text-to-image path")
+        want = bool(self.encoder.cfg["projection_dim"])
+        out = self.encoder.encode_ids(input_ids, want_embeds=want)
+        return SimpleNamespace(text_model_output=SimpleNamespace(last_hidden_state=out[0], pooler_output=out[1]),
+                               text_embeds=out[2] if want else None, image_embeds=None)
+
+    def get_text_features(self, input_ids=None, attention_mask=None, **kw):
+        if not self.encoder.cfg["projection_dim"]:
+            raise L.LttError("ClipModelAdapter.get_text_features: the tower was built without text_projection (projection_dim = 0)")
+        return self.encoder.encode_ids(input_ids, want_hidden=False, want_embeds=True)[2]
 
 
 def relation_phrases(graph: dict, max_relas: int = 5) -> List[str]:

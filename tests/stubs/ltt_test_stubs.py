@@ -72,3 +72,13 @@ class HashTokenizer:
         ids = torch.tensor([r + [self.eos] * (width - len(r)) for r in rows])
         mask = torch.tensor([[1] * len(r) + [0] * (width - len(r)) for r in rows])
         return dict(input_ids=ids, attention_mask=mask)
+
+
+class HashProcessor:
+    """CLIPProcessor's text call surface (txt2img.py:148: processor(text=..., return_tensors="pt", padding=True)) on HashTokenizer."""
+
+    def __init__(self, vocab_size=49408):
+        self.tok = HashTokenizer(vocab_size)
+
+    def __call__(self, text=None, images=None, return_tensors="pt", padding=True):
+        return self.tok(text, padding=padding)

@@ -180,3 +180,96 @@ def test_generate_one_image_and_run_batch_images_unmodified(tmp_path, monkeypatc
     z_solo = _direct(sd, solo)
     err = ((z_solo.cpu() - z3[1:2].float().cpu()).norm() / z3[1:2].float().norm().cpu()).item()
     assert err < 2e-2, err          # same arithmetic, other batch geometry (tile shapes): fp16 noise over 50 steps only
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# every model of the checkpoint from the drop-in tree: UNet + sampler (rows a / b), AutoencoderKL (f1 / f2) and the CLIP text
+# tower (f3) -- text encoder instantiated by load_ckpt from its reference config string, the callers' CLIPModel argument
+# replaced by ClipModelAdapter
+CLIP_SMALL = dict(vocab_size=1000, hidden_size=768, num_attention_heads=12, num_hidden_layers=2, intermediate_size=1024)
+VAE_SMALL = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2],
+                 num_res_blocks=1, attn_resolutions=[], dropout=0.0)
+
+
+def _full_checkpoint(tmp_path):
+    from oracle import clip_text_oracle as co
+    from ldm.models.autoencoder import AutoencoderKL
+    path, sd = _checkpoint(tmp_path)
+    ck = torch.load(path, weights_only=False)
+    cfg = ck["config_dict"]["_content"]
+    cfg["text_encoder"] = dict(target="ldm.modules.encoders.modules.FrozenCLIPEmbedder", params=dict(text_config=CLIP_SMALL))
+    cfg["autoencoder"] = dict(target="ldm.models.autoencoder.AutoencoderKL",
+                              params=dict(ddconfig=VAE_SMALL, embed_dim=4, scale_factor=0.18215))
+    ccfg = dict(co.default_clip_text_config(), **CLIP_SMALL)
+    clip_sd = co.random_state_dict(ccfg, seed=8, with_projection=False)
+    ck["text_encoder"] = {"transformer." + k: v for k, v in clip_sd.items()}
+    torch.manual_seed(4)
+    ck["autoencoder"] = AutoencoderKL(VAE_SMALL, 4, 0.18215).state_dict()
+    torch.save(ck, path)
+    return path, sd, ccfg, clip_sd
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_full_stack_generate_one_image_unmodified(tmp_path, monkeypatch):
+    """Unmodified txt2img.generate_one_image with NOTHING stubbed on the device: drop-in UNet + PLMSSampler, drop-in
+    AutoencoderKL, drop-in FrozenCLIPEmbedder, ClipModelAdapter as `clip_model`.  The conditioning the reference's
+    per-string call sequence hands to the sampler must match ONE batched prepare_conditioning pass (2e-3: tile shapes differ),
+    and both must match the fp32 oracle of the text tower."""
+    txt2img, _ = _import_callers()
+    import ltt_test_stubs as st
+    import sng_parser
+    from ldm.models.diffusion import plms as dropin_plms
+    from layoutllm_t2i_b200.clip import ClipModelAdapter, prepare_conditioning, relation_phrases
+    from oracle import clip_text_oracle as co
+    from oracle.ref_loader import true_fp32
+    path, sd, ccfg, clip_sd = _full_checkpoint(tmp_path)
+    dev = torch.device("cuda", 0)
+    recs = []
+    orig = dropin_plms.PLMSSampler.sample
+
+    def spy(self, S, shape, input, uc=None, guidance_scale=1, mask=None, x0=None):
+        recs.append(dict(context=input["context"].detach().clone(), relations=input["relations"].detach().clone(),
+                         uc=uc.detach().clone(), grounding={k: v.detach().clone() for k, v in input["grounding_input"].items()}))
+        return orig(self, S, shape, input, uc, guidance_scale, mask, x0)
+    monkeypatch.setattr(dropin_plms.PLMSSampler, "sample", spy)
+
+    gligen = list(txt2img.load_all_models(path, dev))
+    model, autoencoder, text_encoder = gligen[0], gligen[1], gligen[2]
+    for m in (model, autoencoder, text_encoder):
+        assert DROPIN in sys.modules[type(m).__module__].__file__, type(m)
+    assert text_encoder.device == dev                  # txt2img.py:112-114
+    text_encoder.set_tokenizer(st.HashTokenizer(ccfg["vocab_size"]))
+    cfg = gligen[4]
+    cfg.update(dict(batch_size=1, no_plms=False, guidance_scale=7.5))
+    gligen[4] = txt2img.OmegaConf.create(cfg)
+    prompt, phrases = "a cat on a sofa near a lamp", ["cat", "sofa", "lamp"]
+    boxes = [[0.1, 0.3, 0.5, 0.8], [0.0, 0.5, 1.0, 1.0], [0.7, 0.1, 0.95, 0.6]]
+    torch.manual_seed(11)
+    imgs = txt2img.generate_one_image(SimpleNamespace(batch_size=1), tuple(gligen), prompt, phrases, boxes,
+                                      clip_model=ClipModelAdapter(text_encoder.engine()), clip_processor=st.HashProcessor(ccfg["vocab_size"]),
+                                      device=dev)
+    assert len(imgs) == 1 and imgs[0].size == (128, 128)          # 2-level test VAE: 64 -> 128
+    rec = recs[-1]
+
+    # ---- ONE batched pass
+    rels = relation_phrases(sng_parser.parse(prompt), cfg["max_relations"])
+    assert len(rels) == 5                               # PAD + 2 triplets twice
+    out = prepare_conditioning(text_encoder.engine(), text_encoder.tokenize_padded, prompt, phrases, boxes, rels, batch=1,
+                               max_relas=cfg["max_relations"])
+
+    def rel_err(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+    assert rel_err(out["context"], rec["context"]) < 2e-3 and rel_err(out["uc"], rec["uc"]) < 2e-3
+    assert rel_err(out["relations"], rec["relations"]) < 2e-3 and float(rec["relations"][0, 5:].abs().max()) == 0.0
+    assert rel_err(out["text_embeddings"], rec["grounding"]["positive_embeddings"]) < 2e-3
+    assert torch.equal(out["boxes"], rec["grounding"]["boxes"]) and torch.equal(out["masks"], rec["grounding"]["masks"])
+
+    # ---- both against the fp32 oracle of the text tower
+    sdd = {k: v.to(dev) for k, v in clip_sd.items()}
+    with torch.no_grad(), true_fp32():
+        z, _ = co.clip_text_forward(sdd, ccfg, text_encoder.tokenize_padded([prompt, ""]).to(dev))
+        pooled = torch.cat([co.clip_text_forward(sdd, ccfg, st.HashTokenizer(ccfg["vocab_size"])(p, padding=True)["input_ids"].to(dev))[1]
+                            for p in phrases])
+    assert rel_err(rec["context"][0], z[0]) < 2e-3 and rel_err(rec["uc"][0], z[1]) < 2e-3
+    assert rel_err(rec["grounding"]["positive_embeddings"][0, :3], pooled) < 2e-3
