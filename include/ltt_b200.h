@@ -204,7 +204,7 @@ int ltt_op_qkv(const void* a, int B, int tokens, int C, const void* w_qkv, int h
 /* softmax(q k^T scale) v  (attention.py:127-141,164-176), out [B, nq, heads*dhead] fp16 */
 int ltt_op_attention(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
                      int heads, int dhead, int dpad, int nq, int nk, float scale, void* out, int ldo, void* stream);
-/* the same with a causal mask (key j visible to query i iff j <= i; n queries = n keys): CLIP text tower self-attention
+/* the same with a causal mask (key j visible to query i iff j <= i; n queries = n keys; dhead = dpad = 64): CLIP text tower self-attention
  * (transformers CLIPAttention with the causal mask of CLIPTextTransformer.forward) */
 int ltt_op_attention_causal(const void* q, int rows_q, const void* k, int rows_k, const void* vt, int pitch_v, int B,
                             int heads, int dhead, int dpad, int n, float scale, void* out, int ldo, void* stream);

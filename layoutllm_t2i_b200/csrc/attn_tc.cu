@@ -28,7 +28,6 @@ struct AttnDeviceArgs {
     __half* out;
     int ldo;
     float scale_log2;
-    int causal;
 };
 
 // PTM: the probabilities P live in tensor memory (tcgen05.st by the softmax threads, A-from-TMEM operand of the PV MMA)
@@ -90,7 +89,8 @@ __device__ __forceinline__ float ex2_poly(float x) {
 // NWG = softmax warpgroups: with 2 the columns of a score tile are split between two threads per query row (half the
 // serial TMEM-load -> exp -> store chain per tile); the pair agrees on the running reference through shared memory.
 // POLY = k > 0: every k-th exponential of a row goes through ex2_poly instead of MUFU.EX2.
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG, int POLY, bool PTM>
+// CAUSAL: key j is visible to query i iff j <= i (compile-time, so that the UNet's kernels keep their uniform tile bounds).
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG, int POLY, bool PTM, bool CAUSAL = false>
 __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const __grid_constant__ AttnDeviceArgs args) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF, PTM>;
     extern __shared__ uint8_t smem_raw[];
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
     // causal: KV tiles entirely to the right of this CTA's last query row are never visited (all three roles agree on nt)
-    const int nt = args.causal ? min((args.nk + BKV - 1) / BKV, (q0 + 127) / BKV + 1) : (args.nk + BKV - 1) / BKV;
+    const int nt = CAUSAL ? min((args.nk + BKV - 1) / BKV, (q0 + 127) / BKV + 1) : (args.nk + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.qmap);
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
             const int sb = j % SBUF, pb = j % PBUF;
             uint8_t* sP = smem + C::OFF_P + pb * C::P_BYTES;
             // columns of this tile visible to this row: the valid keys, under a causal mask only those up to the row's own index
-            const int kvalid = args.causal ? min(args.nk - j * BKV, q0 + r + 1 - j * BKV) : args.nk - j * BKV;   // non-causal: >= 1
-            const bool tail = args.causal || kvalid < BKV;
+            const int kvalid = CAUSAL ? min(args.nk - j * BKV, q0 + r + 1 - j * BKV) : args.nk - j * BKV;   // non-causal: >= 1
+            const bool tail = CAUSAL || kvalid < BKV;
             const uint32_t ts = trow + C::TM_S + sb * BKV;
             mbar_wait(&s_full[sb], (j / SBUF) & 1);
             tc_fence_after();
@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
                 constexpr bool store = decltype(store_tag)::value;
                 float rs = 0.f;
                 const float nm = -mref;
+                // (reading the tile in 16-column pieces with the next tcgen05.ld in flight behind the exponentials -- wait::ld tied to
+                // the piece's registers -- was measured: 91.2 us either way at 4096 x 4126 keys; the 16 softmax warps per SM already
+                // cover each other's TMEM latency)
 #pragma unroll
                 for (int c = 0; c < CW; c += 32) {
                     uint32_t v[32];
@@ -380,20 +383,20 @@ __global__ void __launch_bounds__(att_threads(NWG), MINB) attn_tc_kernel(const _
     }
 }
 
-template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1, int POLY = 0, bool PTM = false>
+template <int DPAD, int DV, int BKV, int SBUF, int PBUF, int MINB, int NWG = 1, int POLY = 0, bool PTM = false, bool CAUSAL = false>
 static int attn_launch_variant(const AttnDeviceArgs& a, dim3 grid, cudaStream_t stream) {
     using C = AttnCfg<DPAD, DV, BKV, SBUF, PBUF, PTM>;
     static bool configured = false;
     if (!configured) {
-        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        LTT_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         configured = true;
         if (getenv("LTT_VERBOSE")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, att_threads(NWG), C::TOTAL);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM, CAUSAL>, att_threads(NWG), C::TOTAL);
             fprintf(stderr, "[ltt] attn_tc_kernel<%d,%d,%d,%d,%d,%d>: %d B smem, %d CTA/SM\n", DPAD, DV, BKV, SBUF, PBUF, MINB, C::TOTAL, nb);
         }
     }
-    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
+    LTT_CUDA_OK(launch_k(attn_tc_kernel<DPAD, DV, BKV, SBUF, PBUF, MINB, NWG, POLY, PTM, CAUSAL>, grid, dim3(att_threads(NWG)), C::TOTAL, stream, a));
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -414,8 +417,8 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
         set_error("attention: unsupported head dim %d (dpad %d)", p.dhead, p.dpad);
         return -1;
     }
-    if (p.causal && p.nq != p.nk) {
-        set_error("attention: the causal mask needs nq == nk (%d, %d)", p.nq, p.nk);
+    if (p.causal && (p.nq != p.nk || p.dhead != 64)) {
+        set_error("attention: the causal variant is built for 64-wide heads and nq == nk (d=%d, %d, %d)", p.dhead, p.nq, p.nk);
         return -1;
     }
     if (p.nk < 1 || p.nq < 1 || p.pitch_v % 8 != 0) {
@@ -447,7 +450,6 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     a.nq = p.nq; a.nk = p.nk; a.dhead = p.dhead; a.dpad = p.dpad;
     a.out = p.out; a.ldo = p.ldo;
     a.scale_log2 = p.scale * 1.4426950408889634f;
-    a.causal = p.causal;
     dim3 grid((p.nq + 127) / 128, p.heads, p.B);
     static const int vwg = getenv("LTT_ATTN_WG") ? atoi(getenv("LTT_ATTN_WG")) : 2;     // softmax warpgroups for d = 80 / 160 (A/B)
     if (dv == 48) {
@@ -482,7 +484,8 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     }
     // P in tensor memory for the wider heads too: d = 80 13.1 -> 12.3 us (1024 x 1054 keys), d = 160 7.3 -> 6.9 us
     static const int ptm_all = getenv("LTT_ATTN_PTM") ? atoi(getenv("LTT_ATTN_PTM")) : 1;
-    if (dv == 64) return attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
+    if (dv == 64) return p.causal ? attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true, true>(a, grid, stream)
+                                  : attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80 && ptm_all) return attn_launch_variant<128, 80, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 160 && ptm_all) return attn_launch_variant<192, 160, 64, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)
