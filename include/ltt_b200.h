@@ -173,6 +173,48 @@ int ltt_clip_encode(ltt_clip* c, const int32_t* ids, int B, int L, float* last_h
 int64_t ltt_clip_launch_count(const ltt_clip* c);
 
 /* ----------------------------------------------------------------------------------------------------------------
+ * Reward path: CLIP vision tower + reward head  (replaces, in Reward.forward of
+ * /root/reference/models/policy.py:106-123,139, the two eager `CLIPModel.get_image_features` calls -- transformers
+ * CLIPVisionTransformer -- and the cosine / AestheticMLP (tools/aesthetic.py:9-31,52-57) arithmetic behind them; the text
+ * features come from ltt_clip_encode's text_embeds)
+ * -------------------------------------------------------------------------------------------------------------- */
+typedef struct ltt_clip_vision ltt_clip_vision;
+
+/* transformers CLIPVisionConfig fields (openai/clip-vit-large-patch14: 224, 14, 1024, 16, 24, 4096, 1e-5, quick_gelu,
+ * projection 768).  hidden / heads must be 64; hidden and ffn multiples of 64; act: 0 = quick_gelu. */
+typedef struct {
+    int image_size, patch, hidden, heads, layers, ffn;
+    float eps;
+    int act;
+    int proj_dim;       /* 0: no visual_projection (CLIPVisionModel); > 0: CLIPModel.visual_projection rows */
+} ltt_clip_vision_config;
+
+int ltt_clip_vision_create(const ltt_clip_vision_config* cfg, int device, ltt_clip_vision** out);
+void ltt_clip_vision_destroy(ltt_clip_vision* c);
+/* state_dict keys of transformers CLIPVisionModel / CLIPModel ("vision_model.embeddings.class_embedding",
+ * "vision_model.embeddings.patch_embedding.weight", "vision_model.pre_layrnorm.weight" (sic), ...,
+ * "vision_model.post_layernorm.bias", "visual_projection.weight"); fp32 device or host pointers. */
+int ltt_clip_vision_load_param(ltt_clip_vision* c, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
+int ltt_clip_vision_finalize(ltt_clip_vision* c);
+/* pixel_values [B, 3, image_size, image_size] fp32 on the device, as CLIPProcessor returns them (resized, cropped,
+ * normalised -- host-side preprocessing stays with the caller's processor).  Outputs, fp32 device, each may be NULL:
+ * last_hidden [B, 1 + patches, hidden] (= last_hidden_state, before post_layernorm), pooled [B, hidden]
+ * (= pooler_output), image_embeds [B, proj_dim] (= get_image_features). */
+int ltt_clip_vision_encode(ltt_clip_vision* c, const float* pixel_values, int B, float* last_hidden, float* pooled,
+                           float* image_embeds, void* stream);
+int64_t ltt_clip_vision_launch_count(const ltt_clip_vision* c);
+
+/* Reward.forward models/policy.py:115-139 from the feature matrices: txt / pred / gt [B, D] fp32 (get_text_features of the
+ * captions, get_image_features of the generated and the ground-truth images; D <= 1024);
+ * clip = cos(txt, pred) + cos(gt, pred); aes = AestheticMLP(pred / |pred|) -- aes_w / aes_b: the five Linear layers
+ * ("layers.0", ".2", ".4", ".6", ".7"), row-major [out, in] fp32 device pointers, aes_dims = {D, 1024, 128, 64, 16, 1};
+ * reward[b] = clip + 0.1 aes + 10 miou[b] + 10 laysim[b]  (miou / laysim: the host-side layout terms, may be NULL = 0).
+ * clip_reward / aes_reward [B] are optional outputs. */
+int ltt_reward_head(const float* txt, const float* pred, const float* gt, int B, int D, const float* const* aes_w,
+                    const float* const* aes_b, const int* aes_dims, const float* miou, const float* laysim, float* reward,
+                    float* clip_reward, float* aes_reward, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * Operator-level API (the same kernels, exposed one by one for parity tests and profiling)
  * -------------------------------------------------------------------------------------------------------------- */
 

@@ -35,6 +35,11 @@ class ClipConfig(C.Structure):
                 ("ffn", C.c_int), ("eps", C.c_float), ("act", C.c_int), ("proj_dim", C.c_int), ("eos_token_id", C.c_int)]
 
 
+class ClipVisionConfig(C.Structure):
+    _fields_ = [("image_size", C.c_int), ("patch", C.c_int), ("hidden", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+                ("ffn", C.c_int), ("eps", C.c_float), ("act", C.c_int), ("proj_dim", C.c_int)]
+
+
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); mirrors include/ltt_b200.h one to one
@@ -69,6 +74,13 @@ _SIGS = {
     "ltt_clip_finalize": (_i, [_vp]),
     "ltt_clip_encode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ltt_clip_launch_count": (_i64, [_vp]),
+    "ltt_clip_vision_create": (_i, [C.POINTER(ClipVisionConfig), _i, C.POINTER(_vp)]),
+    "ltt_clip_vision_destroy": (None, [_vp]),
+    "ltt_clip_vision_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "ltt_clip_vision_finalize": (_i, [_vp]),
+    "ltt_clip_vision_encode": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ltt_clip_vision_launch_count": (_i64, [_vp]),
+    "ltt_reward_head": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),
     "ltt_op_linear_ln_linear": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ltt_op_pack_geglu": (_i, [_vp, _i, _i, _vp, _vp]),

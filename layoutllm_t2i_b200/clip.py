@@ -114,16 +114,102 @@ class ClipTextEncoder:
             pass
 
 
+def default_clip_vision_config() -> dict:
+    """Vision tower of openai/clip-vit-large-patch14 (the ``model_config`` of the reward model, train_rl.py:325)."""
+    return dict(image_size=224, patch_size=14, hidden_size=1024, num_attention_heads=16, num_hidden_layers=24,
+                intermediate_size=4096, layer_norm_eps=1e-5, hidden_act="quick_gelu", projection_dim=768)
+
+
+class ClipVisionEncoder:
+    """CLIP vision tower (``ltt_clip_vision`` of include/ltt_b200.h): transformers ``CLIPVisionTransformer`` +
+    ``visual_projection`` as ``Reward.forward`` calls them (/root/reference/models/policy.py:111-114)."""
+
+    def __init__(self, cfg: Optional[dict] = None, device=0):
+        if not torch.cuda.is_available():
+            raise L.LttError("layoutllm_t2i_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        base = default_clip_vision_config()
+        self.cfg = dict(base, **{k: v for k, v in (cfg or {}).items() if k in base})
+        if self.cfg["hidden_act"] != "quick_gelu":
+            raise L.LttError(f"ClipVisionEncoder: hidden_act {self.cfg['hidden_act']!r} is not supported (quick_gelu only)")
+        c = L.ClipVisionConfig()
+        c.image_size, c.patch, c.hidden = self.cfg["image_size"], self.cfg["patch_size"], self.cfg["hidden_size"]
+        c.heads, c.layers, c.ffn = self.cfg["num_attention_heads"], self.cfg["num_hidden_layers"], self.cfg["intermediate_size"]
+        c.eps, c.act, c.proj_dim = float(self.cfg["layer_norm_eps"]), 0, int(self.cfg["projection_dim"] or 0)
+        self.tokens = (self.cfg["image_size"] // self.cfg["patch_size"]) ** 2 + 1
+        self._h = C.c_void_p()
+        self._lib = L.lib()
+        L.check(self._lib.ltt_clip_vision_create(C.byref(c), self.device.index, C.byref(self._h)), "ltt_clip_vision_create")
+        self._finalized = False
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Accepts the state_dict of transformers CLIPVisionModel or CLIPModel (text keys are skipped)."""
+        for k, v in sd.items():
+            if not (k.startswith("vision_model.") or (k == "visual_projection.weight" and self.cfg["projection_dim"])):
+                continue
+            if k.endswith("position_ids"):
+                continue
+            t = v.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            L.check(self._lib.ltt_clip_vision_load_param(self._h, k.encode(), L.ptr(t), shape, t.dim(), 0 if t.is_cuda else 1),
+                    f"ltt_clip_vision_load_param({k})")
+        self._finalized = False
+
+    def finalize(self) -> None:
+        L.check(self._lib.ltt_clip_vision_finalize(self._h), "ltt_clip_vision_finalize")
+        self._finalized = True
+
+    def encode(self, pixel_values: torch.Tensor, want_hidden: bool = False, want_embeds: bool = True):
+        """pixel_values [B, 3, S, S] (CLIPProcessor output) -> (last_hidden_state or None, pooler_output, image_embeds or None)."""
+        S = self.cfg["image_size"]
+        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, S, S):
+            raise L.LttError(f"ClipVisionEncoder: pixel_values must be [B, 3, {S}, {S}], got {tuple(pixel_values.shape)}")
+        if want_embeds and not self.cfg["projection_dim"]:
+            raise L.LttError("ClipVisionEncoder: image_embeds requested but the tower was built without visual_projection")
+        if not self._finalized:
+            self.finalize()
+        px = pixel_values.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        B, W = px.shape[0], self.cfg["hidden_size"]
+        hid = torch.empty(B, self.tokens, W, device=self.device) if want_hidden else None
+        pooled = torch.empty(B, W, device=self.device)
+        emb = torch.empty(B, self.cfg["projection_dim"], device=self.device) if want_embeds else None
+        with torch.cuda.device(self.device):
+            L.check(self._lib.ltt_clip_vision_encode(self._h, L.ptr(px), B, L.ptr(hid), L.ptr(pooled), L.ptr(emb), L.stream_ptr()),
+                    "ltt_clip_vision_encode")
+        self._keep = px
+        return hid, pooled, emb
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ltt_clip_vision_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.ltt_clip_vision_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class ClipModelAdapter:
     """Stands where the reference's callers pass transformers' ``CLIPModel`` for its TEXT tower: ``model(**inputs)
     .text_model_output.pooler_output`` (get_clip_feature, txt2img.py:147-156; GLIGEN/interface.py has the same function) and
     ``model.get_text_features(**inputs)`` (extract_text_feat, txt2img.py:454-457).  The dummy ``pixel_values`` the callers
     attach are ignored -- no vision pass is run -- and so is ``attention_mask``: under the causal mask the rows up to the
-    end-of-text token, which is where the pooled vector is read, do not see the padding.  Image inputs
-    (``get_clip_feature(..., is_image=True)`` with a real image) are outside the text-to-image path and raise."""
+    end-of-text token, which is where the pooled vector is read, do not see the padding.  With a vision tower attached,
+    ``get_image_features`` serves the reward model (models/policy.py:111-114); the grounding-by-image branch of
+    ``get_clip_feature`` (``is_image=True`` with a real image) is outside the text-to-image path and raises."""
 
-    def __init__(self, encoder: ClipTextEncoder):
+    def __init__(self, encoder: ClipTextEncoder, vision: Optional["ClipVisionEncoder"] = None):
         self.encoder = encoder
+        self.vision = vision
+        self.projection_dim = int(encoder.cfg["projection_dim"] or 0)        # Reward reads model.projection_dim (policy.py:45)
 
     @property
     def device(self):
@@ -149,6 +235,13 @@ class ClipModelAdapter:
         if not self.encoder.cfg["projection_dim"]:
             raise L.LttError("ClipModelAdapter.get_text_features: the tower was built without text_projection (projection_dim = 0)")
         return self.encoder.encode_ids(input_ids, want_hidden=False, want_embeds=True)[2]
+
+
+    def get_image_features(self, pixel_values=None, **kw):
+        """CLIPModel.get_image_features (models/policy.py:111-114)."""
+        if self.vision is None:
+            raise L.LttError("ClipModelAdapter.get_image_features: no vision tower was attached")
+        return self.vision.encode(pixel_values)[2]
 
 
 def relation_phrases(graph: dict, max_relas: int = 5) -> List[str]:

@@ -1,4 +1,5 @@
-// CLIP text tower on the sm_100a kernels: the conditioning prep of the sampler.
+// CLIP towers on the sm_100a kernels: the text tower = conditioning prep of the sampler; the vision
+// tower + reward head = the CLIP part of train_rl's reward (row f4, /root/reference/models/policy.py:106-123,139).
 //
 // Mirrors the third-party module the reference calls -- transformers CLIPTextTransformer (token + position embeddings,
 // pre-LayerNorm blocks with causal self-attention and a quick-GELU MLP, final LayerNorm, pooled = row of the end-of-text
@@ -94,33 +95,185 @@ __global__ void __launch_bounds__(256) clip_pool_kernel(const int32_t* __restric
     }
 }
 
+// ---- vision tower (transformers CLIPVisionEmbeddings / CLIPVisionTransformer)
+// patches[(b * G * G + py * G + px), c * P * P + ky * P + kx] = fp16(pixel[b, c, py * P + ky, px * P + kx]), zero padded to Kpad:
+// the stride-P patch convolution becomes one GEMM against the flattened [W, 3 P P] kernel
+__global__ void __launch_bounds__(256) clipv_patches_kernel(const float* __restrict__ px, int B, int S, int P, int G, int Kpad,
+                                                            __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int K = 3 * P * P;
+    const size_t total = (size_t)B * G * G * Kpad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const size_t row = i / Kpad;
+        float v = 0.f;
+        if (k < K) {
+            const int b = (int)(row / (G * G)), pr = (int)(row % (G * G)), py = pr / G, pxx = pr % G;
+            const int c = k / (P * P), kk = k % (P * P), ky = kk / P, kx = kk % P;
+            v = px[(((size_t)b * 3 + c) * S + py * P + ky) * S + pxx * P + kx];
+        }
+        out[i] = __float2half_rn(v);
+    }
+}
+// [W, 3, P, P] fp32 -> [W, Kpad] fp16 (zero padded rows)
+__global__ void clipv_pack_patch_kernel(const float* __restrict__ w, int W, int K, int Kpad, __half* __restrict__ out) {
+    const size_t total = (size_t)W * Kpad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        out[i] = __float2half_rn(k < K ? w[(i / Kpad) * K + k] : 0.f);
+    }
+}
+// x[b, 0, :] = class_embedding + pos[0];  x[b, 1 + p, :] = patch_out[b * NP + p, :] + pos[1 + p]      (fp32)
+__global__ void __launch_bounds__(256) clipv_assemble_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
+                                                             const float* __restrict__ pos, int B, int T, int W,
+                                                             float* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int vec = W >> 2;
+    const size_t total = (size_t)B * T * vec;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % vec);
+        const size_t row = i / vec;
+        const int b = (int)(row / T), t = (int)(row % T);
+        const float4 a = t == 0 ? reinterpret_cast<const float4*>(cls)[c]
+                                : reinterpret_cast<const float4*>(pe + ((size_t)b * (T - 1) + t - 1) * W)[c];
+        const float4 p = reinterpret_cast<const float4*>(pos + (size_t)t * W)[c];
+        reinterpret_cast<float4*>(x + row * W)[c] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+}
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    return s;
+}
+// pooled[b] = post_layernorm(hidden[b, 0, :]); embeds[b, p] = sum_k pooled[b, k] proj[p, k]   (fp32; one CTA per image)
+__global__ void __launch_bounds__(256) clipv_pool_kernel(const float* __restrict__ hidden, int T, int W, const float* __restrict__ g,
+                                                         const float* __restrict__ bt, float eps, const float* __restrict__ proj,
+                                                         int P, float* __restrict__ pooled, float* __restrict__ embeds) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float prow[];
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const float* src = hidden + (size_t)b * T * W;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < W; i += 256) {
+        prow[i] = src[i];
+        s += prow[i];
+    }
+    const float mean = block_sum_256(s, red) / W;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < W; i += 256) {
+        const float d = prow[i] - mean;
+        ss += d * d;
+    }
+    const float rstd = rsqrtf(block_sum_256(ss, red) / W + eps);
+    for (int i = threadIdx.x; i < W; i += 256) {
+        const float y = (prow[i] - mean) * rstd * g[i] + bt[i];
+        prow[i] = y;
+        if (pooled) pooled[(size_t)b * W + i] = y;
+    }
+    __syncthreads();
+    if (!embeds) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < P; p += 8) {
+        const float* w = proj + (size_t)p * W;
+        float acc = 0.f;
+        for (int k = lane; k < W; k += 32) acc = fmaf(prow[k], w[k], acc);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) embeds[(size_t)b * P + p] = acc;
+    }
+}
+
+// ---- reward head (Reward.forward, models/policy.py:115-139; AestheticMLP tools/aesthetic.py:15-31): one CTA per sample.
+// clip = cos(txt, pred) + cos(gt, pred); aes = the five bias-affine layers (eval: dropout is the identity, there is no
+// activation) on pred / |pred|; reward = clip + 0.1 aes + 10 miou + 10 laysim.   D <= 1024, layer widths <= 1024.
+struct AesW {
+    const float* w[5];
+    const float* b[5];
+    int dim[6];
+};
+__global__ void __launch_bounds__(256) reward_head_kernel(const float* __restrict__ txt, const float* __restrict__ pred,
+                                                          const float* __restrict__ gt, int D, AesW aw,
+                                                          const float* __restrict__ miou, const float* __restrict__ laysim,
+                                                          float* __restrict__ reward, float* __restrict__ clip_out,
+                                                          float* __restrict__ aes_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float buf[2][1024];
+    __shared__ float red[8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *t = txt + (size_t)b * D, *p = pred + (size_t)b * D, *g = gt + (size_t)b * D;
+    float tt = 0.f, pp = 0.f, gg = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) {
+        tt += t[i] * t[i];
+        pp += p[i] * p[i];
+        gg += g[i] * g[i];
+    }
+    // F.normalize: x / max(|x|, 1e-12)
+    const float nt = fmaxf(sqrtf(block_sum_256(tt, red)), 1e-12f), np_ = fmaxf(sqrtf(block_sum_256(pp, red)), 1e-12f),
+                ng = fmaxf(sqrtf(block_sum_256(gg, red)), 1e-12f);
+    float tp = 0.f, gp = 0.f, p2 = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) {
+        const float pn = p[i] / np_;
+        buf[0][i] = pn;
+        tp += (t[i] / nt) * pn;
+        gp += (g[i] / ng) * pn;
+        p2 += pn * pn;
+    }
+    const float clip = block_sum_256(tp, red) + block_sum_256(gp, red);
+    float n2 = sqrtf(block_sum_256(p2, red));       // `normalized`: divide by the norm of the (already normalised) row, 0 -> 1
+    if (n2 == 0.f) n2 = 1.f;
+    for (int i = threadIdx.x; i < D; i += 256) buf[0][i] /= n2;
+    __syncthreads();
+    int cur = 0;
+#pragma unroll 1
+    for (int l = 0; l < 5; ++l) {
+        const int in = aw.dim[l], out = aw.dim[l + 1];
+        for (int o = warp; o < out; o += 8) {
+            const float* w = aw.w[l] + (size_t)o * in;
+            float acc = 0.f;
+            for (int k = lane; k < in; k += 32) acc = fmaf(buf[cur][k], w[k], acc);
+#pragma unroll
+            for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (lane == 0) buf[cur ^ 1][o] = acc + aw.b[l][o];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (threadIdx.x == 0) {
+        const float aes = buf[cur][0];
+        if (clip_out) clip_out[b] = clip;
+        if (aes_out) aes_out[b] = aes;
+        reward[b] = clip + aes * 0.1f + (miou ? miou[b] * 10.f : 0.f) + (laysim ? laysim[b] * 10.f : 0.f);
+    }
+}
+
 struct CParam { float* dev = nullptr; std::vector<int64_t> shape; size_t numel = 0; };
+typedef std::map<std::string, CParam> CParams;
 struct CLayer {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
     __half *wqkv, *wo, *w1, *w2;
     const float *bqkv, *bo, *b1, *b2;
 };
-
-}  // namespace ltt
-
-using namespace ltt;
-
-struct ltt_clip {
-    ltt_clip_config cfg;
-    int device = 0, sms = 148;
-    std::map<std::string, CParam> params;
-    bool finalized = false;
-    std::vector<void*> wptrs, cptrs;
+// the encoder both towers share (transformers CLIPEncoder): weights + the activation workspace of one (B, L)
+struct Tower {
+    int W = 0, heads = 0, ffn = 0;
+    float eps = 1e-5f;
     std::vector<CLayer> layers;
-    const float *tok = nullptr, *pos = nullptr, *fin_g = nullptr, *fin_b = nullptr, *proj = nullptr;
-    // workspace for (B, L)
+    std::vector<void*> wptrs, cptrs;
     int B = 0, L = 0, pitch_v = 0;
-    float *x = nullptr, *hid = nullptr;
+    float* x = nullptr;          // fp32 residual stream [B * L, W]
     __half *h16 = nullptr, *q = nullptr, *k = nullptr, *vt = nullptr, *a16 = nullptr, *f16 = nullptr;
-    int64_t launches = 0;
 };
-
-namespace ltt {
 
 static int calloc_dev(std::vector<void*>& arena, void** out, size_t bytes) {
     void* p = nullptr;
@@ -133,9 +286,9 @@ static void crelease(std::vector<void*>& arena) {
     for (void* p : arena) cudaFree(p);
     arena.clear();
 }
-static const CParam* cfind(ltt_clip* c, const std::string& key, std::initializer_list<int64_t> shape) {
-    auto it = c->params.find(key);
-    if (it == c->params.end()) {
+static const CParam* cfind(const CParams& params, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = params.find(key);
+    if (it == params.end()) {
         set_error("clip: missing parameter '%s' (load_state_dict incomplete)", key.c_str());
         return nullptr;
     }
@@ -145,37 +298,40 @@ static const CParam* cfind(ltt_clip* c, const std::string& key, std::initializer
     }
     return &it->second;
 }
-#define CGET(var, key, ...)                              \
-    const CParam* var = cfind(c, (key), {__VA_ARGS__});  \
+#define CGET(var, key, ...)                                   \
+    const CParam* var = cfind(params, (key), {__VA_ARGS__});  \
     if (!var) return -6;
 
-static int clip_build(ltt_clip* c) {
-    const ltt_clip_config& g = c->cfg;
-    const int64_t W = g.hidden, F = g.ffn;
-    crelease(c->wptrs);
-    c->layers.clear();
-    const std::string tm = "text_model.";
-    {
-        CGET(t, tm + "embeddings.token_embedding.weight", g.vocab, W)
-        CGET(p, tm + "embeddings.position_embedding.weight", g.max_pos, W)
-        CGET(fg, tm + "final_layer_norm.weight", W)
-        CGET(fb, tm + "final_layer_norm.bias", W)
-        c->tok = t->dev; c->pos = p->dev; c->fin_g = fg->dev; c->fin_b = fb->dev;
+static int load_param(CParams& params, int device, const char* key, const float* data, const int64_t* shape, int ndim, int is_host) {
+    LTT_CUDA_OK(cudaSetDevice(device));
+    CParam& p = params[key];
+    size_t n = 1;
+    p.shape.assign(shape, shape + ndim);
+    for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+    if (p.dev && p.numel != n) {
+        cudaFree(p.dev);
+        p.dev = nullptr;
     }
-    c->proj = nullptr;
-    if (g.proj_dim > 0) {
-        CGET(pw, "text_projection.weight", g.proj_dim, W)
-        c->proj = pw->dev;
-    }
-    for (int i = 0; i < g.layers; ++i) {
-        const std::string p = tm + "encoder.layers." + std::to_string(i) + ".";
+    if (!p.dev) LTT_CUDA_OK(cudaMalloc(&p.dev, n * sizeof(float)));
+    p.numel = n;
+    LTT_CUDA_OK(cudaMemcpy(p.dev, data, n * sizeof(float), is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+// encoder.layers.* of one tower (`prefix` = "text_model." / "vision_model.") -> packed fp16 weights
+static int tower_build(Tower& t, const CParams& params, const std::string& prefix, int n_layers) {
+    const int64_t W = t.W, F = t.ffn;
+    crelease(t.wptrs);
+    t.layers.clear();
+    for (int i = 0; i < n_layers; ++i) {
+        const std::string p = prefix + "encoder.layers." + std::to_string(i) + ".";
         CLayer l{};
         CGET(g1, p + "layer_norm1.weight", W) CGET(b1, p + "layer_norm1.bias", W)
         CGET(g2, p + "layer_norm2.weight", W) CGET(b2, p + "layer_norm2.bias", W)
         l.ln1_g = g1->dev; l.ln1_b = b1->dev; l.ln2_g = g2->dev; l.ln2_b = b2->dev;
         void *wq, *bq;
-        RCC(calloc_dev(c->wptrs, &wq, (size_t)3 * W * W * 2));
-        RCC(calloc_dev(c->wptrs, &bq, (size_t)3 * W * 4));
+        RCC(calloc_dev(t.wptrs, &wq, (size_t)3 * W * W * 2));
+        RCC(calloc_dev(t.wptrs, &bq, (size_t)3 * W * 4));
         const char* names[3] = {"q_proj", "k_proj", "v_proj"};
         for (int j = 0; j < 3; ++j) {       // q / k / v stacked into one [3W, W] matrix (the softmax scale stays in the attention kernel)
             CGET(w, p + "self_attn." + names[j] + ".weight", W, W)
@@ -188,7 +344,7 @@ static int clip_build(ltt_clip* c) {
             CGET(w, p + name + ".weight", N, K)
             CGET(b, p + name + ".bias", N)
             void* q;
-            RCC(calloc_dev(c->wptrs, &q, (size_t)N * K * 2));
+            RCC(calloc_dev(t.wptrs, &q, (size_t)N * K * 2));
             RCC(pack_rows_launch(w->dev, (int)N, (int)K, (__half*)q, 0, 0, 0));
             *wout = (__half*)q; *bout = b->dev;
             return 0;
@@ -196,43 +352,111 @@ static int clip_build(ltt_clip* c) {
         RCC(lin("self_attn.out_proj", W, W, &l.wo, &l.bo));
         RCC(lin("mlp.fc1", F, W, &l.w1, &l.b1));
         RCC(lin("mlp.fc2", W, F, &l.w2, &l.b2));
-        c->layers.push_back(l);
+        t.layers.push_back(l);
     }
-    LTT_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 
-static int clip_workspace(ltt_clip* c, int B, int L) {
-    crelease(c->cptrs);
-    const ltt_clip_config& g = c->cfg;
-    const size_t M = (size_t)B * L, W = g.hidden;
-    c->pitch_v = (L + 7) & ~7;
-    auto A = [&](auto** p, size_t bytes) { return calloc_dev(c->cptrs, (void**)p, bytes); };
-    RCC(A(&c->x, M * W * 4)); RCC(A(&c->hid, M * W * 4));
-    RCC(A(&c->h16, M * W * 2)); RCC(A(&c->q, M * W * 2)); RCC(A(&c->k, M * W * 2)); RCC(A(&c->a16, M * W * 2));
-    RCC(A(&c->vt, (size_t)B * W * c->pitch_v * 2));
-    RCC(A(&c->f16, M * (size_t)g.ffn * 2));
-    LTT_CUDA_OK(cudaMemset(c->vt, 0, (size_t)B * W * c->pitch_v * 2));      // pitch padding columns are never written
-    c->B = B; c->L = L;
+static int tower_workspace(Tower& t, int B, int L) {
+    crelease(t.cptrs);
+    const size_t M = (size_t)B * L, W = t.W;
+    t.pitch_v = (L + 7) & ~7;
+    auto A = [&](auto** p, size_t bytes) { return calloc_dev(t.cptrs, (void**)p, bytes); };
+    RCC(A(&t.x, M * W * 4));
+    RCC(A(&t.h16, M * W * 2)); RCC(A(&t.q, M * W * 2)); RCC(A(&t.k, M * W * 2)); RCC(A(&t.a16, M * W * 2));
+    RCC(A(&t.vt, (size_t)B * W * t.pitch_v * 2));
+    RCC(A(&t.f16, M * (size_t)t.ffn * 2));
+    LTT_CUDA_OK(cudaMemset(t.vt, 0, (size_t)B * W * t.pitch_v * 2));      // pitch padding columns are never written
+    t.B = B; t.L = L;
     return 0;
 }
 
 // rows = nb sequences x len tokens; the QKV projection passes the real geometry (its epilogue transposes V per sequence),
 // the other GEMMs run on the flat [B * L] row list (nb = 1)
-static int clip_gemm(ltt_clip* c, cudaStream_t st, int nb, int len, int N, const __half* a, int K, const __half* w,
-                     const GemmEpilogue& epi) {
+static int clip_gemm(int sms, cudaStream_t st, int nb, int len, int N, const __half* a, int K, const __half* w, const GemmEpilogue& epi) {
     GemmProblem p{};
     p.B = nb; p.H = 1; p.W = len; p.N = N; p.nsrc = 1;
     p.src[0] = GemmSrc{a, K, K, 1};
     p.w = w; p.Ktot = K; p.w_static = 1; p.epi = epi;
-    c->launches++;
-    return gemm_tc_launch(p, c->sms, st);
+    return gemm_tc_launch(p, sms, st);
+}
+
+// CLIPEncoder.forward on t.x in place: 7 launches per layer
+static int tower_run(Tower& t, int sms, cudaStream_t st, int causal, int64_t& launches) {
+    const int B = t.B, L = t.L, M = B * L, W = t.W;
+    for (const CLayer& l : t.layers) {
+        RCC(layernorm_launch(t.x, DT_F32, M, W, l.ln1_g, l.ln1_b, t.eps, t.h16, nullptr, st));
+        {
+            GemmEpilogue e;
+            e.bias = l.bqkv;
+            e.out_mode = OUT_QKV;
+            e.q = t.q; e.k = t.k; e.vt = t.vt;
+            e.C = W; e.dhead = 64; e.dpad = 64; e.rows_q = L; e.rows_k = L; e.pitch_v = t.pitch_v; e.tokens = L; e.qkv_base = 0;
+            RCC(clip_gemm(sms, st, B, L, 3 * W, t.h16, W, l.wqkv, e));
+        }
+        {
+            AttnProblem p{};
+            p.B = B; p.heads = t.heads; p.dhead = 64; p.dpad = 64; p.nq = L; p.nk = L;
+            p.q = t.q; p.rows_q = L; p.k = t.k; p.rows_k = L; p.vt = t.vt; p.pitch_v = t.pitch_v;
+            p.out = t.a16; p.ldo = W; p.scale = 0.125f; p.causal = causal;
+            RCC(attn_tc_launch(p, st));
+        }
+        {
+            GemmEpilogue e;
+            e.bias = l.bo; e.res = t.x; e.res_dtype = DT_F32; e.ldr = W; e.out = t.x; e.out_dtype = DT_F32; e.ldo = W;
+            RCC(clip_gemm(sms, st, 1, M, W, t.a16, W, l.wo, e));
+        }
+        RCC(layernorm_launch(t.x, DT_F32, M, W, l.ln2_g, l.ln2_b, t.eps, t.h16, nullptr, st));
+        {
+            GemmEpilogue e;
+            e.bias = l.b1; e.act = ACT_QUICKGELU; e.out = t.f16; e.out_dtype = DT_F16; e.ldo = t.ffn;
+            RCC(clip_gemm(sms, st, 1, M, t.ffn, t.h16, W, l.w1, e));
+        }
+        {
+            GemmEpilogue e;
+            e.bias = l.b2; e.res = t.x; e.res_dtype = DT_F32; e.ldr = W; e.out = t.x; e.out_dtype = DT_F32; e.ldo = W;
+            RCC(clip_gemm(sms, st, 1, M, W, t.f16, t.ffn, l.w2, e));
+        }
+        launches += 7;
+    }
+    return 0;
 }
 
 }  // namespace ltt
 
+using namespace ltt;
+
+struct ltt_clip {
+    ltt_clip_config cfg;
+    int device = 0, sms = 148;
+    CParams params;
+    bool finalized = false;
+    Tower t;
+    const float *tok = nullptr, *pos = nullptr, *fin_g = nullptr, *fin_b = nullptr, *proj = nullptr;
+    float* hid = nullptr;
+    std::vector<void*> hptrs;
+    int64_t launches = 0;
+};
+
+struct ltt_clip_vision {
+    ltt_clip_vision_config cfg;
+    int device = 0, sms = 148;
+    CParams params;
+    bool finalized = false;
+    Tower t;
+    int G = 0, NP = 0, Kpad = 0;           // patches per side, patches per image, padded 3 P P
+    const float *cls = nullptr, *pos = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr, *proj = nullptr;
+    __half* patch_w = nullptr;
+    std::vector<void*> wptrs, cptrs;
+    int B = 0;
+    __half* patches = nullptr;
+    float *pe = nullptr, *xa = nullptr;
+    int64_t launches = 0;
+};
+
 extern "C" {
 
+// ---------------------------------------------------------------------------------------------------- text tower
 int ltt_clip_create(const ltt_clip_config* cfg, int device, ltt_clip** out) {
     if (!cfg || !out) {
         set_error("ltt_clip_create: null argument");
@@ -248,6 +472,7 @@ int ltt_clip_create(const ltt_clip_config* cfg, int device, ltt_clip** out) {
     ltt_clip* c = new ltt_clip();
     c->cfg = *cfg;
     c->device = device;
+    c->t.W = cfg->hidden; c->t.heads = cfg->heads; c->t.ffn = cfg->ffn; c->t.eps = cfg->eps;
     LTT_CUDA_OK(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
     *out = c;
     return 0;
@@ -257,8 +482,9 @@ void ltt_clip_destroy(ltt_clip* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    crelease(c->wptrs);
-    crelease(c->cptrs);
+    crelease(c->t.wptrs);
+    crelease(c->t.cptrs);
+    crelease(c->hptrs);
     for (auto& kv : c->params) cudaFree(kv.second.dev);
     delete c;
 }
@@ -268,26 +494,29 @@ int ltt_clip_load_param(ltt_clip* c, const char* key, const float* data, const i
         set_error("ltt_clip_load_param: null argument");
         return -1;
     }
-    LTT_CUDA_OK(cudaSetDevice(c->device));
-    CParam& p = c->params[key];
-    size_t n = 1;
-    p.shape.assign(shape, shape + ndim);
-    for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
-    if (p.dev && p.numel != n) {
-        cudaFree(p.dev);
-        p.dev = nullptr;
-    }
-    if (!p.dev) LTT_CUDA_OK(cudaMalloc(&p.dev, n * sizeof(float)));
-    p.numel = n;
-    LTT_CUDA_OK(cudaMemcpy(p.dev, data, n * sizeof(float), is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
     c->finalized = false;
-    return 0;
+    return load_param(c->params, c->device, key, data, shape, ndim, is_host);
 }
 
 int ltt_clip_finalize(ltt_clip* c) {
     if (!c) return -1;
     LTT_CUDA_OK(cudaSetDevice(c->device));
-    RCC(clip_build(c));
+    const ltt_clip_config& g = c->cfg;
+    const CParams& params = c->params;
+    const int64_t W = g.hidden;
+    const std::string tm = "text_model.";
+    CGET(t, tm + "embeddings.token_embedding.weight", g.vocab, W)
+    CGET(p, tm + "embeddings.position_embedding.weight", g.max_pos, W)
+    CGET(fg, tm + "final_layer_norm.weight", W)
+    CGET(fb, tm + "final_layer_norm.bias", W)
+    c->tok = t->dev; c->pos = p->dev; c->fin_g = fg->dev; c->fin_b = fb->dev;
+    c->proj = nullptr;
+    if (g.proj_dim > 0) {
+        CGET(pw, "text_projection.weight", g.proj_dim, W)
+        c->proj = pw->dev;
+    }
+    RCC(tower_build(c->t, params, tm, g.layers));
+    LTT_CUDA_OK(cudaDeviceSynchronize());
     c->finalized = true;
     return 0;
 }
@@ -309,55 +538,22 @@ int ltt_clip_encode(ltt_clip* c, const int32_t* ids, int B, int L, float* last_h
     }
     cudaStream_t st = (cudaStream_t)stream;
     LTT_CUDA_OK(cudaSetDevice(c->device));
-    if (B != c->B || L != c->L) {
+    Tower& t = c->t;
+    if (B != t.B || L != t.L) {
         LTT_CUDA_OK(cudaDeviceSynchronize());
-        RCC(clip_workspace(c, B, L));
+        RCC(tower_workspace(t, B, L));
+        crelease(c->hptrs);
+        RCC(calloc_dev(c->hptrs, (void**)&c->hid, (size_t)B * L * g.hidden * 4));
     }
-    const int M = B * L, W = g.hidden, H = g.heads;
+    const int M = B * L, W = g.hidden;
     {
         const int blocks = (int)std::min<size_t>(((size_t)M * (W >> 2) + 255) / 256, (size_t)c->sms * 8);
-        LTT_CUDA_OK(launch_k(clip_embed_kernel, dim3(blocks), dim3(256), 0, st, ids, c->tok, c->pos, M, L, W, g.vocab, c->x));
+        LTT_CUDA_OK(launch_k(clip_embed_kernel, dim3(blocks), dim3(256), 0, st, ids, c->tok, c->pos, M, L, W, g.vocab, t.x));
         c->launches++;
     }
-    for (const CLayer& l : c->layers) {
-        RCC(layernorm_launch(c->x, DT_F32, M, W, l.ln1_g, l.ln1_b, g.eps, c->h16, nullptr, st));
-        c->launches++;
-        {
-            GemmEpilogue e;
-            e.bias = l.bqkv;
-            e.out_mode = OUT_QKV;
-            e.q = c->q; e.k = c->k; e.vt = c->vt;
-            e.C = W; e.dhead = 64; e.dpad = 64; e.rows_q = L; e.rows_k = L; e.pitch_v = c->pitch_v; e.tokens = L; e.qkv_base = 0;
-            RCC(clip_gemm(c, st, B, L, 3 * W, c->h16, W, l.wqkv, e));
-        }
-        {
-            AttnProblem p{};
-            p.B = B; p.heads = H; p.dhead = 64; p.dpad = 64; p.nq = L; p.nk = L;
-            p.q = c->q; p.rows_q = L; p.k = c->k; p.rows_k = L; p.vt = c->vt; p.pitch_v = c->pitch_v;
-            p.out = c->a16; p.ldo = W; p.scale = 0.125f; p.causal = 1;
-            RCC(attn_tc_launch(p, st));
-            c->launches++;
-        }
-        {
-            GemmEpilogue e;
-            e.bias = l.bo; e.res = c->x; e.res_dtype = DT_F32; e.ldr = W; e.out = c->x; e.out_dtype = DT_F32; e.ldo = W;
-            RCC(clip_gemm(c, st, 1, M, W, c->a16, W, l.wo, e));
-        }
-        RCC(layernorm_launch(c->x, DT_F32, M, W, l.ln2_g, l.ln2_b, g.eps, c->h16, nullptr, st));
-        c->launches++;
-        {
-            GemmEpilogue e;
-            e.bias = l.b1; e.act = ACT_QUICKGELU; e.out = c->f16; e.out_dtype = DT_F16; e.ldo = g.ffn;
-            RCC(clip_gemm(c, st, 1, M, g.ffn, c->h16, W, l.w1, e));
-        }
-        {
-            GemmEpilogue e;
-            e.bias = l.b2; e.res = c->x; e.res_dtype = DT_F32; e.ldr = W; e.out = c->x; e.out_dtype = DT_F32; e.ldo = W;
-            RCC(clip_gemm(c, st, 1, M, W, c->f16, g.ffn, l.w2, e));
-        }
-    }
+    RCC(tower_run(t, c->sms, st, 1, c->launches));
     float* hid = last_hidden ? last_hidden : c->hid;
-    RCC(layernorm_launch(c->x, DT_F32, M, W, c->fin_g, c->fin_b, g.eps, nullptr, hid, st));
+    RCC(layernorm_launch(t.x, DT_F32, M, W, c->fin_g, c->fin_b, g.eps, nullptr, hid, st));
     c->launches++;
     if (pooled || text_embeds) {
         LTT_CUDA_OK(launch_k(clip_pool_kernel, dim3(B), dim3(256), (size_t)W * 4, st, ids, (const float*)hid, L, W, g.eos_token_id,
@@ -369,5 +565,170 @@ int ltt_clip_encode(ltt_clip* c, const int32_t* ids, int B, int L, float* last_h
 }
 
 int64_t ltt_clip_launch_count(const ltt_clip* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------- vision tower
+int ltt_clip_vision_create(const ltt_clip_vision_config* cfg, int device, ltt_clip_vision** out) {
+    if (!cfg || !out) {
+        set_error("ltt_clip_vision_create: null argument");
+        return -1;
+    }
+    const bool ok = cfg->image_size >= cfg->patch && cfg->patch >= 1 && cfg->image_size % cfg->patch == 0 && cfg->hidden >= 64 &&
+                    cfg->hidden == cfg->heads * 64 && cfg->hidden <= 4096 && cfg->ffn >= 64 && cfg->ffn % 64 == 0 && cfg->layers >= 1 &&
+                    cfg->act == 0 && cfg->proj_dim >= 0 && cfg->eps > 0.f;
+    if (!ok) {
+        set_error("ltt_clip_vision_create: unsupported vision tower (heads of 64, hidden / ffn multiples of 64, quick_gelu)");
+        return -1;
+    }
+    LTT_CUDA_OK(cudaSetDevice(device));
+    ltt_clip_vision* c = new ltt_clip_vision();
+    c->cfg = *cfg;
+    c->device = device;
+    c->G = cfg->image_size / cfg->patch;
+    c->NP = c->G * c->G;
+    c->Kpad = (3 * cfg->patch * cfg->patch + 63) / 64 * 64;
+    c->t.W = cfg->hidden; c->t.heads = cfg->heads; c->t.ffn = cfg->ffn; c->t.eps = cfg->eps;
+    LTT_CUDA_OK(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    *out = c;
+    return 0;
+}
+
+void ltt_clip_vision_destroy(ltt_clip_vision* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    crelease(c->t.wptrs);
+    crelease(c->t.cptrs);
+    crelease(c->wptrs);
+    crelease(c->cptrs);
+    for (auto& kv : c->params) cudaFree(kv.second.dev);
+    delete c;
+}
+
+int ltt_clip_vision_load_param(ltt_clip_vision* c, const char* key, const float* data, const int64_t* shape, int ndim, int is_host) {
+    if (!c || !key || !data || (ndim > 0 && !shape)) {
+        set_error("ltt_clip_vision_load_param: null argument");
+        return -1;
+    }
+    c->finalized = false;
+    return load_param(c->params, c->device, key, data, shape, ndim, is_host);
+}
+
+int ltt_clip_vision_finalize(ltt_clip_vision* c) {
+    if (!c) return -1;
+    LTT_CUDA_OK(cudaSetDevice(c->device));
+    const ltt_clip_vision_config& g = c->cfg;
+    const CParams& params = c->params;
+    const int64_t W = g.hidden, P = g.patch;
+    const std::string vm = "vision_model.";
+    CGET(cls, vm + "embeddings.class_embedding", W)
+    CGET(pw, vm + "embeddings.patch_embedding.weight", W, 3, P, P)
+    CGET(pos, vm + "embeddings.position_embedding.weight", c->NP + 1, W)
+    CGET(g0, vm + "pre_layrnorm.weight", W) CGET(b0, vm + "pre_layrnorm.bias", W)
+    CGET(g1, vm + "post_layernorm.weight", W) CGET(b1, vm + "post_layernorm.bias", W)
+    c->cls = cls->dev; c->pos = pos->dev; c->pre_g = g0->dev; c->pre_b = b0->dev; c->post_g = g1->dev; c->post_b = b1->dev;
+    c->proj = nullptr;
+    if (g.proj_dim > 0) {
+        CGET(vp, "visual_projection.weight", g.proj_dim, W)
+        c->proj = vp->dev;
+    }
+    crelease(c->wptrs);
+    RCC(calloc_dev(c->wptrs, (void**)&c->patch_w, (size_t)W * c->Kpad * 2));
+    clipv_pack_patch_kernel<<<256, 256>>>(pw->dev, (int)W, (int)(3 * P * P), c->Kpad, c->patch_w);
+    LTT_CUDA_OK(cudaGetLastError());
+    RCC(tower_build(c->t, params, vm, g.layers));
+    LTT_CUDA_OK(cudaDeviceSynchronize());
+    c->finalized = true;
+    return 0;
+}
+
+int ltt_clip_vision_encode(ltt_clip_vision* c, const float* pixel_values, int B, float* last_hidden, float* pooled, float* image_embeds,
+                           void* stream) {
+    if (!c || !c->finalized) {
+        set_error("ltt_clip_vision_encode: call ltt_clip_vision_finalize first");
+        return -8;
+    }
+    const ltt_clip_vision_config& g = c->cfg;
+    if (!pixel_values || B < 1 || (!last_hidden && !pooled && !image_embeds)) {
+        set_error("ltt_clip_vision_encode: bad arguments");
+        return -1;
+    }
+    if (image_embeds && !c->proj) {
+        set_error("ltt_clip_vision_encode: image_embeds requested but the tower has no visual_projection (proj_dim = 0)");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LTT_CUDA_OK(cudaSetDevice(c->device));
+    Tower& t = c->t;
+    const int T = c->NP + 1, W = g.hidden, M = B * T;
+    if (B != c->B) {
+        LTT_CUDA_OK(cudaDeviceSynchronize());
+        RCC(tower_workspace(t, B, T));
+        crelease(c->cptrs);
+        RCC(calloc_dev(c->cptrs, (void**)&c->patches, (size_t)B * c->NP * c->Kpad * 2));
+        RCC(calloc_dev(c->cptrs, (void**)&c->pe, (size_t)B * c->NP * W * 4));
+        RCC(calloc_dev(c->cptrs, (void**)&c->xa, (size_t)M * W * 4));
+        c->B = B;
+    }
+    {
+        const size_t n = (size_t)B * c->NP * c->Kpad;
+        LTT_CUDA_OK(launch_k(clipv_patches_kernel, dim3((unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->sms * 16)), dim3(256), 0, st,
+                             pixel_values, B, g.image_size, g.patch, c->G, c->Kpad, c->patches));
+        GemmEpilogue e;
+        e.out = c->pe; e.out_dtype = DT_F32; e.ldo = W;
+        RCC(clip_gemm(c->sms, st, 1, B * c->NP, W, c->patches, c->Kpad, c->patch_w, e));
+        const size_t m = (size_t)M * (W >> 2);
+        LTT_CUDA_OK(launch_k(clipv_assemble_kernel, dim3((unsigned)std::min<size_t>((m + 255) / 256, (size_t)c->sms * 16)), dim3(256), 0, st,
+                             (const float*)c->pe, c->cls, c->pos, B, T, W, c->xa));
+        RCC(layernorm_launch(c->xa, DT_F32, M, W, c->pre_g, c->pre_b, g.eps, nullptr, t.x, st));
+        c->launches += 4;
+    }
+    RCC(tower_run(t, c->sms, st, 0, c->launches));
+    if (last_hidden) {
+        LTT_CUDA_OK(cudaMemcpyAsync(last_hidden, t.x, (size_t)M * W * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (pooled || image_embeds) {
+        LTT_CUDA_OK(launch_k(clipv_pool_kernel, dim3(B), dim3(256), (size_t)W * 4, st, (const float*)t.x, T, W, c->post_g, c->post_b, g.eps,
+                             image_embeds ? c->proj : (const float*)nullptr, g.proj_dim, pooled, image_embeds));
+        c->launches++;
+    }
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int64_t ltt_clip_vision_launch_count(const ltt_clip_vision* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------- reward head
+int ltt_reward_head(const float* txt, const float* pred, const float* gt, int B, int D, const float* const* aes_w,
+                    const float* const* aes_b, const int* aes_dims, const float* miou, const float* laysim, float* reward,
+                    float* clip_reward, float* aes_reward, void* stream) {
+    if (!txt || !pred || !gt || !aes_w || !aes_b || !aes_dims || !reward || B < 1 || D < 1 || D > 1024) {
+        set_error("ltt_reward_head: bad arguments (B=%d, D=%d; D <= 1024)", B, D);
+        return -1;
+    }
+    AesW aw;
+    for (int i = 0; i < 6; ++i) {
+        aw.dim[i] = aes_dims[i];
+        if (aes_dims[i] < 1 || aes_dims[i] > 1024) {
+            set_error("ltt_reward_head: aesthetic layer width %d outside [1, 1024]", aes_dims[i]);
+            return -1;
+        }
+    }
+    if (aw.dim[0] != D || aw.dim[5] != 1) {
+        set_error("ltt_reward_head: aesthetic MLP must map D=%d -> 1 (got %d -> %d)", D, aw.dim[0], aw.dim[5]);
+        return -1;
+    }
+    for (int i = 0; i < 5; ++i) {
+        aw.w[i] = aes_w[i];
+        aw.b[i] = aes_b[i];
+        if (!aw.w[i] || !aw.b[i]) {
+            set_error("ltt_reward_head: null aesthetic layer %d", i);
+            return -1;
+        }
+    }
+    LTT_CUDA_OK(launch_k(reward_head_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, txt, pred, gt, D, aw, miou, laysim, reward,
+                         clip_reward, aes_reward));
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 }  // extern "C"

@@ -91,22 +91,13 @@ def eos_positions(ids: Tensor, eos_token_id: int) -> Tensor:
     return (ids.to(torch.int) == eos_token_id).int().argmax(dim=-1)
 
 
-def clip_text_forward(sd: SD, cfg: dict, ids: Tensor, attention_mask: Optional[Tensor] = None,
-                      prefix: str = "text_model.") -> Tuple[Tensor, Tensor]:
-    """CLIPTextTransformer.forward -> (last_hidden_state [B, L, W], pooler_output [B, W]).
-
-    embeddings (token + learned position) -> pre-LayerNorm blocks with causal self-attention (plus an additive padding
-    mask over keys when ``attention_mask`` is given) -> final LayerNorm -> pooled = row of the end-of-text token."""
-    B, L = ids.shape
-    W, H = cfg["hidden_size"], cfg["num_attention_heads"]
+def encoder_layers(sd: SD, cfg: dict, x: Tensor, mask: Optional[Tensor], prefix: str) -> Tensor:
+    """CLIPEncoder: pre-LayerNorm blocks (CLIPEncoderLayer: x + attn(LN1(x)), x + mlp(LN2(x))) shared by both towers;
+    ``mask`` is the additive attention mask ([.., L, L], broadcast over batch / heads) or None (vision tower)."""
+    B, L, W = x.shape
+    H = cfg["num_attention_heads"]
     d = W // H
     eps = cfg["layer_norm_eps"]
-    x = F.embedding(ids, sd[prefix + "embeddings.token_embedding.weight"]) + sd[prefix + "embeddings.position_embedding.weight"][:L]
-    neg = torch.finfo(x.dtype).min
-    mask = torch.full((L, L), neg, dtype=x.dtype, device=x.device).triu(1)[None, None]
-    if attention_mask is not None:
-        mask = mask + (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * neg
-        mask = mask.clamp_min(neg)
     for i in range(cfg["num_hidden_layers"]):
         p = f"{prefix}encoder.layers.{i}."
         h = F.layer_norm(x, (W,), sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"], eps)
@@ -114,12 +105,32 @@ def clip_text_forward(sd: SD, cfg: dict, ids: Tensor, attention_mask: Optional[T
         k = F.linear(h, sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"])
         v = F.linear(h, sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"])
         q, k, v = (t.view(B, L, H, d).transpose(1, 2) for t in (q, k, v))
-        w = torch.softmax(q @ k.transpose(-1, -2) + mask, dim=-1)
+        s = q @ k.transpose(-1, -2)
+        w = torch.softmax(s if mask is None else s + mask, dim=-1)
         a = (w @ v).transpose(1, 2).reshape(B, L, W)
         x = x + F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
         h = F.layer_norm(x, (W,), sd[p + "layer_norm2.weight"], sd[p + "layer_norm2.bias"], eps)
         h = _act(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]), cfg["hidden_act"])
         x = x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    return x
+
+
+def clip_text_forward(sd: SD, cfg: dict, ids: Tensor, attention_mask: Optional[Tensor] = None,
+                      prefix: str = "text_model.") -> Tuple[Tensor, Tensor]:
+    """CLIPTextTransformer.forward -> (last_hidden_state [B, L, W], pooler_output [B, W]).
+
+    embeddings (token + learned position) -> pre-LayerNorm blocks with causal self-attention (plus an additive padding
+    mask over keys when ``attention_mask`` is given) -> final LayerNorm -> pooled = row of the end-of-text token."""
+    B, L = ids.shape
+    W = cfg["hidden_size"]
+    eps = cfg["layer_norm_eps"]
+    x = F.embedding(ids, sd[prefix + "embeddings.token_embedding.weight"]) + sd[prefix + "embeddings.position_embedding.weight"][:L]
+    neg = torch.finfo(x.dtype).min
+    mask = torch.full((L, L), neg, dtype=x.dtype, device=x.device).triu(1)[None, None]
+    if attention_mask is not None:
+        mask = mask + (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * neg
+        mask = mask.clamp_min(neg)
+    x = encoder_layers(sd, cfg, x, mask, prefix)
     x = F.layer_norm(x, (W,), sd[prefix + "final_layer_norm.weight"], sd[prefix + "final_layer_norm.bias"], eps)
     pooled = x[torch.arange(B, device=x.device), eos_positions(ids, cfg["eos_token_id"])]
     return x, pooled

@@ -52,5 +52,32 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def hf_vision_model(cfg, sd):
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    keys = ("image_size", "patch_size", "hidden_size", "num_attention_heads", "num_hidden_layers", "intermediate_size",
+            "layer_norm_eps", "hidden_act", "projection_dim")
+    m = CLIPVisionModel(CLIPVisionConfig(**{k: cfg[k] for k in keys})).eval()
+    missing, unexpected = m.load_state_dict({k: v for k, v in sd.items() if k.startswith("vision_model.")}, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    return m
+
+
+def main_vision():
+    from oracle import clip_vision_oracle as cv
+    import transformers
+    cfg = cv.tiny_clip_vision_config()
+    sd = cv.random_state_dict(cfg, seed=6)
+    m = hf_vision_model(cfg, sd)
+    px = torch.randn(3, 3, cfg["image_size"], cfg["image_size"], generator=torch.Generator().manual_seed(1)) * 1.2
+    with torch.no_grad():
+        o = m(pixel_values=px)
+    out = dict(cfg=cfg, seed=6, pixel_values=px, last_hidden_state=o.last_hidden_state.clone(), pooler_output=o.pooler_output.clone(),
+               image_embeds=torch.nn.functional.linear(o.pooler_output, sd["visual_projection.weight"]), transformers=transformers.__version__)
+    path = os.path.join(ROOT, "tests", "golden", "clip_vision.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path), "bytes", tuple(o.last_hidden_state.shape))
+
+
 if __name__ == "__main__":
+    main_vision()
     main()

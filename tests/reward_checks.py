@@ -1,0 +1,189 @@
+"""Reward-path parity: the sm_100a CLIP vision tower, the reward-head kernel and the Reward mirror
+(layoutllm_t2i_b200.reward) through the C-ABI against oracle/clip_vision_oracle.py -- the fp32 restatement pinned to the
+transformers implementation / the reference's own AestheticMLP -- on the same seeded weights and inputs.  The reference
+computes the towers in fp32; the engine uses fp16 tensor-core operands with fp32 accumulation, so tower gates are relative-L2
+tolerances (written with each case); the reward head itself is fp32 arithmetic (1e-5).
+Used by tests/test_reward_gpu.py."""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs"))
+from oracle import clip_text_oracle as co  # noqa: E402
+from oracle import clip_vision_oracle as cv  # noqa: E402
+from oracle.ref_loader import true_fp32  # noqa: E402
+
+DEV = "cuda"
+_CACHE = {}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _vcfg(which):
+    return cv.tiny_clip_vision_config() if which == "tiny" else cv.default_clip_vision_config()
+
+
+def vision(which, seed):
+    key = ("v", which, seed)
+    if key not in _CACHE:
+        from layoutllm_t2i_b200.clip import ClipVisionEncoder
+        cfg = _vcfg(which)
+        sd = {k: v.to(DEV) for k, v in cv.random_state_dict(cfg, seed=seed).items()}
+        enc = ClipVisionEncoder(cfg, 0)
+        enc.load_state_dict(sd)
+        enc.finalize()
+        _CACHE[key] = (cfg, sd, enc)
+    return _CACHE[key]
+
+
+def pixels(cfg, B, seed=0):
+    # CLIPProcessor output range: (x / 255 - mean) / std  ~  [-1.8, 2.2]
+    return (torch.rand(B, 3, cfg["image_size"], cfg["image_size"], generator=torch.Generator().manual_seed(seed)) * 4.0 - 1.8).to(DEV)
+
+
+def check_vision(which, B, seed=0, what="hidden"):
+    cfg, sd, enc = vision(which, seed)
+    px = pixels(cfg, B, seed + 3)
+    hid, pooled, emb = enc.encode(px, want_hidden=True)
+    with torch.no_grad(), true_fp32():
+        z, p = cv.clip_vision_forward(sd, cfg, px)
+        e = torch.nn.functional.linear(p, sd["visual_projection.weight"])
+    return {"hidden": rel(hid, z), "pooled": rel(pooled, p), "embeds": rel(emb, e)}[what]
+
+
+def check_vision_golden():
+    """Engine against the committed transformers outputs themselves (tests/golden/clip_vision.pt)."""
+    from layoutllm_t2i_b200.clip import ClipVisionEncoder
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clip_vision.pt"))
+    enc = ClipVisionEncoder(g["cfg"], 0)
+    enc.load_state_dict(cv.random_state_dict(g["cfg"], seed=g["seed"]))
+    hid, pooled, emb = enc.encode(g["pixel_values"], want_hidden=True)
+    err = max(rel(hid, g["last_hidden_state"]), rel(pooled, g["pooler_output"]), rel(emb, g["image_embeds"]))
+    enc.close()
+    return err
+
+
+def check_vision_batch_invariance(which="tiny"):
+    """image i of a batch == image i alone (no cross-image leakage through the [B * T] row packing), to fp16 tile noise."""
+    cfg, sd, enc = vision(which, 0)
+    px = pixels(cfg, 4, 11)
+    all_ = enc.encode(px)[2].clone()
+    one = torch.cat([enc.encode(px[i:i + 1])[2] for i in range(4)])
+    return rel(one, all_)
+
+
+def check_reward_head(B, D, seed=0, with_layout=True, zero_row=False):
+    from layoutllm_t2i_b200.reward import reward_head
+    g = torch.Generator().manual_seed(seed)
+    t, p, gt = (torch.randn(B, D, generator=g).to(DEV) for _ in range(3))
+    if zero_row:
+        p[0] = 0
+    aes = {k: v.to(DEV) for k, v in cv.aesthetic_state_dict(D, seed=seed + 1).items()}
+    miou = torch.rand(B, generator=g).to(DEV) if with_layout else None
+    lay = torch.rand(B, generator=g).to(DEV) if with_layout else None
+    r, c, a = reward_head(t, p, gt, aes, miou, lay)
+    z = torch.zeros(B, device=DEV)
+    with torch.no_grad(), true_fp32():
+        rr, cc, aa = cv.reward_forward(t, p, gt, aes, z if miou is None else miou, z if lay is None else lay)
+    return max(float((r - rr).abs().max()), float((c - cc).abs().max()), float((a - aa).abs().max()))
+
+
+class _Processor:
+    """CLIPProcessor stand-in (host side): uint8 HWC images -> resized / normalised pixel_values."""
+
+    def __init__(self, size):
+        self.size = size
+
+    def __call__(self, images=None, return_tensors="pt", **kw):
+        x = torch.stack([torch.as_tensor(im).permute(2, 0, 1).float() / 255.0 for im in images])
+        x = torch.nn.functional.interpolate(x, size=(self.size, self.size), mode="bilinear", align_corners=False)
+        mean = torch.tensor([0.4815, 0.4578, 0.4082]).view(1, 3, 1, 1)
+        std = torch.tensor([0.2686, 0.2613, 0.2758]).view(1, 3, 1, 1)
+        return dict(pixel_values=(x - mean) / std)
+
+
+def check_reward_model(which, B=3, seed=0, reference_metrics=True):
+    """Reward.forward (captions, generated images, ground-truth images, layouts) against the oracle composition of
+    models/policy.py:106-139; the layout terms from the reference's own tools/metrics.py (staged under oracle/_ref)."""
+    from ltt_test_stubs import HashTokenizer
+    from layoutllm_t2i_b200.reward import COCO_LABELS, Reward
+    tcfg = dict(co.tiny_clip_text_config() if which == "tiny" else co.default_clip_text_config())
+    vcfg = _vcfg(which)
+    tcfg["projection_dim"] = vcfg["projection_dim"]
+    sd = dict(co.random_state_dict(tcfg, seed=seed))
+    sd.update(cv.random_state_dict(vcfg, seed=seed + 1))
+    aes = cv.aesthetic_state_dict(vcfg["projection_dim"], seed=seed + 2)
+    metrics = None
+    if reference_metrics:
+        from oracle import ref_loader as rl
+        assert rl.available(), "oracle/_ref is not staged"
+        with rl.reference_tree():
+            sys.path.insert(0, rl.REF_ROOT)
+            try:
+                from tools.metrics import compute_docsim, compute_maximum_iou
+            finally:
+                sys.path.remove(rl.REF_ROOT)
+        metrics = (compute_maximum_iou, compute_docsim)
+    tok, proc = HashTokenizer(tcfg["vocab_size"]), _Processor(vcfg["image_size"])
+    rm = Reward(sd, aes, tok, proc, 0, text_config=tcfg, vision_config=vcfg, labels=COCO_LABELS[:12], metrics=metrics)
+    g = torch.Generator().manual_seed(seed + 5)
+    captions = ["a person riding a bicycle", "two cars and a bus on the street", "a boat"][:B]
+    imgs_pred = [(torch.rand(64, 64, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(B)]
+    imgs_gt = [(torch.rand(80, 72, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(B)]
+    box = lambda: sorted(torch.rand(2, generator=g).tolist()) + sorted(torch.rand(2, generator=g).tolist())  # noqa: E731
+    lay_gt = [([box(), box()], ["person", "bicycle"]), ([box(), box(), box()], ["car", "car", "bus"]), ([box()], ["boat"])][:B]
+    lay_pred = [([box(), box()], ["person", "bike rider"]), ([box(), box()], ["car", "bus"]), ([box()], ["boat"])][:B]   # one open-set label
+    reward, clip_r, aes_r, miou, laysim = rm.forward(captions, imgs_pred, imgs_gt, lay_pred, lay_gt, return_parts=True)
+    # ---- oracle composition
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    aesd = {k: v.to(DEV) for k, v in aes.items()}
+    with torch.no_grad(), true_fp32():
+        t = co.text_features(sdd, tcfg, tok(captions, padding=True)["input_ids"].to(DEV), tok(captions, padding=True)["attention_mask"].to(DEV))
+        p = cv.image_features(sdd, vcfg, proc(images=imgs_pred)["pixel_values"].to(DEV))
+        q = cv.image_features(sdd, vcfg, proc(images=imgs_gt)["pixel_values"].to(DEV))
+        want, want_clip, want_aes = cv.reward_forward(t, p, q, aesd, miou.to(DEV), laysim.to(DEV))
+    assert reward.shape == (B,) and torch.isfinite(reward).all()
+    return max(float((clip_r - want_clip).abs().max()), float((aes_r - want_aes).abs().max()) * 0.1, float((reward - want).abs().max()))
+
+
+# towers: fp16 operands / fp32 accumulate against an fp32 reference over 24 layers (measured values: profiles/r02_reward_parity.txt)
+TOL = 3e-3
+ALL = [
+    ("vision tower tiny vs transformers fixture", check_vision_golden, {}, TOL),
+    ("vision tower tiny hidden B=3", check_vision, dict(which="tiny", B=3), TOL),
+    ("vision tower tiny embeds B=1", check_vision, dict(which="tiny", B=1, what="embeds"), TOL),
+    ("vision tower batch invariance", check_vision_batch_invariance, {}, TOL),
+    ("vision tower ViT-L/14 hidden B=2", check_vision, dict(which="full", B=2), TOL),
+    ("vision tower ViT-L/14 pooled B=5", check_vision, dict(which="full", B=5, what="pooled"), TOL),
+    ("vision tower ViT-L/14 image_embeds B=16", check_vision, dict(which="full", B=16, what="embeds"), TOL),
+    ("reward head D=768 B=8", check_reward_head, dict(B=8, D=768), 1e-5),
+    ("reward head D=64 B=1, no layout terms", check_reward_head, dict(B=1, D=64, with_layout=False), 1e-5),
+    ("reward head zero feature row", check_reward_head, dict(B=3, D=768, zero_row=True), 1e-5),
+    # reward = cos + cos + 0.1 aes + ...: absolute error of the scalar (|reward| ~ 1 .. 20)
+    ("Reward.forward tiny towers", check_reward_model, dict(which="tiny"), 5e-3),
+    ("Reward.forward ViT-L/14 towers", check_reward_model, dict(which="full"), 5e-3),
+]
+
+
+def main():
+    for name, fn, kw, tol in ALL:
+        try:
+            err = fn(**kw)
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print(f"EXC  {name:64s} {ex!r}"[:300], flush=True)
+            continue
+        print(f"{'ok ' if err < tol else 'FAIL'} {name:64s} {err:.3e}  (gate {tol:g})", flush=True)
+
+
+if __name__ == "__main__":
+    main()

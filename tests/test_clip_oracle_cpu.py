@@ -67,3 +67,45 @@ def test_eos_position_rules():
     assert co.eos_positions(ids, 2).tolist() == [2, 1]
     assert co.eos_positions(ids, 999).tolist() == [2, 1]
     assert co.eos_positions(torch.tensor([[998, 7, 3, 999]]), 999).tolist() == [3]
+
+
+# ------------------------------------------------------------------------------------------------- vision tower / reward head
+def test_vision_oracle_matches_transformers_fixture():
+    from oracle import clip_vision_oracle as cv
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "clip_vision.pt"))
+    sd = cv.random_state_dict(g["cfg"], seed=g["seed"])
+    with torch.no_grad():
+        z, pooled = cv.clip_vision_forward(sd, g["cfg"], g["pixel_values"])
+        emb = cv.image_features(sd, g["cfg"], g["pixel_values"])
+    assert rel(z, g["last_hidden_state"]) < 2e-6 and rel(pooled, g["pooler_output"]) < 2e-6 and rel(emb, g["image_embeds"]) < 2e-6
+
+
+def test_reward_head_oracle_matches_reference_pieces():
+    """AestheticMLP / normalized are the reference's own code (tools/aesthetic.py, staged under oracle/_ref); the reward
+    expression is models/policy.py:115-139 evaluated with them."""
+    from oracle import clip_vision_oracle as cv
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("oracle/_ref not staged")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "stubs"))
+    with rl.reference_tree():
+        sys.path.insert(0, rl.REF_ROOT)
+        try:
+            from tools.aesthetic import AestheticMLP, normalized
+        finally:
+            sys.path.remove(rl.REF_ROOT)
+    sd = cv.aesthetic_state_dict(64, seed=3)
+    m = AestheticMLP(64).eval()
+    m.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(0)
+    t, p, g = (torch.randn(5, 64, generator=gen) for _ in range(3))
+    miou, laysim = torch.rand(5, generator=gen), torch.rand(5, generator=gen)
+    with torch.no_grad():
+        import torch.nn.functional as F
+        tn, pn, gn = F.normalize(t, dim=-1), F.normalize(p, dim=-1), F.normalize(g, dim=-1)
+        clip_reward = (tn * pn).sum(dim=-1) + (gn * pn).sum(dim=-1)
+        aes = m(torch.from_numpy(normalized(pn.numpy())).float()).flatten()
+        want = clip_reward + aes * 0.1 + miou * 10 + laysim * 10
+        got, got_clip, got_aes = cv.reward_forward(t, p, g, sd, miou, laysim)
+    assert rel(got_clip, clip_reward) < 1e-6 and rel(got_aes, aes) < 1e-5 and rel(got, want) < 1e-6
