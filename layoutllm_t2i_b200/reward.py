@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .clip import ClipTextEncoder, ClipVisionEncoder
+from .clip import ClipModelAdapter, ClipTextEncoder, ClipVisionEncoder
 
 COCO_LABELS = ['person', 'bicycle', 'car', 'motorcycle', 'airplane', 'bus', 'train', 'truck', 'boat', 'traffic light', 'fire hydrant',
                'stop sign', 'parking meter', 'bench', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant', 'bear', 'zebra',
@@ -77,9 +77,18 @@ class Reward:
         self.aesthetic_sd = {k: v.detach().to(self.device, torch.float32) for k, v in aesthetic_sd.items()}
         self.tokenizer, self.processor = tokenizer, processor
         self._metrics = tuple(metrics) if metrics is not None else None
+        # what the callers read off the reward model: `.model` / `.processor` go to run_batch_images as clip_model /
+        # clip_processor (train_rl.py:91), `.tokenizer` / `.model.get_text_features` / `.device` to load_data (data.py:41-54)
+        self.model = ClipModelAdapter(self.text, self.vision)
         self.labels = list(labels)
         self.label2index = {l: i for i, l in enumerate(self.labels)}
         self.emb_labels()
+
+    def to(self, *a, **k):          # train_rl.py:326 (`reward_model.to(device)`): the towers already live on `device`
+        return self
+
+    def eval(self):
+        return self
 
     # ---- policy.py:53-75
     def get_text_features(self, texts: Sequence[str]) -> torch.Tensor:

@@ -141,6 +141,12 @@ def check_reward_model(which, B=3, seed=0, reference_metrics=True):
     lay_gt = [([box(), box()], ["person", "bicycle"]), ([box(), box(), box()], ["car", "car", "bus"]), ([box()], ["boat"])][:B]
     lay_pred = [([box(), box()], ["person", "bike rider"]), ([box(), box()], ["car", "bus"]), ([box()], ["boat"])][:B]   # one open-set label
     reward, clip_r, aes_r, miou, laysim = rm.forward(captions, imgs_pred, imgs_gt, lay_pred, lay_gt, return_parts=True)
+    # the attributes the callers read off the reward model (train_rl.py:91,326; data.py:41-54)
+    assert rm.to(DEV) is rm and rm.processor is proc and rm.tokenizer is tok
+    inputs = tok(captions, padding=True, return_tensors="pt")
+    feats = rm.model.get_text_features(**{k: v.to(rm.device) for k, v in inputs.items()})
+    assert torch.equal(feats, rm.get_text_features(captions)) and rm.model.projection_dim == vcfg["projection_dim"]
+    assert rm.model.get_image_features(pixel_values=proc(images=imgs_pred)["pixel_values"]).shape == (B, vcfg["projection_dim"])
     # ---- oracle composition
     sdd = {k: v.to(DEV) for k, v in sd.items()}
     aesd = {k: v.to(DEV) for k, v in aes.items()}
