@@ -202,6 +202,13 @@ int ltt_clip_vision_finalize(ltt_clip_vision* c);
  * (= pooler_output), image_embeds [B, proj_dim] (= get_image_features). */
 int ltt_clip_vision_encode(ltt_clip_vision* c, const float* pixel_values, int B, float* last_hidden, float* pooled,
                            float* image_embeds, void* stream);
+/* The image preprocessing in front of the tower, on the device (replaces `self.processor(images=..., return_tensors="pt")`
+ * of Reward.forward, models/policy.py:109-112 = transformers CLIPImageProcessor on PIL images: shortest edge -> image_size
+ * with Pillow's BICUBIC resize, centre crop, * 1/255, (x - mean) / std): images [B, H, W, 3] uint8 on the device (the
+ * layout ltt_vae_decode writes) -> pixel_values [B, 3, image_size, image_size] fp32.  Bit-exact against Pillow's
+ * Resample.c (integer arithmetic, 8-bit rounding after each pass) and the float32 normalisation. */
+int ltt_clip_vision_preprocess(ltt_clip_vision* c, const uint8_t* images, int B, int H, int W, const float* mean, const float* std_,
+                               float* pixel_values, void* stream);
 int64_t ltt_clip_vision_launch_count(const ltt_clip_vision* c);
 
 /* Reward.forward models/policy.py:115-139 from the feature matrices: txt / pred / gt [B, D] fp32 (get_text_features of the

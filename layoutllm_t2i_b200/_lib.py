@@ -79,6 +79,7 @@ _SIGS = {
     "ltt_clip_vision_load_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
     "ltt_clip_vision_finalize": (_i, [_vp]),
     "ltt_clip_vision_encode": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ltt_clip_vision_preprocess": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "ltt_clip_vision_launch_count": (_i64, [_vp]),
     "ltt_reward_head": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp]),
     "ltt_op_linear": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _f, _i, _vp, _i, _i, _vp]),

@@ -30,6 +30,8 @@ def default_clip_text_config() -> dict:
 
 
 _PREFIXES = ("transformer.text_model.", "text_model.")
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)        # transformers OPENAI_CLIP_MEAN / OPENAI_CLIP_STD
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
 class ClipTextEncoder:
@@ -180,6 +182,23 @@ class ClipVisionEncoder:
                     "ltt_clip_vision_encode")
         self._keep = px
         return hid, pooled, emb
+
+    def preprocess(self, images_u8: torch.Tensor, mean=CLIP_MEAN, std=CLIP_STD) -> torch.Tensor:
+        """[B, H, W, 3] uint8 images ON THE DEVICE (what ``VaeDecoder.decode(..., images_u8=True)`` returns) -> pixel_values
+        [B, 3, S, S]: the CLIPImageProcessor pipeline of ``Reward.forward`` (models/policy.py:109-112) without the round trip
+        through PIL on the host; bit-exact against Pillow's BICUBIC resize + the float32 rescale / normalise."""
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[-1] != 3:
+            raise L.LttError(f"ClipVisionEncoder.preprocess: expected uint8 [B, H, W, 3], got {images_u8.dtype} {tuple(images_u8.shape)}")
+        im = images_u8.detach().to(self.device).contiguous()
+        B, H, W, _ = im.shape
+        S = self.cfg["image_size"]
+        out = torch.empty(B, 3, S, S, device=self.device)
+        m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.ltt_clip_vision_preprocess(self._h, L.ptr(im), B, H, W, m, s, L.ptr(out), L.stream_ptr()),
+                    "ltt_clip_vision_preprocess")
+        self._keep_img = im
+        return out
 
     @property
     def launch_count(self) -> int:

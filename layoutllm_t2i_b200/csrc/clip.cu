@@ -193,6 +193,66 @@ __global__ void __launch_bounds__(256) clipv_pool_kernel(const float* __restrict
     }
 }
 
+// ---- image preprocessing in front of the vision tower (transformers CLIPImageProcessor with the PIL backend: Pillow's
+// two-pass BICUBIC resize -- src/libImaging/Resample.c, 8-bit rounding after each pass, horizontal first -- centre crop,
+// rescale, normalise).  Integer arithmetic on bytes: bit-exact against Pillow.
+constexpr int PRE_BITS = 32 - 8 - 2;      // Resample.c PRECISION_BITS
+__device__ __forceinline__ uint8_t pre_clip8(int v) {
+    v >>= PRE_BITS;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+// in [B, H, W, 3] u8 -> tmp [B, H, rw, 3] u8
+__global__ void __launch_bounds__(256) clip_resize_h_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int rw,
+                                                            const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                            uint8_t* __restrict__ tmp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t total = (size_t)B * H * rw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % rw);
+        const size_t row = i / rw;                  // b * H + y
+        const int xmin = bounds[2 * xo], n = bounds[2 * xo + 1];
+        const uint8_t* src = in + (row * W + xmin) * 3;
+        const int* k = kk + (size_t)xo * ksize;
+        int a0 = 1 << (PRE_BITS - 1), a1 = a0, a2 = a0;
+        for (int x = 0; x < n; ++x) {
+            const int w = k[x];
+            a0 += src[3 * x] * w;
+            a1 += src[3 * x + 1] * w;
+            a2 += src[3 * x + 2] * w;
+        }
+        uint8_t* dst = tmp + i * 3;
+        dst[0] = pre_clip8(a0); dst[1] = pre_clip8(a1); dst[2] = pre_clip8(a2);
+    }
+}
+// tmp [B, H, rw, 3] u8 -> vertical pass at the cropped positions only -> out [B, 3, S, S] fp32 through the [3][256] table
+__global__ void __launch_bounds__(256) clip_resize_v_kernel(const uint8_t* __restrict__ tmp, int B, int H, int rw, int S, int top,
+                                                            int left, const int* __restrict__ bounds, const int* __restrict__ kk,
+                                                            int ksize, const float* __restrict__ lut, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t total = (size_t)B * S * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(i % S), yo = (int)((i / S) % S), b = (int)(i / ((size_t)S * S));
+        const int yy = yo + top;
+        const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+        const uint8_t* src = tmp + (((size_t)b * H + ymin) * rw + xo + left) * 3;
+        const int* k = kk + (size_t)yy * ksize;
+        int a0 = 1 << (PRE_BITS - 1), a1 = a0, a2 = a0;
+        for (int y = 0; y < n; ++y) {
+            const int w = k[y];
+            const uint8_t* p = src + (size_t)y * rw * 3;
+            a0 += p[0] * w;
+            a1 += p[1] * w;
+            a2 += p[2] * w;
+        }
+        const size_t plane = (size_t)S * S, o = (size_t)b * 3 * plane + (size_t)yo * S + xo;
+        out[o] = lut[pre_clip8(a0)];
+        out[o + plane] = lut[256 + pre_clip8(a1)];
+        out[o + 2 * plane] = lut[512 + pre_clip8(a2)];
+    }
+}
+
 // ---- reward head (Reward.forward, models/policy.py:115-139; AestheticMLP tools/aesthetic.py:15-31): one CTA per sample.
 // clip = cos(txt, pred) + cos(gt, pred); aes = the five bias-affine layers (eval: dropout is the identity, there is no
 // activation) on pred / |pred|; reward = clip + 0.1 aes + 10 miou + 10 laysim.   D <= 1024, layer widths <= 1024.
@@ -451,8 +511,58 @@ struct ltt_clip_vision {
     int B = 0;
     __half* patches = nullptr;
     float *pe = nullptr, *xa = nullptr;
+    // preprocessing workspace for (B, H, W) + normalisation table
+    std::vector<void*> pptrs;
+    int pB = 0, pH = 0, pW = 0, p_rw = 0, p_rh = 0, p_top = 0, p_left = 0, p_ksx = 0, p_ksy = 0;
+    float p_mean[3] = {0, 0, 0}, p_std[3] = {0, 0, 0};
+    int *p_bx = nullptr, *p_kx = nullptr, *p_by = nullptr, *p_ky = nullptr;
+    float* p_lut = nullptr;
+    uint8_t* p_tmp = nullptr;
     int64_t launches = 0;
 };
+
+namespace ltt {
+
+// Resample.c bicubic_filter / precompute_coeffs / normalize_coeffs_8bpc for the full-image box, in the same double arithmetic
+static double pil_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+static int pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
+    double scale = (double)in_size / out_size, filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 2.0 * filterscale;
+    const int ksize = (int)ceil(support) * 2 + 1;
+    bounds.assign((size_t)out_size * 2, 0);
+    kk.assign((size_t)out_size * ksize, 0);
+    const double ss = 1.0 / filterscale;
+    std::vector<double> w(ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) {
+            w[x] = pil_bicubic((x + xmin - center + 0.5) * ss);
+            ww += w[x];
+        }
+        for (int x = 0; x < xmax; ++x) {
+            const double v = ww != 0.0 ? w[x] / ww : w[x];
+            kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << PRE_BITS)) : (int)(0.5 + v * (1 << PRE_BITS));
+        }
+        bounds[2 * xx] = xmin;
+        bounds[2 * xx + 1] = xmax;
+    }
+    return ksize;
+}
+
+}  // namespace ltt
 
 extern "C" {
 
@@ -600,6 +710,7 @@ void ltt_clip_vision_destroy(ltt_clip_vision* c) {
     crelease(c->t.cptrs);
     crelease(c->wptrs);
     crelease(c->cptrs);
+    crelease(c->pptrs);
     for (auto& kv : c->params) cudaFree(kv.second.dev);
     delete c;
 }
@@ -691,6 +802,59 @@ int ltt_clip_vision_encode(ltt_clip_vision* c, const float* pixel_values, int B,
                              image_embeds ? c->proj : (const float*)nullptr, g.proj_dim, pooled, image_embeds));
         c->launches++;
     }
+    LTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int ltt_clip_vision_preprocess(ltt_clip_vision* c, const uint8_t* images, int B, int H, int W, const float* mean, const float* std_,
+                               float* pixel_values, void* stream) {
+    if (!c || !images || !mean || !std_ || !pixel_values || B < 1 || H < 1 || W < 1) {
+        set_error("ltt_clip_vision_preprocess: bad arguments");
+        return -1;
+    }
+    const int S = c->cfg.image_size;
+    cudaStream_t st = (cudaStream_t)stream;
+    LTT_CUDA_OK(cudaSetDevice(c->device));
+    const bool same_norm = memcmp(mean, c->p_mean, 12) == 0 && memcmp(std_, c->p_std, 12) == 0;
+    if (B != c->pB || H != c->pH || W != c->pW || !same_norm) {
+        LTT_CUDA_OK(cudaDeviceSynchronize());
+        crelease(c->pptrs);
+        // shortest edge -> S, long edge int(S * long / short) (transformers get_resize_output_image_size), centre crop S x S
+        const int shortE = W <= H ? W : H, longE = W <= H ? H : W;
+        const int new_long = (int)((double)S * longE / shortE);
+        c->p_rh = W <= H ? new_long : S;
+        c->p_rw = W <= H ? S : new_long;
+        c->p_top = (c->p_rh - S) / 2;
+        c->p_left = (c->p_rw - S) / 2;
+        std::vector<int> bx, kx, by, ky;
+        c->p_ksx = pil_coeffs(W, c->p_rw, bx, kx);
+        c->p_ksy = pil_coeffs(H, c->p_rh, by, ky);
+        std::vector<float> lut(3 * 256);
+        for (int ch = 0; ch < 3; ++ch)
+            for (int u = 0; u < 256; ++u) {
+                const float v = (float)((double)u * (1.0 / 255.0));      // rescale in float64, cast to float32
+                lut[ch * 256 + u] = (v - mean[ch]) / std_[ch];          // normalize in float32
+            }
+        auto up = [&](auto** dst, const void* src, size_t bytes) -> int {
+            RCC(calloc_dev(c->pptrs, (void**)dst, bytes));
+            LTT_CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+            return 0;
+        };
+        RCC(up(&c->p_bx, bx.data(), bx.size() * 4)); RCC(up(&c->p_kx, kx.data(), kx.size() * 4));
+        RCC(up(&c->p_by, by.data(), by.size() * 4)); RCC(up(&c->p_ky, ky.data(), ky.size() * 4));
+        RCC(up(&c->p_lut, lut.data(), lut.size() * 4));
+        RCC(calloc_dev(c->pptrs, (void**)&c->p_tmp, (size_t)B * H * c->p_rw * 3));
+        memcpy(c->p_mean, mean, 12);
+        memcpy(c->p_std, std_, 12);
+        c->pB = B; c->pH = H; c->pW = W;
+    }
+    const size_t n1 = (size_t)B * H * c->p_rw, n2 = (size_t)B * S * S;
+    LTT_CUDA_OK(launch_k(clip_resize_h_kernel, dim3((unsigned)std::min<size_t>((n1 + 255) / 256, (size_t)c->sms * 16)), dim3(256), 0, st,
+                         images, B, H, W, c->p_rw, (const int*)c->p_bx, (const int*)c->p_kx, c->p_ksx, c->p_tmp));
+    LTT_CUDA_OK(launch_k(clip_resize_v_kernel, dim3((unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)c->sms * 16)), dim3(256), 0, st,
+                         (const uint8_t*)c->p_tmp, B, H, c->p_rw, S, c->p_top, c->p_left, (const int*)c->p_by, (const int*)c->p_ky,
+                         c->p_ksy, (const float*)c->p_lut, pixel_values));
+    c->launches += 2;
     LTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

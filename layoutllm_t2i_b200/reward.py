@@ -98,6 +98,13 @@ class Reward:
     def get_image_features(self, images) -> torch.Tensor:
         return self.vision.encode(self.processor(images=images, return_tensors="pt")["pixel_values"])[2]
 
+    def _pixel_values(self, images) -> torch.Tensor:
+        """uint8 [B, H, W, 3] tensors already on the device (the decoder's images) are preprocessed there -- the RL loop's
+        generated images never visit the host; anything else (PIL images, arrays) goes through the caller's processor."""
+        if torch.is_tensor(images) and images.dtype == torch.uint8 and images.is_cuda:
+            return self.vision.preprocess(images)
+        return self.processor(images=images, return_tensors="pt")["pixel_values"].to(self.device)
+
     def emb_labels(self) -> None:
         self.labels_emb = torch.nn.functional.normalize(self.get_text_features(self.labels), dim=-1)
 
@@ -132,8 +139,7 @@ class Reward:
     @torch.no_grad()
     def forward(self, captions: List[str], imgs_pred, imgs_gt, layout_pred, layout_gt, return_parts: bool = False):
         txt = self.get_text_features(captions)
-        px = torch.cat([self.processor(images=imgs_pred, return_tensors="pt")["pixel_values"],
-                        self.processor(images=imgs_gt, return_tensors="pt")["pixel_values"]])
+        px = torch.cat([self._pixel_values(imgs_pred), self._pixel_values(imgs_gt)])
         emb = self.vision.encode(px)[2]                                   # ONE vision pass over generated + ground-truth images
         B = txt.shape[0]
         miou, laysim = self._layout_terms(layout_pred, layout_gt)

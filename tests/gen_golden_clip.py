@@ -78,6 +78,23 @@ def main_vision():
     print("wrote", path, os.path.getsize(path), "bytes", tuple(o.last_hidden_state.shape))
 
 
+def main_preprocess():
+    """Outputs of the PIL-backed transformers CLIP image processor (the reference-era behaviour; the default processor of
+    transformers 5 resizes with torchvision and differs by one grey level on ~0.4 % of the pixels) on small seeded images."""
+    import numpy as np
+    from PIL import Image
+    from transformers.models.clip import CLIPImageProcessorPil
+    rng = np.random.default_rng(5)
+    shapes = [(70, 90), (64, 64), (33, 120), (32, 32), (20, 27)]          # down- and up-scaling, crop on either axis, identity
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    p = CLIPImageProcessorPil(size={"shortest_edge": 32}, crop_size={"height": 32, "width": 32})
+    pv = np.concatenate([p(images=[Image.fromarray(i)], return_tensors="np")["pixel_values"] for i in imgs])
+    path = os.path.join(ROOT, "tests", "golden", "clip_preprocess.npz")
+    np.savez_compressed(path, pixel_values=pv, size=32, **{f"img{i}": im for i, im in enumerate(imgs)})
+    print("wrote", path, os.path.getsize(path), "bytes", pv.shape)
+
+
 if __name__ == "__main__":
+    main_preprocess()
     main_vision()
     main()

@@ -27,6 +27,8 @@ def rel(a, b):
 
 
 def _vcfg(which):
+    if which == "tiny224":
+        return dict(cv.tiny_clip_vision_config(), image_size=224)
     return cv.tiny_clip_vision_config() if which == "tiny" else cv.default_clip_vision_config()
 
 
@@ -159,6 +161,58 @@ def check_reward_model(which, B=3, seed=0, reference_metrics=True):
     return max(float((clip_r - want_clip).abs().max()), float((aes_r - want_aes).abs().max()) * 0.1, float((reward - want).abs().max()))
 
 
+def check_preprocess(shapes, B=2, seed=0, against="oracle"):
+    """Device-side CLIPImageProcessor (resize shortest edge -> 224 with Pillow's BICUBIC, centre crop, rescale, normalise) on
+    uint8 HWC device images: fraction of output values that differ from the oracle / from transformers' PIL-backed processor
+    (must be 0: integer arithmetic + one float32 table)."""
+    import numpy as np
+    from oracle import clip_preprocess_oracle as cp
+    cfg, sd, enc = vision("tiny224", 0)
+    rng = np.random.default_rng(seed)
+    bad = 0.0
+    for h, w in shapes:
+        imgs = rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)
+        got = enc.preprocess(torch.from_numpy(imgs).to(DEV)).cpu().numpy()
+        if against == "oracle":
+            want = cp.preprocess(list(imgs))
+        else:
+            from PIL import Image
+            from transformers.models.clip import CLIPImageProcessorPil
+            want = CLIPImageProcessorPil()(images=[Image.fromarray(i) for i in imgs], return_tensors="np")["pixel_values"]
+        assert got.shape == want.shape == (B, 3, 224, 224)
+        bad = max(bad, float((got != want).mean()))
+    return bad
+
+
+def check_reward_device_images(seed=0):
+    """Reward.forward fed the generated images as a uint8 device tensor (decoder output) == fed through a host processor that
+    implements the same pipeline (the oracle's): identical pixel_values -> identical reward bits."""
+    import numpy as np
+    from ltt_test_stubs import HashTokenizer
+    from layoutllm_t2i_b200.reward import COCO_LABELS, Reward
+    from oracle import clip_preprocess_oracle as cp
+    tcfg = dict(co.tiny_clip_text_config())
+    vcfg = dict(cv.tiny_clip_vision_config(), image_size=224)
+    tcfg["projection_dim"] = vcfg["projection_dim"]
+    sd = dict(co.random_state_dict(tcfg, seed=seed))
+    sd.update(cv.random_state_dict(vcfg, seed=seed + 1))
+    aes = cv.aesthetic_state_dict(vcfg["projection_dim"], seed=seed + 2)
+
+    class Proc:
+        def __call__(self, images=None, return_tensors="pt", **kw):
+            return dict(pixel_values=torch.from_numpy(cp.preprocess([np.asarray(i) for i in images])))
+    rm = Reward(sd, aes, HashTokenizer(tcfg["vocab_size"]), Proc(), 0, text_config=tcfg, vision_config=vcfg, labels=COCO_LABELS[:4],
+                metrics=(lambda a, b: np.full(len(a), 0.25, np.float32), lambda a, b: np.full(len(a), 0.5, np.float32)))
+    rng = np.random.default_rng(seed)
+    pred = rng.integers(0, 256, (2, 512, 512, 3), dtype=np.uint8)
+    gt = rng.integers(0, 256, (2, 300, 260, 3), dtype=np.uint8)
+    caps = ["a person on a bicycle", "a car"]
+    lay = [([[0.1, 0.1, 0.5, 0.5]], ["person"]), ([[0.2, 0.2, 0.9, 0.9]], ["car"])]
+    r_dev = rm.forward(caps, torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV), lay, lay)
+    r_host = rm.forward(caps, list(pred), list(gt), lay, lay)
+    return 0.0 if torch.equal(r_dev, r_host) else float((r_dev - r_host).abs().max()) + 1e-9
+
+
 # towers: fp16 operands / fp32 accumulate against an fp32 reference over 24 layers (measured values: profiles/r02_reward_parity.txt)
 TOL = 3e-3
 ALL = [
@@ -169,6 +223,11 @@ ALL = [
     ("vision tower ViT-L/14 hidden B=2", check_vision, dict(which="full", B=2), TOL),
     ("vision tower ViT-L/14 pooled B=5", check_vision, dict(which="full", B=5, what="pooled"), TOL),
     ("vision tower ViT-L/14 image_embeds B=16", check_vision, dict(which="full", B=16, what="embeds"), TOL),
+    ("preprocess 512x512 / 224x224 / 64x80 / 300x260 / 97x211 vs oracle (bit-exact)", check_preprocess,
+     dict(shapes=[(512, 512), (224, 224), (64, 80), (300, 260), (97, 211)]), 1e-12),
+    ("preprocess 512x512 / 1024x768 vs transformers' PIL-backed processor (bit-exact)", check_preprocess,
+     dict(shapes=[(512, 512), (1024, 768)], B=3, seed=1, against="transformers"), 1e-12),
+    ("Reward.forward on device uint8 images == host-processor path", check_reward_device_images, {}, 1e-12),
     ("reward head D=768 B=8", check_reward_head, dict(B=8, D=768), 1e-5),
     ("reward head D=64 B=1, no layout terms", check_reward_head, dict(B=1, D=64, with_layout=False), 1e-5),
     ("reward head zero feature row", check_reward_head, dict(B=3, D=768, zero_row=True), 1e-5),

@@ -109,3 +109,24 @@ def test_reward_head_oracle_matches_reference_pieces():
         want = clip_reward + aes * 0.1 + miou * 10 + laysim * 10
         got, got_clip, got_aes = cv.reward_forward(t, p, g, sd, miou, laysim)
     assert rel(got_clip, clip_reward) < 1e-6 and rel(got_aes, aes) < 1e-5 and rel(got, want) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- image preprocessing
+def test_preprocess_oracle_matches_fixture():
+    """tests/golden/clip_preprocess.npz = outputs of transformers' PIL-backed CLIP image processor: bit-exact."""
+    import numpy as np
+    from oracle import clip_preprocess_oracle as cp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "clip_preprocess.npz"))
+    imgs = [g[f"img{i}"] for i in range(5)]
+    assert np.array_equal(cp.preprocess(imgs, size=int(g["size"])), g["pixel_values"])
+
+
+def test_preprocess_resize_matches_pillow_live():
+    import numpy as np
+    PIL = pytest.importorskip("PIL.Image")
+    from oracle import clip_preprocess_oracle as cp
+    rng = np.random.default_rng(1)
+    for h, w in ((512, 512), (64, 80), (300, 224), (97, 211), (640, 480)):
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        rh, rw, _, _ = cp.output_geometry(h, w)
+        assert np.array_equal(np.asarray(PIL.fromarray(a).resize((rw, rh), resample=PIL.BICUBIC)), cp.pil_resize_bicubic(a, rw, rh)), (h, w)

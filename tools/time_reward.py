@@ -60,6 +60,27 @@ vision.encode(torch.cat([px_pred, px_gt]))
 flops = 2 * B * (257 * 24 * (4 * 1024 ** 2 + 2 * 1024 * 4096) * 2 + 24 * 4 * 257 * 257 * 1024 + 2 * 256 * 588 * 1024)
 print(f"B = {B} samples: sm_100a reward path (text pass + one vision pass over {2 * B} images + head kernel): {ms:.2f} ms "
       f"({vision.launch_count - n0} launches per vision pass; vision tower {flops / 1e12:.2f} TFLOP -> {flops / ms / 1e9:.0f} TFLOP/s incl. the rest)")
+# device-side preprocessing of the decoder's uint8 images vs the host processor the reference uses (PIL resize + numpy)
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+imgs = torch.randint(0, 256, (2 * B, 512, 512, 3), dtype=torch.uint8, device=DEV)
+pre_ms = timed(lambda: vision.preprocess(imgs))
+try:
+    from PIL import Image
+    from transformers.models.clip import CLIPImageProcessorPil
+    proc = CLIPImageProcessorPil()
+    host = imgs.cpu().numpy()
+    t0 = time.perf_counter()
+    pv = proc(images=[Image.fromarray(i) for i in host], return_tensors="pt")["pixel_values"].to(DEV)
+    torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t0) * 1e3
+    same = bool(torch.equal(pv, vision.preprocess(imgs)))
+    print(f"preprocessing of {2 * B} 512x512 images: device kernels {pre_ms:.3f} ms; host CLIPImageProcessor (PIL backend) + H2D {host_ms:.1f} ms "
+          f"(+ the D2H of the generated images the reference pays before it); outputs identical: {same}")
+except Exception as ex:  # noqa: BLE001
+    print(f"preprocessing of {2 * B} 512x512 images: device kernels {pre_ms:.3f} ms (host processor unavailable: {ex!r})")
 r_ours = ours()
 try:
     from transformers import CLIPConfig, CLIPModel
