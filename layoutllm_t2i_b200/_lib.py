@@ -111,7 +111,10 @@ def load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise LttError(f"{LIB_PATH} is missing: the sm_100a extension must be built (there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
+    partial = bool(os.environ.get("LTT_LIB")) and os.environ.get("LTT_LIB_PARTIAL") == "1"      # A/B against an OLDER build only
     for name, (res, args) in _SIGS.items():
+        if partial and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -160,8 +160,7 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float y = v[i] + bv[i];
-            if (e.act == ACT_QUICKGELU) y = y / (1.0f + __expf(-1.702f * y));      // fp32 through the activation (fp32 reference)
-            else if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
+            if (e.out_dtype == DT_F16 || e.res || e.rowvec || e.act) y = r16(y);
             if (e.rowvec) {
                 const float2 f = __half22float2(rvh[i >> 1]);
                 y = r16(y + ((i & 1) ? f.y : f.x));
@@ -229,11 +228,12 @@ __device__ __forceinline__ void epilogue_group8(const GemmEpilogue& e, const Row
 // ---- specialised epilogues: the model's GEMMs fall into a handful of epilogue shapes; each gets a branch-free inner
 // loop (the generic routine above costs ~12 issue slots per element, which made small-K GEMMs epilogue bound).
 // All produce bit-identical results to epilogue_group8 for their flag combination.
-enum : int { EK_GENERIC = 0, EK_F16 = 1, EK_GATE16 = 2, EK_GEGLU = 3, EK_QKV = 4, EK_RES32 = 5 };
+enum : int { EK_GENERIC = 0, EK_F16 = 1, EK_GATE16 = 2, EK_GEGLU = 3, EK_QKV = 4, EK_RES32 = 5, EK_QGELU = 6 };
 
 __host__ __device__ inline int epilogue_kind(const GemmEpilogue& e) {
     if (e.out_mode == OUT_QKV) return (!e.act && !e.has_gate && !e.rowvec) ? EK_QKV : EK_GENERIC;
     if (e.act == ACT_GEGLU) return (!e.res && !e.has_gate && !e.rowvec && e.out_dtype == DT_F16) ? EK_GEGLU : EK_GENERIC;
+    if (e.act == ACT_QUICKGELU) return EK_QGELU;      // the launcher rejects any other operand with it
     if (e.act != ACT_NONE || e.rowvec) return EK_GENERIC;
     if (e.res && e.res_dtype == DT_F32) return e.has_gate ? EK_GENERIC : EK_RES32;
     if (e.out_dtype != DT_F16) return EK_GENERIC;
@@ -269,6 +269,12 @@ __device__ __forceinline__ void epi_group8(const GemmEpilogue& e, const RowInfo&
                 const __half2* rh = reinterpret_cast<const __half2*>(&o.res[j]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) h[i] = __hadd2(h[i], rh[i]);     // one rounding of the exact sum
+            }
+        } else if constexpr (KIND == EK_QGELU) {        // CLIP MLP: x * sigmoid(1.702 x) on the fp32 value (fp32 reference), fp16 out
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float y0 = v[2 * i] + bs[2 * i], y1 = v[2 * i + 1] + bs[2 * i + 1];
+                h[i] = __floats2half2_rn(y0 / (1.0f + __expf(-1.702f * y0)), y1 / (1.0f + __expf(-1.702f * y1)));
             }
         } else if constexpr (KIND == EK_GATE16) {
             const __half2* rh = reinterpret_cast<const __half2*>(&o.res[j]);
@@ -735,6 +741,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_MINB) gemm_tc_kernel(const 
                     case EK_GEGLU: run_tile(KindTag<EK_GEGLU>{}); break;
                     case EK_QKV: run_tile(KindTag<EK_QKV>{}); break;
                     case EK_RES32: run_tile(KindTag<EK_RES32>{}); break;
+                    case EK_QGELU: run_tile(KindTag<EK_QGELU>{}); break;
                     default: run_tile(KindTag<EK_GENERIC>{}); break;
                 }
                 tc_fence_before();
@@ -986,6 +993,10 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
     // its share of L2->SM bandwidth (~75 B/cycle/SM); the epilogue costs ~600 + 6*BN cycles per tile; a cluster
     // reduction moves 128*BN*4 B per CTA through DSMEM (~20 B/cycle) plus the dump; launch + prologue ~3000 cycles.
     const bool geglu = p.epi.act == ACT_GEGLU;
+    if (p.epi.act == ACT_QUICKGELU && (p.epi.res || p.epi.has_gate || p.epi.rowvec || p.epi.out_dtype != DT_F16 || p.epi.out_mode != OUT_ROWMAJOR)) {
+        set_error("gemm: the quick-GELU epilogue takes bias -> activation -> fp16 only");
+        return -1;
+    }
     if (geglu && p.N % 128 != 0) {
         set_error("gemm: GEGLU needs N %% 128 == 0 (N=%d)", p.N);
         return -1;
