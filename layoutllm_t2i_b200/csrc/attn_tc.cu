@@ -484,8 +484,12 @@ int attn_tc_launch(const AttnProblem& p, cudaStream_t stream) {
     }
     // P in tensor memory for the wider heads too: d = 80 13.1 -> 12.3 us (1024 x 1054 keys), d = 160 7.3 -> 6.9 us
     static const int ptm_all = getenv("LTT_ATTN_PTM") ? atoi(getenv("LTT_ATTN_PTM")) : 1;
-    if (dv == 64) return p.causal ? attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true, true>(a, grid, stream)
-                                  : attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
+    // d = 64 (CLIP towers): the vision tower's 257-token sequences give 768+ CTAs of three KV tiles each -> two CTAs per SM
+    // (one S and one P buffer: 256 TMEM columns) instead of one CTA with both double buffered; LTT_ATTN64=1: the latter (A/B)
+    static const int v64 = getenv("LTT_ATTN64") ? atoi(getenv("LTT_ATTN64")) : 0;
+    if (dv == 64 && p.causal) return attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true, true>(a, grid, stream);
+    if (dv == 64) return v64 == 1 ? attn_launch_variant<64, 64, 128, 2, 2, 1, 2, 0, true>(a, grid, stream)
+                                  : attn_launch_variant<64, 64, 128, 1, 1, 2, 2, 0, true>(a, grid, stream);
     if (dv == 80 && ptm_all) return attn_launch_variant<128, 80, 128, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 160 && ptm_all) return attn_launch_variant<192, 160, 64, 2, 2, 1, 2, 0, true>(a, grid, stream);
     if (dv == 80) return vwg == 2 ? attn_launch_variant<128, 80, 128, 2, 2, 1, 2>(a, grid, stream)

@@ -1051,6 +1051,7 @@ int gemm_tc_launch(const GemmProblem& p, int num_sms, cudaStream_t stream, int* 
             if (forced && (p.force_pair || sp != p.force_splits)) continue;
             int resident = num_sms;
             if (sp > 1) {
+                if (p.epi.act == ACT_QUICKGELU) break;      // the cluster-reduction path runs the generic epilogue, which has no quick-GELU
                 if (sp * 2 > iters) break;
                 const int per = (iters + sp - 1) / sp;
                 if ((iters + per - 1) / per != sp) continue;      // every rank must own at least one iteration

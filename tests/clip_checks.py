@@ -68,6 +68,8 @@ def check_linear_quick_gelu(M, N, K, seed=0):
 
 # ------------------------------------------------------------------------------------------------- text tower
 def _cfg(which):
+    if which == "small768":      # few output tiles and a deep K at one short string: the shape where the GEMM launcher prefers split-K
+        return dict(co.default_clip_text_config(), vocab_size=1000, num_hidden_layers=2, intermediate_size=1024)
     return co.tiny_clip_text_config() if which == "tiny" else co.default_clip_text_config()
 
 
@@ -253,6 +255,9 @@ ALL = [
     ("tower tiny hidden B=5 L=77", check_tower, dict(which="tiny", lengths=[5, 0, 12, 75, 1]), TOL),
     ("tower tiny pooled L=9", check_tower, dict(which="tiny", lengths=[3, 7, 1], L_=9, what="pooled"), TOL),
     ("tower tiny outlier channels", check_tower, dict(which="tiny", lengths=[8, 20], seed=5, outliers=True), TOL),
+    ("tower 768 / ffn 1024, one string (few-tile GEMMs)", check_tower, dict(which="small768", lengths=[6]), TOL),
+    ("tower 768 / ffn 1024, one unpadded phrase L=5", check_tower, dict(which="small768", lengths=[3], L_=5, what="pooled"), TOL),
+    ("tower ViT-L/14 hidden B=1 L=77", check_tower, dict(which="full", lengths=[9]), TOL),
     ("tower ViT-L/14 hidden B=2 L=77", check_tower, dict(which="full", lengths=[12, 0]), TOL),
     ("tower ViT-L/14 pooled B=37 L=77", check_tower, dict(which="full", lengths=[14, 0] + [2] * 30 + [5] * 5, what="pooled"), TOL),
     ("tower ViT-L/14 text_embeds B=4 L=20", check_tower, dict(which="full", lengths=[3, 18, 9, 1], L_=20, what="embeds"), TOL),
