@@ -49,6 +49,10 @@ FILES = [
     "GLIGEN/ldm/modules/diffusionmodules/model.py",
     "GLIGEN/ldm/modules/distributions/__init__.py",
     "GLIGEN/ldm/modules/distributions/distributions.py",
+    # next row f3: the text encoder wrapper (the transformer itself is the third-party `transformers` package)
+    "GLIGEN/ldm/modules/encoders/__init__.py",
+    "GLIGEN/ldm/modules/encoders/modules.py",
+    "GLIGEN/ldm/modules/x_transformer.py",
 ]
 
 

@@ -241,6 +241,55 @@ def check_dropin_embedder(seed=0):
     return max(rel(z, z_ref), rel(p, p_ref), rel(one, one_ref))
 
 
+def check_dropin_vs_reference_class(which="tiny", seed=0):
+    """The drop-in FrozenCLIPEmbedder against the reference's OWN class (GLIGEN/ldm/modules/encoders/modules.py:144-182,
+    byte-identical copy under oracle/_ref) running transformers' CLIPTextModel in eager fp32 on the same GPU with the same
+    weights: encode, encode(return_pooler_output=True) and encode_one_token.  The reference class is constructed without
+    `from_pretrained` (no network); tokenizer = the same stand-in on both sides."""
+    from ltt_test_stubs import HashTokenizer
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from oracle import ref_loader as rl
+    assert rl.available(), "oracle/_ref is not staged"
+    with rl.reference_tree():
+        from ldm.modules.encoders.modules import FrozenCLIPEmbedder as RefEmbedder
+    cfg = _cfg(which)
+    sd = co.random_state_dict(cfg, seed=seed, with_projection=False)
+    keys = ("vocab_size", "max_position_embeddings", "hidden_size", "num_attention_heads", "num_hidden_layers", "intermediate_size",
+            "layer_norm_eps", "hidden_act", "projection_dim", "eos_token_id")
+    hf = CLIPTextModel(CLIPTextConfig(**{k: cfg[k] for k in keys}, bos_token_id=cfg["vocab_size"] - 2, pad_token_id=1)).to(DEV).eval()
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    tok = HashTokenizer(cfg["vocab_size"])
+
+    class Tok:      # CLIPTokenizer returns a BatchEncoding (dict access) -- what the reference's forward indexes
+        def __call__(self, text=None, **kw):
+            return tok(text, **kw)
+    ref = object.__new__(RefEmbedder)
+    torch.nn.Module.__init__(ref)
+    ref.tokenizer, ref.transformer, ref.device, ref.max_length = Tok(), hf, DEV, 77
+    # ---- ours, through the reference's config-string instantiation
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "layoutllm_t2i_b200", "dropin")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import _ltt_dropin_hook
+    _ltt_dropin_hook.install()
+    from ldm.util import instantiate_from_config
+    m = instantiate_from_config(dict(target="ldm.modules.encoders.modules.FrozenCLIPEmbedder",
+                                     params=dict(text_config={k: v for k, v in cfg.items() if k != "projection_dim"})))
+    m.load_state_dict(ref.state_dict())            # the reference module's own state_dict, strict
+    m = m.to(DEV).eval()
+    m.device = DEV
+    m.set_tokenizer(Tok())
+    texts = ["a photo of a cat", "", "two dogs playing with a ball on the beach"]
+    with torch.no_grad(), true_fp32():
+        z_ref = ref.encode(texts)
+        z2_ref, p_ref = ref.encode(texts, return_pooler_output=True)
+        one_ref = ref.encode_one_token("wooden bench")
+    z, (z2, p), one = m.encode(texts), m.encode(texts, return_pooler_output=True), m.encode_one_token("wooden bench")
+    assert z.shape == z_ref.shape and p.shape == p_ref.shape and one.shape == one_ref.shape and torch.equal(z_ref, z2_ref)
+    return max(rel(z, z_ref), rel(z2, z_ref), rel(p, p_ref), rel(one, one_ref))
+
+
 # fp16 operands / fp32 accumulate against an fp32 reference: 2e-3 relative L2 (measured values in profiles/r02_clip_parity.txt)
 TOL = 2e-3
 ALL = [
@@ -270,6 +319,8 @@ ALL = [
      dict(which="full", n_boxes=30, n_rel=1, with_none=True), TOL),
     ("prepare_conditioning 0 boxes 0 relations", check_prepare_conditioning, dict(which="tiny", n_boxes=0, n_rel=0, batch=1), TOL),
     ("drop-in FrozenCLIPEmbedder", check_dropin_embedder, {}, TOL),
+    ("drop-in FrozenCLIPEmbedder vs the reference's own class (eager fp32 transformers), tiny", check_dropin_vs_reference_class, {}, TOL),
+    ("drop-in FrozenCLIPEmbedder vs the reference's own class, ViT-L/14", check_dropin_vs_reference_class, dict(which="full", seed=4), TOL),
 ]
 
 

@@ -213,6 +213,92 @@ def check_reward_device_images(seed=0):
     return 0.0 if torch.equal(r_dev, r_host) else float((r_dev - r_host).abs().max()) + 1e-9
 
 
+def check_reward_vs_reference_class(which="tiny224", B=3, seed=0):
+    """The mirror against the reference's OWN `Reward.forward` (models/policy.py:105-139, byte-identical copy under
+    oracle/_ref) running eager fp32 on the same GPU: transformers CLIPModel with the same seeded weights, the reference's
+    AestheticMLP, transformers' PIL-backed image processor, the reference's tools/metrics.  The class is constructed without
+    `from_pretrained` (no network); the only adaptation is version skew -- transformers 5 returns an output object from
+    get_*_features where the 4.x API the reference was written for returned the tensor."""
+    import numpy as np
+    from PIL import Image
+    from transformers import CLIPConfig, CLIPModel
+    from transformers.models.clip import CLIPImageProcessorPil
+    from ltt_test_stubs import HashTokenizer
+    from layoutllm_t2i_b200.reward import Reward
+    from oracle import ref_loader as rl
+    assert rl.available(), "oracle/_ref is not staged"
+    with rl.reference_tree():
+        sys.path.insert(0, rl.REF_ROOT)
+        try:
+            from models.policy import Reward as RefReward
+            from tools.aesthetic import AestheticMLP
+        finally:
+            sys.path.remove(rl.REF_ROOT)
+    tcfg = dict(co.tiny_clip_text_config() if which != "full" else co.default_clip_text_config())
+    vcfg = _vcfg(which)
+    tcfg["projection_dim"] = vcfg["projection_dim"]
+    sd = dict(co.random_state_dict(tcfg, seed=seed))
+    sd.update(cv.random_state_dict(vcfg, seed=seed + 1))
+    aes = cv.aesthetic_state_dict(vcfg["projection_dim"], seed=seed + 2)
+    tk = ("vocab_size", "max_position_embeddings", "hidden_size", "num_attention_heads", "num_hidden_layers", "intermediate_size",
+          "layer_norm_eps", "hidden_act", "eos_token_id")
+    vk = ("image_size", "patch_size", "hidden_size", "num_attention_heads", "num_hidden_layers", "intermediate_size", "layer_norm_eps",
+          "hidden_act")
+    hf = CLIPModel(CLIPConfig(text_config=dict({k: tcfg[k] for k in tk}, bos_token_id=tcfg["vocab_size"] - 2, pad_token_id=1),
+                              vision_config={k: vcfg[k] for k in vk}, projection_dim=vcfg["projection_dim"])).to(DEV).eval()
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k or k == "logit_scale" for k in missing), (missing, unexpected)
+
+    class Hf4:          # transformers 4.x surface of CLIPModel over the installed 5.x
+        projection_dim = vcfg["projection_dim"]
+
+        @staticmethod
+        def _t(o):
+            return o if torch.is_tensor(o) else o.pooler_output
+
+        def get_text_features(self, **kw):
+            return self._t(hf.get_text_features(**kw))
+
+        def get_image_features(self, **kw):
+            return self._t(hf.get_image_features(**kw))
+
+    tok = HashTokenizer(tcfg["vocab_size"])
+
+    class Enc(dict):
+        def to(self, device):
+            return Enc({k: v.to(device) for k, v in self.items()})
+
+    class Tok:
+        def __call__(self, texts, padding=True, return_tensors="pt"):
+            return Enc(tok(texts, padding=padding))
+    proc = CLIPImageProcessorPil(size={"shortest_edge": vcfg["image_size"]}, crop_size={"height": vcfg["image_size"], "width": vcfg["image_size"]})
+    ref = object.__new__(RefReward)
+    torch.nn.Module.__init__(ref)
+    ref.tokenizer, ref.processor, ref.model, ref.device = Tok(), proc, Hf4(), DEV
+    ref.args = type("A", (), dict(img_dir="x/train2014"))()
+    ref.aesthetic_model = AestheticMLP(vcfg["projection_dim"]).to(DEV).eval()
+    ref.aesthetic_model.load_state_dict(aes)
+    g = torch.Generator().manual_seed(seed + 5)
+    captions = ["a person riding a bicycle", "two cars and a bus on the street", "a boat"][:B]
+    pred = [(torch.rand(96, 96, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(B)]
+    gt = [(torch.rand(120, 100, 3, generator=g) * 255).to(torch.uint8).numpy() for _ in range(B)]
+    box = lambda: sorted(torch.rand(2, generator=g).tolist()) + sorted(torch.rand(2, generator=g).tolist())  # noqa: E731
+    lay_gt = [([box(), box()], ["person", "bicycle"]), ([box(), box(), box()], ["car", "car", "bus"]), ([box()], ["boat"])][:B]
+    lay_pred = [([box(), box()], ["person", "bike rider"]), ([box(), box()], ["car", "bus"]), ([box()], ["boat"])][:B]
+    with torch.no_grad(), true_fp32():
+        ref.emb_labels()
+        want = ref.forward(captions, [Image.fromarray(i) for i in pred], [Image.fromarray(i) for i in gt], lay_pred, lay_gt)
+    rm = Reward(sd, aes, Tok(), proc, 0, text_config=tcfg, vision_config=vcfg, metrics=None)
+    sys.path.insert(0, rl.REF_ROOT)          # Reward's default layout terms: `from tools.metrics import ...` of the caller's checkout
+    try:
+        with rl.reference_tree():
+            got = rm.forward(captions, torch.from_numpy(np.stack(pred)).to(DEV), [Image.fromarray(i) for i in gt], lay_pred, lay_gt)
+    finally:
+        sys.path.remove(rl.REF_ROOT)
+    assert rm.labels == ref.labels
+    return float((got - want.to(got.dtype)).abs().max())
+
+
 # towers: fp16 operands / fp32 accumulate against an fp32 reference over 24 layers (measured values: profiles/r02_reward_parity.txt)
 TOL = 3e-3
 ALL = [
@@ -228,6 +314,8 @@ ALL = [
     ("preprocess 512x512 / 1024x768 vs transformers' PIL-backed processor (bit-exact)", check_preprocess,
      dict(shapes=[(512, 512), (1024, 768)], B=3, seed=1, against="transformers"), 1e-12),
     ("Reward.forward on device uint8 images == host-processor path", check_reward_device_images, {}, 1e-12),
+    ("Reward.forward vs the reference's own Reward class (eager fp32 transformers), tiny towers", check_reward_vs_reference_class, {}, 5e-3),
+    ("Reward.forward vs the reference's own Reward class, ViT-L/14 towers", check_reward_vs_reference_class, dict(which="full", seed=3), 5e-3),
     ("reward head D=768 B=8", check_reward_head, dict(B=8, D=768), 1e-5),
     ("reward head D=64 B=1, no layout terms", check_reward_head, dict(B=1, D=64, with_layout=False), 1e-5),
     ("reward head zero feature row", check_reward_head, dict(B=3, D=768, zero_row=True), 1e-5),
