@@ -449,7 +449,7 @@ def main():
         step_ms = ms_dev / args.steps
         k_scale = step_ms / ms_instrumented
         cls = {k: dict(v, ms_raw=v["ms"], ms=v["ms"] * k_scale) for k, v in prof.items()}
-        named = ("gemm_tc", "attn_tc", "groupnorm", "layernorm")
+        named = ("gemm_tc", "attn_tc", "groupnorm", "layernorm", "relation")
         other_ms = max(step_ms - sum(cls[k]["ms"] for k in named), 0.0)
         dom = max(named, key=lambda k: cls[k]["ms"])
         d = cls[dom]

@@ -95,7 +95,8 @@ int64_t ltt_launch_count(const ltt_model* m);
  * of the evaluation (the mode the timed path runs in); a bracket then holds the times of its graph's last replay and
  * ltt_profile_report weights it by the graph's replay count (calling ltt_profile_enable(m, 2) again restarts the
  * counts).  on = 0: off.  ltt_profile_report synchronises and returns, for class cls (0 = tcgen05 GEMM / implicit conv,
- * 1 = tcgen05 attention, 2 = GroupNorm, 3 = LayerNorm, 4 = whole UNet forward), the summed event time [ms], the
+ * 1 = tcgen05 attention, 2 = GroupNorm, 3 = LayerNorm, 4 = whole UNet forward, 5 = relation fusion: box pooling, folded
+ * relation attention, scatter + norm2), the summed event time [ms], the
  * algorithmic FLOPs (2*M*N*K; 4*nq*nk*d per head) and bytes, and the launch count since it was enabled. */
 int ltt_profile_enable(ltt_model* m, int on);
 int ltt_profile_report(ltt_model* m, int cls, double* ms, double* flops, double* bytes, int64_t* launches);

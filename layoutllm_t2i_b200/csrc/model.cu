@@ -537,7 +537,7 @@ static int build_plan(ltt_model* m) {
 }
 
 // ------------------------------------------------------------------------------------------------------ profiling
-enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_GN = 2, PC_LN = 3, PC_FORWARD = 4, PC_COUNT = 5 };
+enum : int { PC_GEMM = 0, PC_ATTN = 1, PC_GN = 2, PC_LN = 3, PC_FORWARD = 4, PC_RELA = 5, PC_COUNT = 6 };
 struct ProfScope {
     ltt_model* m;
     cudaStream_t st;
@@ -906,12 +906,15 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     const int ng = m->n_grounded;
     const __half* feats_final = nullptr;
     if (ng > 0) {
-        RC(rela_pool_launch(nullptr, x16, r3, s.r_ln3.g, s.r_ln3.b, m->rects[level], ng, mo, H, W, C, m->feats, st));
+        {
+            ProfScope ps(m, st, PC_RELA, 0.0, (double)ng * mo * C * 2.0);
+            RC(rela_pool_launch(nullptr, x16, r3, s.r_ln3.g, s.r_ln3.b, m->rects[level], ng, mo, H, W, C, m->feats, st));
+        }
         m->launches++;
         const int R = ng * mo;
         if (m->rela_fused) {
             // norm1 -> (to_q, attention over the relation tokens, to_out: folded) -> gated residual -> norm2, one kernel
-            ProfScope ps(m, st, PC_LN, 0.0, (double)R * C * 6.0);
+            ProfScope ps(m, st, PC_RELA, 0.0, (double)R * C * 6.0);
             RC(rela_attn_fused_launch(m->feats, ng, mo, C, s.heads, m->n_rel, s.r_A, s.r_Bm, s.r_out.bias, s.r_ta, s.r_ln1.g,
                                       s.r_ln1.b, s.r_ln2.g, s.r_ln2.b, 1e-5f, m->rela_scratch, m->rela_tickets, m->feats2, m->featln, st));
             m->launches++;
@@ -941,8 +944,11 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         feats_final = m->feats3;
     }
     // scatter + the block's norm2 in one kernel
-    RC(rela_scatter_launch(nullptr, r3, s.r_ln3.g, s.r_ln3.b, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
-                           m->ln16, st));
+    {   // (the block's norm2 rides in this kernel)
+        ProfScope ps(m, st, PC_RELA, 0.0, (double)M * C * 8.0);
+        RC(rela_scatter_launch(nullptr, r3, s.r_ln3.g, s.r_ln3.b, x16, feats_final, m->rects[level], ng, B, mo, H, W, C, m->xe32, s.ln2.g, s.ln2.b, 1e-5f,
+                               m->ln16, st));
+    }
     m->launches++;
     RC(tap(m, st, s.p + ":rela", m->xe32, DT_F32, M, C));
     // attn2 over the cached text K/V

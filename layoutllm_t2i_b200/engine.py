@@ -140,7 +140,7 @@ class Engine:
                                               L.stream_ptr()), "ltt_plms_sample")
         return xx
 
-    PROFILE_CLASSES = ("gemm_tc", "attn_tc", "groupnorm", "layernorm", "forward")
+    PROFILE_CLASSES = ("gemm_tc", "attn_tc", "groupnorm", "layernorm", "forward", "relation")
 
     def profile(self, mode) -> None:
         """0 / False: off.  1 / True: eager launches, every class launch bracketed by CUDA events.  2: the brackets are
