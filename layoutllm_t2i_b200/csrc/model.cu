@@ -155,6 +155,8 @@ struct ltt_model {
     bool use_graphs = true;
     bool rela_fused = true;           // LTT_RELA_UNFUSED=1: q-GEMM / attention / out-GEMM as separate launches (A/B checks)
     bool ln_fold = false;             // LTT_LNFOLD=1: LayerNorms of the token stream folded into the consumer GEMMs (see ltt_create)
+    bool fold_r3 = false;             // only the producer half for the relation block's norm3: its row statistics come from the
+                                      // epilogue of the GEMM that wrote the stream instead of a pass over it
     // GEMM tiling autotuner: the first (eager) evaluation of a geometry times every legal (tile width, split-K cluster,
     // CTA-pair) choice of each distinct GEMM shape on the device and keeps the fastest; LTT_NO_AUTOTUNE=1: cycle model only
     bool autotune = true, tuning = false;
@@ -805,8 +807,8 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     // buffer (`produce`); the projection that consumes the norm reads the raw rows and normalises in its epilogue (`consume`)
     const bool fold = m->ln_fold;
     int slots[2] = {0, 0};
-    auto produce = [&](GemmEpilogue& e, int which) {
-        if (fold) {
+    auto produce = [&](GemmEpilogue& e, int which, bool writes_x16 = false) {      // writes_x16: the stream norm3 of the relation block reads
+        if (fold || (m->fold_r3 && writes_x16)) {
             e.stats_out = m->rstats[which];
             e.stats_ld = GEMM_STATS_LD;
         }
@@ -843,7 +845,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     {
         GemmEpilogue e = epi_out(m->xb, C);
         e.res = m->xa; e.ldr = C;
-        produce(e, 1);
+        produce(e, 1, alpha_scale == 0.0f);
         RC(r.gemm(H, W, C, {GemmSrc{m->ao, C, C, 1}}, s.a1_out, e, -1, &slots[1]));
     }
     __half* x16 = m->xb;   // fp16 stream after attn1 (+ fuser); its row statistics are in rstats[1]
@@ -885,7 +887,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
         {
             GemmEpilogue e = epi_out(m->xb, C);
             e.res = m->xa; e.ldr = C; e.has_gate = 1; e.gate = alpha_scale * s.f_td;
-            produce(e, 1);
+            produce(e, 1, true);
             RC(r.gemm(H, W, C, {GemmSrc{m->ffbuf, 4 * C, 4 * C, 1}}, s.f_ff2, e, -1, &slots[1]));
         }
         x16 = m->xb;
@@ -895,7 +897,7 @@ static int run_st(Run& r, StW& s, const __half* x_in, int H, int W, int level, f
     // norm3 is never materialised: the pool and scatter kernels normalise on the fly from per-row statistics -- the
     // partial sums the producing GEMM's epilogue left (LayerNorm fold) or one statistics pass over x16
     RowStatSrc r3;
-    if (fold) {
+    if (fold || m->fold_r3) {
         r3.p = m->rstats[1]; r3.ld = GEMM_STATS_LD; r3.slots = slots[1]; r3.K = C; r3.eps = 1e-5f;
     } else {
         m->launches++;
@@ -1312,7 +1314,11 @@ int ltt_create(const ltt_unet_config* cfg, int device, ltt_model** out) {
     // two more FP32 operations per accumulator on GEMMs that are epilogue bound already, and the separate LayerNorm
     // kernels were nearly free at B=1 because the next GEMM's prologue and weight prefetch overlap them (PDL).  Off by
     // default; LTT_LNFOLD=1 switches it on (kept for larger hidden sizes, where the balance shifts).
-    m->ln_fold = getenv("LTT_LNFOLD") != nullptr;
+    {
+        const char* lf = getenv("LTT_LNFOLD");
+        m->fold_r3 = lf && !strcmp(lf, "r3");
+        m->ln_fold = lf && !m->fold_r3;
+    }
     m->autotune = getenv("LTT_NO_AUTOTUNE") == nullptr;
     *out = m;
     return 0;

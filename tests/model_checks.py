@@ -228,11 +228,12 @@ def check_dropin_sampler(cfg, seed, B, H, W, S, mode):
     return rel(out, ref)
 
 
-def check_unet_lnfold(cfg, seed, B, H, W, n_boxes, t, scale):
-    """The same forward with the LayerNorms folded into the consumer GEMMs (LTT_LNFOLD=1, read at ltt_create)."""
-    os.environ["LTT_LNFOLD"] = "1"
+def check_unet_lnfold(cfg, seed, B, H, W, n_boxes, t, scale, mode="1"):
+    """The same forward with the LayerNorms folded into the consumer GEMMs (LTT_LNFOLD=1, read at ltt_create); mode "r3": only
+    the relation block's norm3 statistics come from the producing GEMM's epilogue."""
+    os.environ["LTT_LNFOLD"] = mode
     try:
-        e, sd = engine_for(cfg, seed, "lnfold")
+        e, sd = engine_for(cfg, seed, "lnfold" + mode)
     finally:
         del os.environ["LTT_LNFOLD"]
     sd_dev = {k: v.to(DEV) for k, v in sd.items()}
@@ -259,6 +260,10 @@ ALL = [
      dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0), 3e-3),
     ("tiny UNet with the LayerNorm fold on, alpha=0", check_unet_lnfold,
      dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=401, scale=0.0), 3e-3),
+    ("tiny UNet with the norm3 statistics from the producer epilogue (LTT_LNFOLD=r3), alpha=1", check_unet_lnfold,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=981, scale=1.0, mode="r3"), 3e-3),
+    ("tiny UNet with the norm3 statistics from the producer epilogue, alpha=0", check_unet_lnfold,
+     dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=3, t=401, scale=0.0, mode="r3"), 3e-3),
     ("tiny UNet cond-only / null-only batches", check_cond_only_batch, dict(cfg=TINY, seed=7, B=2, H=16, W=16, n_boxes=30, t=21), 3e-3),
     ("tiny PLMS 5 steps, CFG 7.5", check_plms_vs_oracle, dict(cfg=TINY, seed=7, B=2, H=16, W=16, S=5), 5e-3),
     ("drop-in UNetModel.forward(dict), cond + uncond, both gate values", check_dropin_forward,
