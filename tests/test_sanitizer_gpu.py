@@ -1,5 +1,6 @@
 """compute-sanitizer memcheck over a small end-to-end workload of the sm_100a library (tools/sanitize_smoke.py): tiny UNet
-forward at both gate values, a fused 5-step PLMS loop with CUDA-graph replay, a small VAE decode.  (pytest -m gpu)"""
+forward at both gate values, a fused 5-step PLMS loop with CUDA-graph replay, a small VAE decode, tiny CLIP towers, the image
+preprocessing and the cluster reward head.  (pytest -m gpu)"""
 import os
 import shutil
 import subprocess

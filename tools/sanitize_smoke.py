@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end workload for `compute-sanitizer` (tests/test_sanitizer_gpu.py): a tiny UNet [cond ; uncond] forward at
-both gate values, a 5-step fused PLMS loop (CUDA-graph replay included) and a small VAE decode, all through the C-ABI.
+both gate values, a 5-step fused PLMS loop (CUDA-graph replay included), a small VAE decode, tiny CLIP text / vision passes,
+the image preprocessing and the reward head, all through the C-ABI.
 Prints one line per stage; any kernel fault surfaces as a sanitizer error."""
 import os
 import sys
@@ -54,4 +55,28 @@ dec.load_state_dict(vsd)
 img, u8 = dec.decode(torch.randn(2, 4, 16, 16, generator=g).cuda(), images_u8=True)
 torch.cuda.synchronize()
 print(f"vae decode: {tuple(img.shape)} finite={bool(torch.isfinite(img).all())} u8={tuple(u8.shape)}", flush=True)
+# ---- conditioning prep / reward path: tiny CLIP towers (causal and plain d = 64 attention, quick-GELU epilogue, pooling /
+# projection kernels), the image preprocessing kernels on an odd-sized image, the cluster reward head
+from layoutllm_t2i_b200.clip import ClipTextEncoder, ClipVisionEncoder  # noqa: E402
+from layoutllm_t2i_b200.reward import reward_head  # noqa: E402
+from oracle import clip_text_oracle as co  # noqa: E402
+from oracle import clip_vision_oracle as cv  # noqa: E402
+
+tcfg, vcfg = co.tiny_clip_text_config(), cv.tiny_clip_vision_config()
+text, vision = ClipTextEncoder(tcfg, 0), ClipVisionEncoder(vcfg, 0)
+text.load_state_dict(co.random_state_dict(tcfg, seed=1))
+vision.load_state_dict(cv.random_state_dict(vcfg, seed=2))
+for lengths, L_ in (([5, 0, 12, 75, 1], None), ([3], 5)):
+    hid, pooled, emb = text.encode_ids(co.synthetic_ids(tcfg, lengths, L=L_, seed=3), want_embeds=True)
+torch.cuda.synchronize()
+print(f"clip text: finite={bool(torch.isfinite(hid).all() and torch.isfinite(emb).all())}", flush=True)
+imgs = torch.randint(0, 256, (3, 97, 131, 3), dtype=torch.uint8, generator=g).cuda()
+px = vision.preprocess(imgs)
+_, vp, ve = vision.encode(px)
+torch.cuda.synchronize()
+print(f"clip vision + preprocess: {tuple(px.shape)} finite={bool(torch.isfinite(px).all() and torch.isfinite(ve).all())}", flush=True)
+aes = {k: v.cuda() for k, v in cv.aesthetic_state_dict(vcfg["projection_dim"], seed=4).items()}
+r, c, a = reward_head(emb[:3], ve, ve.flip(0), aes, torch.rand(3, generator=g).cuda(), None)
+torch.cuda.synchronize()
+print(f"reward head: finite={bool(torch.isfinite(r).all())}", flush=True)
 print("SANITIZE_SMOKE_DONE", flush=True)
