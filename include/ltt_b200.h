@@ -164,6 +164,8 @@ void ltt_clip_destroy(ltt_clip* c);
  * "text_model.encoder.layers.3.self_attn.q_proj.bias", ..., "text_model.final_layer_norm.weight") and, for proj_dim > 0,
  * CLIPModel's "text_projection.weight"; fp32 device or host pointers. */
 int ltt_clip_load_param(ltt_clip* c, const char* key, const float* data, const int64_t* shape, int ndim, int is_host);
+/* packs the projection matrices to fp16 and releases their fp32 copies (a finalize after further ltt_clip_load_param calls
+ * needs the whole state_dict loaded again, as load_state_dict does) */
 int ltt_clip_finalize(ltt_clip* c);
 /* ids [B, L] int32 on the device, L <= max_pos, rows laid out by CLIPTokenizer (<bos> ... <eos> padding); attention is
  * causal with NO padding mask (what FrozenCLIPEmbedder does; rows up to <eos> -- hence the pooled vector -- are the

@@ -406,7 +406,9 @@ static int load_param(CParams& params, int device, const char* key, const float*
 }
 
 // encoder.layers.* of one tower (`prefix` = "text_model." / "vision_model.") -> packed fp16 weights
-static int tower_build(Tower& t, const CParams& params, const std::string& prefix, int n_layers) {
+// `packed` collects the keys of the fp32 matrices that live on as packed fp16 copies (released by the caller after the packing
+// kernels have run: biases, norms, embeddings and projections stay fp32)
+static int tower_build(Tower& t, const CParams& params, const std::string& prefix, int n_layers, std::vector<std::string>& packed) {
     const int64_t W = t.W, F = t.ffn;
     crelease(t.wptrs);
     t.layers.clear();
@@ -423,6 +425,7 @@ static int tower_build(Tower& t, const CParams& params, const std::string& prefi
         for (int j = 0; j < 3; ++j) {       // q / k / v stacked into one [3W, W] matrix (the softmax scale stays in the attention kernel)
             CGET(w, p + "self_attn." + names[j] + ".weight", W, W)
             CGET(b, p + "self_attn." + names[j] + ".bias", W)
+            packed.push_back(p + "self_attn." + names[j] + ".weight");
             RCC(pack_rows_launch(w->dev, (int)W, (int)W, (__half*)wq, j * (int)W, 0, 0));
             LTT_CUDA_OK(cudaMemcpy((float*)bq + j * W, b->dev, W * 4, cudaMemcpyDeviceToDevice));
         }
@@ -430,6 +433,7 @@ static int tower_build(Tower& t, const CParams& params, const std::string& prefi
         auto lin = [&](const std::string& name, int64_t N, int64_t K, __half** wout, const float** bout) -> int {
             CGET(w, p + name + ".weight", N, K)
             CGET(b, p + name + ".bias", N)
+            packed.push_back(p + name + ".weight");
             void* q;
             RCC(calloc_dev(t.wptrs, &q, (size_t)N * K * 2));
             RCC(pack_rows_launch(w->dev, (int)N, (int)K, (__half*)q, 0, 0, 0));
@@ -442,6 +446,16 @@ static int tower_build(Tower& t, const CParams& params, const std::string& prefi
         t.layers.push_back(l);
     }
     return 0;
+}
+
+static void release_packed(CParams& params, const std::vector<std::string>& packed) {
+    for (const std::string& k : packed) {
+        auto it = params.find(k);
+        if (it != params.end()) {
+            cudaFree(it->second.dev);
+            params.erase(it);
+        }
+    }
 }
 
 static int tower_workspace(Tower& t, int B, int L) {
@@ -637,6 +651,7 @@ int ltt_clip_load_param(ltt_clip* c, const char* key, const float* data, const i
 
 int ltt_clip_finalize(ltt_clip* c) {
     if (!c) return -1;
+    if (c->finalized) return 0;             // nothing was loaded since the last call
     LTT_CUDA_OK(cudaSetDevice(c->device));
     const ltt_clip_config& g = c->cfg;
     const CParams& params = c->params;
@@ -652,8 +667,10 @@ int ltt_clip_finalize(ltt_clip* c) {
         CGET(pw, "text_projection.weight", g.proj_dim, W)
         c->proj = pw->dev;
     }
-    RCC(tower_build(c->t, params, tm, g.layers));
+    std::vector<std::string> packed;
+    RCC(tower_build(c->t, params, tm, g.layers, packed));
     LTT_CUDA_OK(cudaDeviceSynchronize());
+    release_packed(c->params, packed);      // 2/3 of the tower's device memory; a later finalize needs the state_dict loaded again
     c->finalized = true;
     return 0;
 }
@@ -753,6 +770,7 @@ int ltt_clip_vision_load_param(ltt_clip_vision* c, const char* key, const float*
 
 int ltt_clip_vision_finalize(ltt_clip_vision* c) {
     if (!c) return -1;
+    if (c->finalized) return 0;
     LTT_CUDA_OK(cudaSetDevice(c->device));
     const ltt_clip_vision_config& g = c->cfg;
     const CParams& params = c->params;
@@ -773,8 +791,10 @@ int ltt_clip_vision_finalize(ltt_clip_vision* c) {
     RCC(calloc_dev(c->wptrs, (void**)&c->patch_w, (size_t)W * c->Kpad * 2));
     clipv_pack_patch_kernel<<<256, 256>>>(pw->dev, (int)W, (int)(3 * P * P), c->Kpad, c->patch_w);
     LTT_CUDA_OK(cudaGetLastError());
-    RCC(tower_build(c->t, params, vm, g.layers));
+    std::vector<std::string> packed;
+    RCC(tower_build(c->t, params, vm, g.layers, packed));
     LTT_CUDA_OK(cudaDeviceSynchronize());
+    release_packed(c->params, packed);
     c->finalized = true;
     return 0;
 }
