@@ -188,6 +188,7 @@ struct ltt_vae {
     std::map<std::string, VParam> params;
     bool finalized = false;
     std::vector<void*> wptrs, cptrs;
+    std::vector<std::string> packed;    // fp32 weights that live on as packed fp16 copies: released after ltt_vae_finalize
     // plan
     std::vector<VRes> res;              // mid.block_1, mid.block_2, then the up blocks in execution order
     std::vector<std::vector<int>> level_res;   // per executed level (high -> low index): indices into res
@@ -246,11 +247,13 @@ static int vconv3(ltt_vae* v, const std::string& p, int cin, int cout, const std
     void* q;
     RCV(valloc(v->wptrs, &q, (size_t)cout * K * 2));
     RCV(pack_conv_launch(w->dev, cout, cin, 9, 0, cin, (__half*)q, K, 0, 0));
+    v->packed.push_back(p + ".weight");
     const float* bias = b->dev;
     if (cskip) {
         VGET(sw, skip + ".weight")
         VGET(sb, skip + ".bias")
         RCV(pack_conv_launch(sw->dev, cout, cskip, 1, 0, cskip, (__half*)q, K, 9 * cin, 0));
+        v->packed.push_back(skip + ".weight");
         std::vector<float> hb(cout), hs(cout);
         LTT_CUDA_OK(cudaMemcpy(hb.data(), b->dev, cout * 4, cudaMemcpyDeviceToHost));
         LTT_CUDA_OK(cudaMemcpy(hs.data(), sb->dev, cout * 4, cudaMemcpyDeviceToHost));
@@ -278,6 +281,7 @@ static int vres(ltt_vae* v, const std::string& p, int cin, int cout) {
 static int vae_build(ltt_vae* v) {
     const ltt_vae_config& c = v->cfg;
     vrelease(v->wptrs);
+    v->packed.clear();
     v->res.clear(); v->level_res.clear(); v->ups.clear();
     int block_in = c.ch * c.ch_mult[c.n_levels - 1];
     v->Cmid = block_in;
@@ -301,6 +305,7 @@ static int vae_build(ltt_vae* v) {
             VGET(w, std::string("decoder.mid.attn_1.") + names[i] + ".weight")
             VGET(b, std::string("decoder.mid.attn_1.") + names[i] + ".bias")
             RCV(pack_rows_launch(w->dev, C, C, (__half*)q, i * C, 0, 0));
+            v->packed.push_back(std::string("decoder.mid.attn_1.") + names[i] + ".weight");
             LTT_CUDA_OK(cudaMemcpy((float*)bb + i * C, b->dev, C * 4, cudaMemcpyDeviceToDevice));
         }
         v->attn_qkv = VLin{(__half*)q, (const float*)bb, 3 * C, C};
@@ -309,6 +314,7 @@ static int vae_build(ltt_vae* v) {
         void* o;
         RCV(valloc(v->wptrs, &o, (size_t)C * C * 2));
         RCV(pack_rows_launch(w->dev, C, C, (__half*)o, 0, 0, 0));
+        v->packed.push_back("decoder.mid.attn_1.proj_out.weight");
         v->attn_out = VLin{(__half*)o, b->dev, C, C};
     }
     char buf[128];
@@ -337,9 +343,18 @@ static int vae_build(ltt_vae* v) {
         void* q;
         RCV(valloc(v->wptrs, &q, (size_t)c.out_ch * 9 * block_in * 2));
         RCV(pack_conv_launch(w->dev, c.out_ch, block_in, 9, 0, block_in, (__half*)q, 9 * block_in, 0, 0));
+        v->packed.push_back("decoder.conv_out.weight");
         v->out_w = (__half*)q; v->out_b = b->dev;
     }
     LTT_CUDA_OK(cudaDeviceSynchronize());
+    for (const std::string& k : v->packed) {       // (a later finalize needs the state_dict loaded again, as load_state_dict does)
+        auto it = v->params.find(k);
+        if (it != v->params.end()) {
+            cudaFree(it->second.dev);
+            v->params.erase(it);
+        }
+    }
+    v->packed.clear();
     return 0;
 }
 
@@ -518,6 +533,7 @@ int ltt_vae_load_param(ltt_vae* v, const char* key, const float* data, const int
 
 int ltt_vae_finalize(ltt_vae* v) {
     if (!v) return -1;
+    if (v->finalized) return 0;             // nothing was loaded since the last call
     LTT_CUDA_OK(cudaSetDevice(v->device));
     RCV(vae_build(v));
     v->finalized = true;
