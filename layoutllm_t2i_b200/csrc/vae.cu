@@ -486,7 +486,7 @@ int ltt_vae_create(const ltt_vae_config* cfg, int device, ltt_vae** out) {
     }
     bool ok = cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->out_ch >= 1 && cfg->out_ch <= 4 && cfg->z_channels <= 8 &&
               cfg->embed_dim <= 8 && cfg->num_res_blocks >= 0 && cfg->scale_factor != 0.0f;
-    for (int i = 0; ok && i < cfg->n_levels; ++i) ok = (cfg->ch * cfg->ch_mult[i]) % 64 == 0;
+    for (int i = 0; ok && i < cfg->n_levels; ++i) ok = cfg->ch * cfg->ch_mult[i] > 0 && (cfg->ch * cfg->ch_mult[i]) % 64 == 0;
     if (!ok) {
         set_error("ltt_vae_create: unsupported decoder configuration (channels must be multiples of 64, out_ch <= 4)");
         return -1;
