@@ -288,38 +288,40 @@ def prepare_conditioning(encoder: ClipTextEncoder, tokenize: Callable[[Sequence[
     path passes no reference images).  Requires the phrase tower and the prompt tower to hold the same weights, which is the
     reference's set-up (both are ``openai/clip-vit-large-patch14``)."""
     phrases = list(phrases)
-    if len(phrases) > max_objs or len(locations) < len(phrases):
-        raise ValueError(f"prepare_conditioning: {len(phrases)} phrases / {len(locations)} boxes (max_objs = {max_objs})")
+    if len(phrases) > max_objs:
+        raise ValueError(f"prepare_conditioning: {len(phrases)} phrases exceed max_objs = {max_objs}")
+    n_boxes = min(len(phrases), len(locations))            # prepare_batch zips locations with the phrase features
     relations = list(relations)[:max_relas]
-    live = [i for i, p in enumerate(phrases) if p is not None]
+    live = [i for i, p in enumerate(phrases[:n_boxes]) if p is not None]
     strings = [prompt, negative_prompt] + [phrases[i] for i in live] + relations
-    ids = tokenize(strings)
-    hid, pooled = encoder.encode_ids(ids)
+    hid, pooled = encoder.encode_ids(tokenize(strings))
     W = hid.shape[-1]
     dev = hid.device
     n_ph = len(live)
-    boxes = torch.zeros(max_objs, 4, device=dev)
-    masks = torch.zeros(max_objs, device=dev)
-    text_masks = torch.zeros(max_objs, device=dev)
-    text_emb = torch.zeros(max_objs, W, device=dev)
-    for idx, box in enumerate(locations[:len(phrases)]):
-        boxes[idx] = torch.as_tensor(box, dtype=torch.float32)
-        masks[idx] = 1
+    # the small bookkeeping tensors are assembled on the host and moved once
+    boxes_h = torch.zeros(max_objs, 4)
+    masks_h = torch.zeros(max_objs)
+    text_masks_h = torch.zeros(max_objs)
+    if n_boxes:
+        boxes_h[:n_boxes] = torch.as_tensor([list(map(float, b)) for b in locations[:n_boxes]], dtype=torch.float32)
+        masks_h[:n_boxes] = 1
     if n_ph:
-        sel = torch.as_tensor(live, device=dev)
-        text_emb[sel] = pooled[2:2 + n_ph]
-        text_masks[sel] = 1
-    rel = torch.zeros(max_relas, W, device=dev)
-    if relations:
-        rel[:len(relations)] = pooled[2 + n_ph:]
-    tm = torch.ones(max_objs, device=dev)
+        text_masks_h[live] = 1
+    tm = torch.ones(max_objs)
     if text_mask is not None:                  # complete_mask (txt2img.py:160-170)
         if isinstance(text_mask, (int, float)):
             tm = tm * text_mask
         else:
             for i, v in enumerate(text_mask):
                 tm[i] = v
+    boxes, masks, text_masks = boxes_h.to(dev), masks_h.to(dev), (text_masks_h * tm).to(dev)
+    text_emb = torch.zeros(max_objs, W, device=dev)
+    if n_ph:
+        text_emb[torch.as_tensor(live, device=dev)] = pooled[2:2 + n_ph]
+    rel = torch.zeros(max_relas, W, device=dev)
+    if relations:
+        rel[:len(relations)] = pooled[2 + n_ph:]
     rep = lambda t: t.unsqueeze(0).repeat(batch, *([1] * t.dim()))  # noqa: E731
     return dict(context=rep(hid[0]), uc=rep(hid[1]), relations=rep(rel),
-                boxes=rep(boxes), masks=rep(masks), text_masks=rep(text_masks * tm), image_masks=rep(torch.zeros(max_objs, device=dev)),
+                boxes=rep(boxes), masks=rep(masks), text_masks=rep(text_masks), image_masks=rep(torch.zeros(max_objs, device=dev)),
                 text_embeddings=rep(text_emb), image_embeddings=rep(torch.zeros(max_objs, W, device=dev)))
