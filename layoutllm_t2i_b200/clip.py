@@ -84,7 +84,9 @@ class ClipTextEncoder:
         """ids [B, L] (L <= 77) -> (last_hidden_state [B, L, W] or None, pooler_output [B, W][, text_embeds [B, P]])."""
         if ids.dim() != 2 or ids.shape[1] < 1 or ids.shape[1] > self.cfg["max_position_embeddings"]:
             raise L.LttError(f"ClipTextEncoder: ids must be [B, L <= {self.cfg['max_position_embeddings']}], got {tuple(ids.shape)}")
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.cfg["vocab_size"]):
+        # host ids (what a tokenizer returns) are range-checked here; ids already on the device are clamped by the kernel
+        # instead -- checking them would cost two reductions and a host synchronisation per call
+        if not ids.is_cuda and ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.cfg["vocab_size"]):
             raise L.LttError("ClipTextEncoder: token id outside the vocabulary")
         if not self._finalized:
             self.finalize()
