@@ -1256,7 +1256,6 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
     float* __restrict__ scratch, int* __restrict__ tickets, __half* __restrict__ feats2, __half* __restrict__ ln2out) {
     pdl_launch_dependents();
-    pdl_wait();
     extern __shared__ float ra_smem[];
     float* xs = ra_smem;                 // [C] feature row, later f2
     float* ls = xs + C;                  // [max(C, 2048)] LN1 output (fp16-rounded), later partial sums of the out phase
@@ -1277,6 +1276,40 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
         for (int k = 0; k < RA_THREADS / 32; ++k) t += red[k];
         return t;
     };
+    // ---- step-invariant operands first: the folded relation keys / values of this (sample, head) and the norm parameters do
+    // not depend on the predecessor grid, so their L2 round trips overlap its tail and the LayerNorm below instead of sitting
+    // on the kernel's dependent chain (load row -> LN1 -> logits -> softmax -> p . Bm -> ticket -> LN2)
+    const __half* Ah = A + ((size_t)g * HJ + (size_t)h * nrel) * C;
+    const __half* Bh = Bm + ((size_t)g * HJ + (size_t)h * nrel) * C;
+    const int P = max(1, RA_THREADS / nvec);
+    uint4 ua[5], ub[8];
+    if (warp < nrel) {                   // logits: warp j handles relation j (nrel <= 8 warps; a second round reloads below)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int cv = lane + 32 * i;
+            if (cv < nvec) ua[i] = *reinterpret_cast<const uint4*>(Ah + (size_t)warp * C + cv * 8);
+        }
+    }
+    {
+        const int cv = tid % nvec, part = tid / nvec;
+        if (part < P) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = part + i * P;
+                if (j < nrel) ub[i] = *reinterpret_cast<const uint4*>(Bh + (size_t)j * C + cv * 8);
+            }
+        }
+    }
+    float g1r[5], b1r[5];                // LN1 parameters of this thread's channels (C <= 5 * RA_THREADS)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int c = tid + i * RA_THREADS;
+        if (c < C) {
+            g1r[i] = g1[c];
+            b1r[i] = b1[c];
+        }
+    }
+    pdl_wait();
     // ---- load + LN1
     float s = 0.f;
     for (int c = tid; c < C; c += RA_THREADS) {
@@ -1291,16 +1324,19 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
         ss += dlt * dlt;
     }
     const float rstd = rsqrtf(block_sum(ss) / C + eps);
-    for (int c = tid; c < C; c += RA_THREADS) ls[c] = r16f((xs[c] - mean) * rstd * g1[c] + b1[c]);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int c = tid + i * RA_THREADS;
+        if (c < C) ls[c] = r16f((xs[c] - mean) * rstd * g1r[i] + b1r[i]);
+    }
     __syncthreads();
     // ---- logits of this head: one warp per relation, lanes over C in 16-byte vectors (<= 5 loads in flight per lane)
-    const __half* Ah = A + ((size_t)g * HJ + (size_t)h * nrel) * C;
     for (int j = warp; j < nrel; j += RA_THREADS / 32) {
         uint4 u[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const int cv = lane + 32 * i;
-            if (cv < nvec) u[i] = *reinterpret_cast<const uint4*>(Ah + (size_t)j * C + cv * 8);
+            if (cv < nvec) u[i] = j == warp ? ua[i] : *reinterpret_cast<const uint4*>(Ah + (size_t)j * C + cv * 8);
         }
         float acc = 0.f;
 #pragma unroll
@@ -1333,8 +1369,7 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
     }
     __syncthreads();
     // ---- this head's share of p . Bm: relations split over P thread groups, all loads of a thread in flight together
-    const __half* Bh = Bm + ((size_t)g * HJ + (size_t)h * nrel) * C;
-    const int P = max(1, RA_THREADS / nvec);
+    // (the first round was fetched ahead of the wait)
     {
         const int cv = tid % nvec, part = tid / nvec;
         if (part < P) {
@@ -1344,7 +1379,7 @@ __global__ void __launch_bounds__(RA_THREADS) rela_attn_fused_kernel(
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int j = jb + i * P;
-                    if (j < nrel) u[i] = *reinterpret_cast<const uint4*>(Bh + (size_t)j * C + cv * 8);
+                    if (j < nrel) u[i] = jb == part ? ub[i] : *reinterpret_cast<const uint4*>(Bh + (size_t)j * C + cv * 8);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
